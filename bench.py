@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the lift-splat hot path (BASELINE.json: "BEV-pool frames/s + % HBM peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|bf16] [--impl ours|reference]
+
+Workload at N=1 = BASELINE.json configs[1]: lift-splat forward+backward, batch 16,
+4 cameras, 48 depth bins, 64-channel features, 200x200 BEV at 0.1 m, synthetic
+encoder outputs / intrinsics / extrinsics (jittered CARLA rig), fp32 (or bf16).
+A "step" is one pass of the whole path over one batch: camera transform, index,
+counting sort, softmax, NHWC staging, splat, and the full backward.
+
+Under torchrun (N>1) every rank runs the same per-GPU batch on its own GPU (the path is
+per-sample: weak scaling, no data-path collective); the timed region is bracketed by a
+barrier + synchronize and the MAX over ranks is reported.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitions of
+value / e2e / roofline / cpu_baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from e2e_parking_carla_b200.synthetic import (LiftSplatShape, make_encoder_outputs, make_rig,  # noqa: E402
+                                              make_upstream_grads)
+
+METRIC = "lift_splat_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload(args) -> LiftSplatShape:
+    if args.workload == "cfg2":
+        return LiftSplatShape(batch=args.batch or 16, channels=64)
+    if args.workload == "stress":
+        return LiftSplatShape.stress(batch=args.batch or 32)
+    raise SystemExit("unknown workload")
+
+
+def algorithmic_bytes(shape: LiftSplatShape, s_in: int):
+    """per-sample algorithmic HBM bytes (softmax upstream + prob write)."""
+    n, hw = shape.cams, shape.fh * shape.fw
+    c, d = shape.channels, shape.depth_bins
+    x = int(round((shape.bev_x_bound[1] - shape.bev_x_bound[0]) / shape.bev_x_bound[2]))
+    y = int(round((shape.bev_y_bound[1] - shape.bev_y_bound[0]) / shape.bev_y_bound[2]))
+    io = n * hw * (c + d) * s_in
+    bev = c * x * y * 4
+    return {"fwd": io + bev, "bwd": bev + 2 * io,
+            # per kernel (DESIGN.md "Kernels"): what each one must move at minimum
+            "splat_fwd": io + bev, "bwd_transpose": bev, "bwd_gather": 2 * io}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle/torch_port.py) on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(shape: LiftSplatShape, sample_batch: int, steps: int, warmup: int, dtype):
+    from oracle import lift_splat_oracle as lo
+    from oracle import torch_port as tp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sub = LiftSplatShape(**{**shape.__dict__, "batch": sample_batch})
+    intr, extr = make_rig(sample_batch, sub.cams, jitter=True, seed=1)
+    feat, logits = make_encoder_outputs(sub, seed=0)
+    gb, gp = make_upstream_grads(sub, seed=0)
+    res, start, dim = lo.bev_grid_params(sub.bev_x_bound, sub.bev_y_bound, sub.bev_z_bound)
+    fr = torch.from_numpy(lo.create_frustum(sub.d_bound, sub.final_dim, sub.bev_down_sample))
+    a = (feat, logits, intr, extr, fr, torch.from_numpy(start), torch.from_numpy(res), torch.from_numpy(dim), gb, gp)
+    for _ in range(warmup):
+        tp.fwd_bwd_step(*a)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tp.fwd_bwd_step(*a)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d step(s) of fwd+bwd on a %d-sample slice of the workload, torch %s CPU ops (the "
+                      "reference's own aten op chain, oracle/torch_port.py), %d threads"
+                      % (steps, sample_batch, torch.__version__, threads),
+            "ms_per_step": dt * 1e3}
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+class Stepper:
+    """Pre-allocated device buffers + direct C-ABI calls (what LiftSplatFunction does,
+    minus the autograd bookkeeping) so the timed region is the library, not Python."""
+
+    def __init__(self, shape: LiftSplatShape, dtype, device, seed=0):
+        from e2e_parking_carla_b200 import _lib, lift_splat as ls
+        from e2e_parking_carla_b200.bev_model import BevModel
+        from e2e_parking_carla_b200.synthetic import make_cfg
+        self.ls, self.lib, self.shape, self.dtype, self.device = ls, _lib.load(), shape, dtype, device
+        model = BevModel(make_cfg(shape), cam_encoder=torch.nn.Identity())
+        self.grid = model._grid
+        self.frustum = model.frustum.data.to(device)
+        self.s = ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw, shape.channels,
+                               self.grid)
+        self.code = ls.LS_F32 if dtype == torch.float32 else ls.LS_BF16
+        intr, extr = make_rig(shape.batch, shape.cams, jitter=True, seed=1 + seed)
+        feat, logits = make_encoder_outputs(shape, seed=seed)
+        gb, gp = make_upstream_grads(shape, seed=seed)
+        self.host = {"feat": feat.to(dtype).pin_memory(), "logits": logits.to(dtype).pin_memory(),
+                     "intr": intr.pin_memory(), "extr": extr.pin_memory(), "gbev": gb.pin_memory(),
+                     "gprob": gp.to(dtype).pin_memory()}
+        self.dev = {k: v.to(device) for k, v in self.host.items()}
+        B, Cc, X, Y = shape.batch, shape.channels, self.grid.dim[0], self.grid.dim[1]
+        self.M = torch.empty(B, shape.cams, 3, 3, device=device)
+        self.t = torch.empty(B, shape.cams, 3, device=device)
+        self.bev = torch.empty(B, Cc, X, Y, device=device)
+        self.prob = torch.empty_like(self.dev["logits"])
+        self.gfeat = torch.empty_like(self.dev["feat"])
+        self.glogits = torch.empty_like(self.dev["logits"])
+        self.ws = torch.empty(ls.workspace_bytes(self.s, self.code, True), dtype=torch.uint8, device=device)
+        self.st = ls._bev_strides(self.bev)
+        self.gst = ls._bev_strides(self.dev["gbev"])
+        self.out_host = {"bev": torch.empty(self.bev.shape, dtype=self.bev.dtype).pin_memory(),
+                         "prob": torch.empty(self.prob.shape, dtype=self.prob.dtype).pin_memory(),
+                         "gfeat": torch.empty(self.gfeat.shape, dtype=self.gfeat.dtype).pin_memory(),
+                         "glogits": torch.empty(self.glogits.shape, dtype=self.glogits.dtype).pin_memory()}
+
+    def _p(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def step(self):
+        """One device-resident pass: 3 ABI calls (transform, forward, backward)."""
+        ls, lib, d = self.ls, self.lib, self.dev
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ls.check(lib.ls_camera_transform(self._p(d["intr"]), self._p(d["extr"]), self.shape.batch * self.shape.cams,
+                                         self._p(self.M), self._p(self.t), stream), "ls_camera_transform")
+        ls.check(lib.ls_forward(self._p(d["feat"]), self._p(d["logits"]), self.code, self._p(self.M),
+                                self._p(self.t), self._p(self.frustum), C.byref(self.s), self._p(self.ws),
+                                self.ws.numel(), self._p(self.bev), C.byref(self.st), self._p(self.prob), stream),
+                 "ls_forward")
+        ls.check(lib.ls_backward(self._p(d["gbev"]), C.byref(self.gst), self._p(d["gprob"]), self._p(self.prob),
+                                 self.code, C.byref(self.s), self._p(self.ws), self.ws.numel(), self._p(self.gfeat),
+                                 self._p(self.glogits), stream), "ls_backward")
+
+    def step_e2e(self):
+        """Host buffers in, host buffers out: every input (including the upstream
+        gradients) is copied from pinned host memory and every output is copied back."""
+        for k, v in self.host.items():
+            self.dev[k].copy_(v, non_blocking=True)
+        self.step()
+        self.out_host["bev"].copy_(self.bev, non_blocking=True)
+        self.out_host["prob"].copy_(self.prob, non_blocking=True)
+        self.out_host["gfeat"].copy_(self.gfeat, non_blocking=True)
+        self.out_host["glogits"].copy_(self.glogits, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def e2e_bytes(self):
+        h2d = sum(v.numel() * v.element_size() for v in self.host.values())
+        d2h = sum(v.numel() * v.element_size() for v in self.out_host.values())
+        return h2d, d2h
+
+    def stage_times(self, steps: int):
+        """Per-stage CUDA-event timing of the same pipeline, stage by stage through the
+        ABI's individual entry points (same kernels, same order as ls_forward/ls_backward)."""
+        ls, lib, d, s = self.ls, self.lib, self.dev, self.s
+        sh = self.shape
+        tiles, cells = ls.grid_cells(s)
+        dev = self.device
+        npts = sh.cams * sh.depth_bins * sh.fh * sh.fw
+        rank = torch.empty(sh.batch, npts, dtype=torch.int32, device=dev)
+        counts = torch.zeros(sh.batch, cells, dtype=torch.int32, device=dev)
+        seg = torch.empty(sh.batch, cells + 1, dtype=torch.int32, device=dev)
+        order = torch.empty_like(rank)
+        otmp = torch.empty_like(rank)
+        featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, sh.channels, dtype=self.dtype, device=dev)
+        gT = torch.empty(sh.batch, cells, sh.channels, device=dev)
+        gprob = torch.empty(sh.batch * npts, device=dev)
+        gfeatT = torch.empty_like(featT)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        bn, hw = sh.batch * sh.cams, sh.fh * sh.fw
+        P = self._p
+        stages = [
+            ("camera_transform", lambda: lib.ls_camera_transform(P(d["intr"]), P(d["extr"]), bn, P(self.M), P(self.t), stream)),
+            ("index+hist", lambda: (counts.zero_(), lib.ls_index(P(self.M), P(self.t), P(self.frustum), C.byref(s), P(rank), P(counts), stream))[1]),
+            ("sort(scan+place)", lambda: lib.ls_sort(P(rank), C.byref(s), P(counts), 1, P(seg), P(order), stream)),
+            ("softmax", lambda: lib.ls_softmax(P(d["logits"]), self.code, C.byref(s), P(self.prob), stream)),
+            ("nchw_to_nhwc", lambda: lib.ls_nchw_to_nhwc(P(d["feat"]), self.code, bn, sh.channels, hw, P(featT), stream)),
+            ("splat_fwd", lambda: lib.ls_splat_fwd(P(featT), P(self.prob), self.code, P(order), P(seg), P(otmp), C.byref(s), P(self.bev), C.byref(self.st), stream)),
+            ("splat_bwd(transpose+gather)", lambda: lib.ls_splat_bwd(P(d["gbev"]), C.byref(self.gst), P(featT), P(self.prob), self.code, P(rank), C.byref(s), P(gT), P(gprob), P(gfeatT), stream)),
+            ("nhwc_to_nchw", lambda: lib.ls_nhwc_to_nchw(P(gfeatT), self.code, bn, sh.channels, hw, P(self.gfeat), stream)),
+            ("softmax_bwd", lambda: lib.ls_softmax_bwd(P(self.prob), P(gprob), P(d["gprob"]), self.code, C.byref(s), P(self.glogits), stream)),
+        ]
+        acc = {n: 0.0 for n, _ in stages}
+        for it in range(steps + 2):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
+            evs[0].record()
+            for i, (n, fn) in enumerate(stages):
+                ls.check(fn(), n)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                for i, (n, _) in enumerate(stages):
+                    acc[n] += evs[i].elapsed_time(evs[i + 1])
+        return {n: v / steps for n, v in acc.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "stress"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="samples in the bounded CPU-baseline slice")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    shape = workload(args)
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    s_in = 4 if args.dtype == "fp32" else 2
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl_name = ("lift-splat fwd+bwd, batch %d/GPU, %d cams, D=%d, C=%d, %dx%d BEV (BASELINE.json configs[%d])"
+               % (shape.batch, shape.cams, shape.depth_bins, shape.channels,
+                  int(round((shape.bev_x_bound[1] - shape.bev_x_bound[0]) / shape.bev_x_bound[2])),
+                  int(round((shape.bev_y_bound[1] - shape.bev_y_bound[0]) / shape.bev_y_bound[2])),
+                  1 if args.workload == "cfg2" else 3))
+    config = {"workload": wl_name, "per_gpu_batch": shape.batch, "global_batch": shape.batch * world,
+              "rig": "CARLA 4-camera rig with per-sample jitter (SURVEY.md 8d rig B)",
+              "parallelism": "dp%d (per-sample path, no collective)" % world,
+              "l2": "no flush: one step streams ~0.6 GB (BEV + grad BEV + cell-major gradient) through the 126 MB L2"}
+
+    # ---------------- reference arm ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_run(shape, args.cpu_batch, max(1, args.steps), max(1, min(args.warmup, 2)), dtype)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ----------------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=device)
+    from e2e_parking_carla_b200 import _lib
+    lib = _lib.load()
+    st = Stepper(shape, dtype, device, seed=rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        st.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.ls_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        st.step()
+    e1.record()
+    barrier()
+    launches = int(lib.ls_launch_count() - l0)
+    ms = e0.elapsed_time(e1)
+    # end to end: host buffers in/out, same number of steps
+    for _ in range(2):
+        st.step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    f0.record()
+    for _ in range(e2e_steps):
+        st.step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    ms_step = ms / args.steps
+    value = shape.batch * world / (ms_step * 1e-3)
+    e2e_value = shape.batch * world / (ms_e2e / e2e_steps * 1e-3)
+    h2d, d2h = st.e2e_bytes()
+
+    if rank == 0:
+        stages = st.stage_times(min(args.steps, 20))
+        peak, peak_src = measured_peak()
+        ab = algorithmic_bytes(shape, s_in)
+        # dominant kernel of the step and its own algorithmic traffic
+        cand = {"splat_fwd": stages["splat_fwd"], "splat_bwd(transpose+gather)": stages["splat_bwd(transpose+gather)"]}
+        dom = max(cand, key=cand.get)
+        dom_bytes = (ab["splat_fwd"] if dom == "splat_fwd" else ab["bwd_transpose"] + ab["bwd_gather"]) * shape.batch
+        achieved = dom_bytes / (cand[dom] * 1e-3) / 1e9
+        step_bytes = (ab["fwd"] + ab["bwd"]) * shape.batch
+        step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+                "config": config,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / e2e_steps,
+                        "what": "pinned host buffers -> device -> ls_camera_transform/ls_forward/ls_backward -> "
+                                "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": cand[dom]},
+                "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak,
+                                  "unit": "GB/s", "frac": step_gbs / peak},
+                "stage_ms": stages, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_run(shape, args.cpu_batch, 3, 1, dtype)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,12 @@
+"""B200-native lift-splat (camera -> BEV) for E2E Parking.
+
+Drop-in for ``model/bev_model.py`` of qintonguav/e2e-parking-carla: ``BevModel`` keeps
+the reference's constructor, parameters and ``forward/calc_bev_feature`` contract and
+runs the projection in hand-written sm_100a CUDA kernels (``libls_b200.so``, C ABI in
+``include/ls_b200.h``).  The package directory is spelled with underscores because
+Python cannot import a hyphenated name.
+"""
+from .bev_model import BevModel, calculate_birds_eye_view_parameters  # noqa: F401
+from .lift_splat import GridSpec, LiftSplatFunction, lift_splat  # noqa: F401
+
+__all__ = ["BevModel", "calculate_birds_eye_view_parameters", "GridSpec", "LiftSplatFunction", "lift_splat"]

@@ -1,0 +1,152 @@
+"""Drop-in ``BevModel`` (reference: model/bev_model.py) on the B200 lift-splat kernels.
+
+Same constructor argument (a ``Configuration``-like object), same attributes and
+``state_dict`` entries (``bev_res``, ``bev_start_pos``, ``bev_dim`` (int64!),
+``frustum``, ``cam_encoder.*`` - SURVEY.md 8b), same method names, same returns:
+``forward(images, intrinsics, extrinsics) -> (bev f32[B,C,X,Y], pred_depth[B*N,D,h,w])``.
+``ParkingModel.encoder`` (model/parking_model.py:55) and the seg/depth/control losses
+use it unchanged.
+
+What differs is what happens inside ``calc_bev_feature``: the B x N x D x h x w x C
+frustum tensor, the per-sample python loop, the boolean-index host syncs, argsort and
+the cumsum trick are replaced by one call into ``libls_b200.so``
+(``LiftSplatFunction``).  The camera encoder stays stock PyTorch and is injected.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import lift_splat as ls
+
+
+def calculate_birds_eye_view_parameters(x_bounds, y_bounds, z_bounds):
+    """Grid resolution / first-cell centre / size (reference: tool/geometry.py:40-59).
+
+    Returns float32 ``bev_resolution[3]``, float32 ``bev_start_position[3]`` and int64
+    ``bev_dimension[3]``.  Values are produced exactly like the reference's (python
+    float arithmetic, then torch's casts) so that checkpoints and voxel indices agree.
+    """
+    bounds = (x_bounds, y_bounds, z_bounds)
+    step = [float(b[2]) for b in bounds]
+    first = [float(b[0]) + float(b[2]) / 2.0 for b in bounds]
+    count = [(float(b[1]) - float(b[0])) / float(b[2]) for b in bounds]
+    return (torch.tensor(step), torch.tensor(first), torch.tensor(count, dtype=torch.long))
+
+
+class BevModel(nn.Module):
+    """Camera -> BEV lift-splat stage.
+
+    Parameters
+    ----------
+    cfg : object with ``bev_x_bound, bev_y_bound, bev_z_bound, d_bound, final_dim,
+        bev_down_sample, use_depth_distribution`` (tool/config.py:29-37).
+    cam_encoder : the image encoder returning ``(feat[B*N,C,h,w], depth_logits[B*N,D,h,w])``.
+        The reference constructs ``CamEncoder(cfg, D)`` itself (model/bev_model.py:26);
+        when ``None`` we do the same if the reference's ``model.cam_encoder`` is importable.
+    geometry : ``"native"`` (default) computes E^-1, K^-1 in ``ls_camera_transform``
+        (no host sync, graph-capturable); ``"torch"`` calls ``torch.inverse`` exactly as
+        model/bev_model.py:46,53 does, for bit-parity with the reference on the same device.
+    """
+
+    def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native"):
+        super().__init__()
+        self.cfg = cfg
+        if geometry not in ("native", "torch"):
+            raise ValueError("geometry must be 'native' or 'torch'")
+        self.geometry_mode = geometry
+        if not getattr(cfg, "use_depth_distribution", 1):
+            # the reference crashes in this mode too (depth is None at bev_model.py:64)
+            raise ValueError("use_depth_distribution=0 is not supported (nor by the reference)")
+
+        bev_res, bev_start_pos, bev_dim = calculate_birds_eye_view_parameters(
+            cfg.bev_x_bound, cfg.bev_y_bound, cfg.bev_z_bound)
+        self.bev_res = nn.Parameter(bev_res, requires_grad=False)
+        self.bev_start_pos = nn.Parameter(bev_start_pos, requires_grad=False)
+        self.bev_dim = nn.Parameter(bev_dim, requires_grad=False)
+        # host copy taken once: sizes never come from device tensors at call time
+        self._grid = ls.GridSpec(tuple(float(v) for v in bev_start_pos.tolist()),
+                                 tuple(float(v) for v in bev_res.tolist()),
+                                 tuple(int(v) for v in bev_dim.tolist()))
+        if self._grid.dim[2] != 1:
+            raise ValueError("bev_z_bound must give a single Z cell (reference squeezes Z, bev_model.py:104)")
+
+        self.down_sample = cfg.bev_down_sample
+        self.frustum = self.create_frustum()
+        self.depth_channel, _, _, _ = self.frustum.shape
+        if cam_encoder is None:
+            try:
+                from model.cam_encoder import CamEncoder  # running inside the reference tree
+            except Exception as e:  # pragma: no cover - depends on the host environment
+                raise RuntimeError("pass cam_encoder=...: the reference CamEncoder "
+                                   "(efficientnet_pytorch) is not importable here: %s" % e)
+            cam_encoder = CamEncoder(cfg, self.depth_channel)
+        self.cam_encoder = cam_encoder
+
+    # ---- a3: model/bev_model.py:28-43 -------------------------------------------------
+    def create_frustum(self):
+        """(u, v, d) of every frustum point, f32[D, h, w, 3], as a frozen Parameter (it is
+        a state_dict entry; the kernels read it as data)."""
+        img_h, img_w = self.cfg.final_dim
+        fh, fw = img_h // self.down_sample, img_w // self.down_sample
+        depth = torch.arange(*self.cfg.d_bound, dtype=torch.float)
+        cols = torch.linspace(0, img_w - 1, fw, dtype=torch.float)
+        rows = torch.linspace(0, img_h - 1, fh, dtype=torch.float)
+        n_d = depth.numel()
+        grid = torch.empty(n_d, fh, fw, 3, dtype=torch.float)
+        grid[..., 0] = cols.view(1, 1, fw)
+        grid[..., 1] = rows.view(1, fh, 1)
+        grid[..., 2] = depth.view(n_d, 1, 1)
+        return nn.Parameter(grid, requires_grad=False)
+
+    # ---- a4: model/bev_model.py:45-57 -------------------------------------------------
+    def camera_transform(self, intrinsics, extrinsics):
+        """(M [B,N,3,3], t [B,N,3]) with M = R . K^-1 from E^-1 = [R | t]."""
+        if self.geometry_mode == "torch":
+            inv = torch.inverse(extrinsics)
+            rot, trans = inv[..., :3, :3], inv[..., :3, 3]
+            return rot.matmul(torch.inverse(intrinsics)).contiguous(), trans.contiguous()
+        return ls.camera_transform(intrinsics, extrinsics)
+
+    def _shape(self, batch, cams, channels):
+        d, fh, fw, _ = self.frustum.shape
+        return ls.make_shape(batch, cams, d, fh, fw, channels, self._grid)
+
+    def get_geometry(self, intrinsics, extrinsics):
+        """Ego-frame coordinates of every frustum point, f32[B,N,D,h,w,3].  Kept for API
+        compatibility; ``calc_bev_feature`` never materialises this tensor."""
+        M, t = self.camera_transform(intrinsics, extrinsics)
+        b, n = M.shape[:2]
+        return ls.geometry(M, t, self.frustum, self._shape(b, n, 2))
+
+    # ---- a5: model/bev_model.py:59-72 -------------------------------------------------
+    def encoder_forward(self, images):
+        """Reference-shaped lift: returns the (B,N,D,h,w,C) outer-product *view* and the
+        depth probabilities.  Compatibility only (it materialises the big tensor with
+        torch ops); the fused path is ``calc_bev_feature``."""
+        b, n, c, h, w = images.shape
+        feat, depth = self.cam_encoder(images.view(b * n, c, h, w))
+        depth_prob = depth.softmax(dim=1)
+        lifted = depth_prob.unsqueeze(1) * feat.unsqueeze(2)
+        lifted = lifted.view(b, n, *lifted.shape[1:]).permute(0, 1, 3, 4, 5, 2)
+        return lifted, depth_prob
+
+    # ---- a6: model/bev_model.py:74-107 ------------------------------------------------
+    def proj_bev_feature(self, geom, image_feature):
+        raise NotImplementedError(
+            "proj_bev_feature(geom, x) consumes the materialised frustum tensor; use "
+            "calc_bev_feature / forward, which fuse lift and splat")
+
+    # ---- a8: model/bev_model.py:109-117 -----------------------------------------------
+    def calc_bev_feature(self, images, intrinsics, extrinsics):
+        b, n, c, h, w = images.shape
+        feat, depth_logits = self.cam_encoder(images.view(b * n, c, h, w))
+        M, t = self.camera_transform(intrinsics, extrinsics)
+        bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid)
+        return bev_feature, pred_depth
+
+    def forward(self, images, intrinsics, extrinsics):
+        bev_feature, pred_depth = self.calc_bev_feature(images, intrinsics, extrinsics)
+        return bev_feature.squeeze(1), pred_depth

@@ -1,0 +1,237 @@
+"""Host side of the lift-splat hot path: thin wrappers that hand torch device memory
+and the current CUDA stream to the C ABI (``include/ls_b200.h``), plus the
+``torch.autograd.Function`` that ``BevModel.calc_bev_feature`` routes through.
+
+PyTorch is plumbing here (allocator, streams, autograd graph); every per-point
+operation runs in ``libls_b200.so``.  CUDA tensors only - there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LS_BF16, LS_F32, LsBevStrides, LsShape, check
+
+
+# --------------------------------------------------------------------------------------
+# problem description
+# --------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class GridSpec:
+    """bev_start_pos / bev_res / bev_dim of a BevModel as host scalars (read once at
+    construction, so no call ever syncs on the on-device nn.Parameters the way
+    model/bev_model.py:76,101 does)."""
+    start: Tuple[float, float, float]
+    res: Tuple[float, float, float]
+    dim: Tuple[int, int, int]
+
+
+def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec) -> LsShape:
+    s = LsShape()
+    s.B, s.N, s.D, s.fh, s.fw, s.C = B, N, D, fh, fw, Cc
+    s.X, s.Y, s.Z = grid.dim
+    for i in range(3):
+        s.start[i] = grid.start[i]
+        s.res[i] = grid.res[i]
+    return s
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return LS_F32
+    if t.dtype == torch.bfloat16:
+        return LS_BF16
+    raise TypeError("lift-splat supports float32 and bfloat16, got %s" % t.dtype)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("lift-splat kernels need CUDA tensors (no CPU fallback); got %s" % t.device)
+
+
+def _bev_strides(t: torch.Tensor) -> LsBevStrides:
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise ValueError("BEV tensor must be [B,C,X,Y] with unit Y stride")
+    return LsBevStrides(t.stride(0), t.stride(1), t.stride(2))
+
+
+def grid_cells(shape: LsShape) -> Tuple[int, int]:
+    tiles, cells = C.c_int32(), C.c_int32()
+    check(_lib.load().ls_grid_cells(C.byref(shape), C.byref(tiles), C.byref(cells)), "ls_grid_cells")
+    return tiles.value, cells.value
+
+
+# --------------------------------------------------------------------------------------
+# one wrapper per ABI entry point (used by BevModel, the tests and bench.py)
+# --------------------------------------------------------------------------------------
+def camera_transform(intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(M f32[B,N,3,3], t f32[B,N,3]) - model/bev_model.py:46-47,53."""
+    _need_cuda(intrinsics, extrinsics)
+    b, n = extrinsics.shape[:2]
+    intr = intrinsics.detach().to(torch.float32).contiguous()
+    extr = extrinsics.detach().to(torch.float32).contiguous()
+    M = torch.empty(b, n, 3, 3, dtype=torch.float32, device=extr.device)
+    t = torch.empty(b, n, 3, dtype=torch.float32, device=extr.device)
+    check(_lib.load().ls_camera_transform(_ptr(intr), _ptr(extr), b * n, _ptr(M), _ptr(t), _stream(extr)),
+          "ls_camera_transform")
+    return M, t
+
+
+def geometry(M, t, frustum, shape: LsShape) -> torch.Tensor:
+    """geom f32[B,N,D,fh,fw,3] - model/bev_model.py:49-55 (compat / tests only)."""
+    _need_cuda(M, t, frustum)
+    geom = torch.empty(shape.B, shape.N, shape.D, shape.fh, shape.fw, 3, dtype=torch.float32, device=M.device)
+    check(_lib.load().ls_geometry(_ptr(M.contiguous()), _ptr(t.contiguous()), _ptr(frustum.contiguous()),
+                                  C.byref(shape), _ptr(geom), _stream(M)), "ls_geometry")
+    return geom
+
+
+def index(M, t, frustum, shape: LsShape, with_hist: bool = False):
+    """rank i32[B,Npts] (-1 dropped) and optionally the per-cell histogram."""
+    _need_cuda(M, t, frustum)
+    npts = shape.N * shape.D * shape.fh * shape.fw
+    rank = torch.empty(shape.B, npts, dtype=torch.int32, device=M.device)
+    counts = None
+    if with_hist:
+        counts = torch.zeros(shape.B, grid_cells(shape)[1], dtype=torch.int32, device=M.device)
+    check(_lib.load().ls_index(_ptr(M.contiguous()), _ptr(t.contiguous()), _ptr(frustum.contiguous()),
+                               C.byref(shape), _ptr(rank), _ptr(counts), _stream(M)), "ls_index")
+    return (rank, counts) if with_hist else rank
+
+
+def export_indices(M, t, frustum, shape: LsShape):
+    """(vox i64[B,Npts,3], keep bool[B,Npts], rank i64[B,Npts]) in the reference's
+    convention (model/bev_model.py:85-95) for the bit-exact tests."""
+    _need_cuda(M, t, frustum)
+    npts = shape.N * shape.D * shape.fh * shape.fw
+    dev = M.device
+    vox = torch.empty(shape.B, npts, 3, dtype=torch.int64, device=dev)
+    keep = torch.empty(shape.B, npts, dtype=torch.uint8, device=dev)
+    rank = torch.empty(shape.B, npts, dtype=torch.int64, device=dev)
+    check(_lib.load().ls_export_indices(_ptr(M.contiguous()), _ptr(t.contiguous()), _ptr(frustum.contiguous()),
+                                        C.byref(shape), _ptr(vox), _ptr(keep), _ptr(rank), _stream(M)),
+          "ls_export_indices")
+    return vox, keep.bool(), rank
+
+
+def sort(rank: torch.Tensor, shape: LsShape, counts: Optional[torch.Tensor] = None):
+    """(seg_start i32[B,cells+1], order i32[B,Npts]) - counting sort by cell."""
+    _need_cuda(rank)
+    cells = grid_cells(shape)[1]
+    have = counts is not None
+    if counts is None:
+        counts = torch.empty(shape.B, cells, dtype=torch.int32, device=rank.device)
+    seg = torch.empty(shape.B, cells + 1, dtype=torch.int32, device=rank.device)
+    order = torch.empty_like(rank)
+    check(_lib.load().ls_sort(_ptr(rank), C.byref(shape), _ptr(counts), int(have), _ptr(seg), _ptr(order),
+                              _stream(rank)), "ls_sort")
+    return seg, order
+
+
+def export_sorted_ranks(seg_start: torch.Tensor, shape: LsShape, b: int) -> torch.Tensor:
+    """``ranks[ranks.argsort()]`` of sample b (model/bev_model.py:97) rebuilt from the CSR."""
+    cells = grid_cells(shape)[1]
+    out = torch.empty(cells, 2, dtype=torch.int64, device=seg_start.device)
+    check(_lib.load().ls_export_cell_counts(_ptr(seg_start), C.byref(shape), b, _ptr(out), None,
+                                            _stream(seg_start)), "ls_export_cell_counts")
+    out = out[out[:, 1] > 0]
+    out = out[out[:, 0].argsort()]
+    return torch.repeat_interleave(out[:, 0], out[:, 1])
+
+
+def kept_counts(seg_start: torch.Tensor, shape: LsShape) -> torch.Tensor:
+    kept = torch.empty(shape.B, dtype=torch.int32, device=seg_start.device)
+    check(_lib.load().ls_export_cell_counts(_ptr(seg_start), C.byref(shape), 0, None, _ptr(kept),
+                                            _stream(seg_start)), "ls_export_cell_counts")
+    return kept
+
+
+def workspace_bytes(shape: LsShape, dtype_code: int, with_backward: bool) -> int:
+    n = _lib.load().ls_workspace_bytes(C.byref(shape), dtype_code, int(with_backward))
+    if n == 0:
+        raise ValueError("unsupported lift-splat shape (need Z == 1, even C <= 256)")
+    return n
+
+
+# --------------------------------------------------------------------------------------
+# autograd
+# --------------------------------------------------------------------------------------
+class LiftSplatFunction(torch.autograd.Function):
+    """(feat, depth_logits) -> (bev, depth_prob); replaces softmax + outer product +
+    voxelise + sort + VoxelsSumming + scatter (model/bev_model.py:64-105,
+    tool/geometry.py:285-317) with one forward and one backward pipeline call.
+    Gradients flow to ``feat`` and ``depth_logits`` only, as in the reference
+    (geometry is cut by ``.long()``, bev_model.py:86)."""
+
+    @staticmethod
+    def forward(ctx, feat, logits, M, t, frustum, shape: LsShape):
+        _need_cuda(feat, logits, M, t, frustum)
+        if feat.dtype != logits.dtype:
+            raise TypeError("feat and depth logits must share a dtype")
+        code = _dtype_code(feat)
+        feat_c = feat.contiguous()
+        logits_c = logits.contiguous()
+        need_bwd = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        ws = torch.empty(workspace_bytes(shape, code, need_bwd), dtype=torch.uint8, device=feat.device)
+        bev = torch.empty(shape.B, shape.C, shape.X, shape.Y, dtype=torch.float32, device=feat.device)
+        prob = torch.empty_like(logits_c)
+        st = _bev_strides(bev)
+        check(_lib.load().ls_forward(_ptr(feat_c), _ptr(logits_c), code, _ptr(M.contiguous()),
+                                     _ptr(t.contiguous()), _ptr(frustum.contiguous()), C.byref(shape), _ptr(ws),
+                                     ws.numel(), _ptr(bev), C.byref(st), _ptr(prob), _stream(feat)), "ls_forward")
+        ctx.shape, ctx.code, ctx.ws = shape, code, ws
+        ctx.feat_shape, ctx.logits_shape = feat.shape, logits.shape
+        ctx.save_for_backward(prob)
+        return bev, prob
+
+    @staticmethod
+    def backward(ctx, grad_bev, grad_prob):
+        (prob,) = ctx.saved_tensors
+        shape, code, ws = ctx.shape, ctx.code, ctx.ws
+        if ws is None or ws.numel() < workspace_bytes(shape, code, True):
+            raise RuntimeError("lift-splat forward ran without a backward workspace")
+        dev = prob.device
+        if grad_bev is None:
+            grad_bev = torch.zeros(shape.B, shape.C, shape.X, shape.Y, dtype=torch.float32, device=dev)
+        grad_bev = grad_bev.to(torch.float32)
+        if grad_bev.stride(3) != 1:
+            grad_bev = grad_bev.contiguous()
+        if grad_prob is not None:
+            grad_prob = grad_prob.to(prob.dtype).contiguous()
+        gfeat = torch.empty(ctx.feat_shape, dtype=prob.dtype, device=dev)
+        glogits = torch.empty(ctx.logits_shape, dtype=prob.dtype, device=dev)
+        st = _bev_strides(grad_bev)
+        check(_lib.load().ls_backward(_ptr(grad_bev), C.byref(st), _ptr(grad_prob), _ptr(prob), code,
+                                      C.byref(shape), _ptr(ws), ws.numel(), _ptr(gfeat), _ptr(glogits),
+                                      _stream(prob)), "ls_backward")
+        return gfeat, glogits, None, None, None, None
+
+
+def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, t: torch.Tensor,
+               frustum: torch.Tensor, grid: GridSpec) -> Tuple[torch.Tensor, torch.Tensor]:
+    """feat [B*N,C,fh,fw], depth_logits [B*N,D,fh,fw] (CamEncoder outputs,
+    model/cam_encoder.py:102-111), M [B,N,3,3], t [B,N,3], frustum [D,fh,fw,3] ->
+    (bev f32[B,C,X,Y], depth_prob [B*N,D,fh,fw])."""
+    B, N = M.shape[:2]
+    bn, Cc, fh, fw = feat.shape
+    D = depth_logits.shape[1]
+    if bn != B * N or depth_logits.shape[0] != bn or tuple(depth_logits.shape[2:]) != (fh, fw):
+        raise ValueError("feat %s / depth %s do not match %d x %d cameras" %
+                         (tuple(feat.shape), tuple(depth_logits.shape), B, N))
+    if tuple(frustum.shape) != (D, fh, fw, 3):
+        raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
+    shape = make_shape(B, N, D, fh, fw, Cc, grid)
+    return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape)

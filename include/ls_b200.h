@@ -1,0 +1,174 @@
+/*
+ * ls_b200.h - C ABI of the B200 (sm_100a) lift-splat library  (libls_b200.so)
+ *
+ * Drop-in boundary for the camera->BEV projection hot path of E2E Parking
+ * (reference: model/bev_model.py, tool/geometry.py:40-59,285-317).  The reference
+ * is pure Python/PyTorch and has no FFI of its own; these entry points are what a
+ * ctypes (or TORCH_LIBRARY) binding inside the reference's BevModel would bind -
+ * INTEGRATION.md shows that stub.  Plain pointers and sizes only: no torch types,
+ * no exceptions across the boundary; every function returns an LsStatus.
+ *
+ * All pointers are DEVICE pointers unless the name ends in _host.  Every call is
+ * asynchronous on `stream` (pass the caller's current stream), performs no host
+ * synchronisation and no allocation, so a whole forward/backward is CUDA-graph
+ * capturable.
+ *
+ * Point order inside a sample is the reference's: p = ((cam*D + d)*fh + row)*fw + col
+ * (model/bev_model.py:83).  rank = gx*(Y*Z) + gy*Z + gz (model/bev_model.py:94-95),
+ * -1 for a dropped point.
+ */
+#ifndef LS_B200_H_
+#define LS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ls_stream_t; /* cudaStream_t */
+
+typedef enum LsStatus {
+  LS_OK = 0,
+  LS_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, odd channel count ... */
+  LS_ERR_UNSUPPORTED = -2,  /* e.g. Z != 1 for the splat (reference squeezes Z, bev_model.py:104) */
+  LS_ERR_WORKSPACE = -3,    /* workspace too small */
+  LS_ERR_CUDA = -4          /* a CUDA runtime call / launch failed; see ls_last_cuda_error() */
+} LsStatus;
+
+typedef enum LsDtype { LS_F32 = 0, LS_BF16 = 1 } LsDtype;
+
+/* Sizes of one lift-splat problem.  start/res/dim are BevModel.bev_start_pos /
+ * bev_res / bev_dim (tool/geometry.py:40-59, model/bev_model.py:15-20). */
+typedef struct LsShape {
+  int32_t B, N;        /* batch, cameras                                       */
+  int32_t D, fh, fw;   /* depth bins, feature rows, feature cols (frustum dims) */
+  int32_t C;           /* feature channels (even)                               */
+  int32_t X, Y, Z;     /* bev_dim                                               */
+  float start[3];      /* bev_start_pos                                         */
+  float res[3];        /* bev_res                                               */
+} LsShape;
+
+/* Element strides of the BEV tensor [B, C, X, Y] (Y stride must be 1). */
+typedef struct LsBevStrides {
+  int64_t b, c, x;
+} LsBevStrides;
+
+const char* ls_version(void);
+const char* ls_strerror(int status);
+const char* ls_last_cuda_error(void);
+
+/* Internal BEV tiling: the grid is cut in tiles of tile_x * tile_y voxels; cells are
+ * numbered tile-major.  cells_padded = tiles * tile_x * tile_y  (>= X*Y). */
+int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded);
+
+/* a4 first half - model/bev_model.py:46-47,53:  E^-1 = inverse(extrinsics),
+ * M = E^-1[:3,:3] . inverse(intrinsics),  t = E^-1[:3,3].
+ * intrinsics f32[BN,3,3], extrinsics f32[BN,4,4] -> M f32[BN,3,3], t f32[BN,3].
+ * Inverse = float64 Gauss-Jordan with partial pivoting rounded once to float32
+ * (oracle/lift_splat_oracle.py:camera_transform is the bit-exact statement). */
+int ls_camera_transform(const float* intrinsics, const float* extrinsics, int32_t BN,
+                        float* M, float* t, ls_stream_t stream);
+
+/* a4 second half - model/bev_model.py:49-55 (BevModel.get_geometry):
+ * geom f32[B,N,D,fh,fw,3] = M.(u*d, v*d, d) + t, unfused float32, bit-exact with
+ * torch-CPU.  Only for API compatibility / tests: the hot path never stores geom. */
+int ls_geometry(const float* M, const float* t, const float* frustum, const LsShape* s,
+                float* geom, ls_stream_t stream);
+
+/* a4+a6.1-a6.3 fused - model/bev_model.py:49-55,85-95: per-point voxel index in
+ * registers, keep test, rank.  rank i32[B,Npts] (-1 = dropped), may be NULL.
+ * counts i32[B,cells_padded] (may be NULL): per-cell histogram, accumulated with
+ * integer atomics - must be zero on entry. */
+int ls_index(const float* M, const float* t, const float* frustum, const LsShape* s,
+             int32_t* rank, int32_t* counts, ls_stream_t stream);
+
+/* Debug/test export in the reference's own convention (model/bev_model.py:85-97):
+ * vox i64[B,Npts,3] = .long() of the voxel coordinate (INT64_MIN where x86 gives
+ * 'integer indefinite'), keep u8[B,Npts], rank i64[B,Npts] (-1 dropped). Any may be NULL. */
+int ls_export_indices(const float* M, const float* t, const float* frustum, const LsShape* s,
+                      int64_t* vox, uint8_t* keep, int64_t* rank, ls_stream_t stream);
+
+/* a6.3 - model/bev_model.py:96-97 (argsort + gathers) and the segment boundaries of
+ * tool/geometry.py:295-296, as a counting sort by cell.
+ * counts: the histogram from ls_index (have_hist=1) or scratch (have_hist=0, then it
+ * is zeroed and built here).  Outputs: seg_start i32[B,cells_padded+1] (CSR offsets
+ * into order), order i32[B,Npts] (point ids grouped by cell; entries past the kept
+ * count are unspecified).  The order of ids inside one cell is made canonical
+ * (ascending) by the consumer, ls_splat_fwd. */
+int ls_sort(const int32_t* rank, const LsShape* s, int32_t* counts, int have_hist,
+            int32_t* seg_start, int32_t* order, ls_stream_t stream);
+
+/* Test export: for sample b, out i64[cells_padded,2] = (row-major rank, number of kept
+ * points) of every cell, zeros for empty / padding cells; from it the reference's
+ * ``ranks[ranks.argsort()]`` (model/bev_model.py:97) is rebuilt by repeating each rank
+ * count times in ascending rank order.  kept i32[B] receives every sample's kept count.
+ * Either output may be NULL. */
+int ls_export_cell_counts(const int32_t* seg_start, const LsShape* s, int32_t b, int64_t* out,
+                          int32_t* kept, ls_stream_t stream);
+
+/* a5 - model/bev_model.py:64: prob = softmax(depth_logits, dim=1).
+ * logits/prob: [B*N, D, fh, fw] of `dtype`. */
+int ls_softmax(const void* logits, int dtype, const LsShape* s, void* prob, ls_stream_t stream);
+
+/* Layout helpers: [images, C, HW] <-> [images, HW, C]  (coalesced smem transposes). */
+int ls_nchw_to_nhwc(const void* src, int dtype, int32_t images, int32_t C, int32_t HW,
+                    void* dst, ls_stream_t stream);
+int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32_t HW,
+                    void* dst, ls_stream_t stream);
+
+/* a5(outer product)+a6.4-a6.5 fused - model/bev_model.py:66-72,99-105 and
+ * VoxelsSumming.forward (tool/geometry.py:289-305): deterministic segment sum of
+ * prob[p]*feat[pix(p),:] per cell, written (zeros included) to bev f32[B,C,X,Y].
+ * feat_nhwc: [B*N, fh, fw, C] of `dtype`; prob: [B*N, D, fh, fw] of `dtype`.
+ * order_tmp i32[B,Npts]: scratch used to canonicalise cells with >32 points. */
+int ls_splat_fwd(const void* feat_nhwc, const void* prob, int dtype, const int32_t* order,
+                 const int32_t* seg_start, int32_t* order_tmp, const LsShape* s, float* bev,
+                 const LsBevStrides* bev_strides, ls_stream_t stream);
+
+/* a7 + autograd of a5/a6 - VoxelsSumming.backward (tool/geometry.py:307-317) and the
+ * backward of the outer product: every kept point receives its cell's gradient;
+ *   grad_prob[p]      = sum_c feat[pix,c] * g[c, cell(p)]
+ *   grad_feat[pix, c] = sum_d prob[d,pix] * g[c, cell(d,pix)]      (pixel-stationary,
+ * no atomics, fixed order).  grad_bev f32 [B,C,X,Y] with strides; gT_ws
+ * f32[B,cells_padded,C] scratch; grad_prob f32[B*N,D,fh,fw] (always float);
+ * grad_feat_nhwc [B*N,fh,fw,C] of `dtype`. */
+int ls_splat_bwd(const float* grad_bev, const LsBevStrides* grad_strides, const void* feat_nhwc,
+                 const void* prob, int dtype, const int32_t* rank, const LsShape* s, float* gT_ws,
+                 float* grad_prob, void* grad_feat_nhwc, ls_stream_t stream);
+
+/* backward of a5's softmax (model/bev_model.py:64): grad_logits = prob * (g - sum_d prob*g),
+ * g = grad_prob (+ grad_prob_ext: the gradient arriving on the returned pred_depth,
+ * `dtype`, may be NULL). */
+int ls_softmax_bwd(const void* prob, const float* grad_prob, const void* grad_prob_ext, int dtype,
+                   const LsShape* s, void* grad_logits, ls_stream_t stream);
+
+/* ---- one-call pipelines (what BevModel.calc_bev_feature uses) -------------------
+ * Workspace: one device blob, >= ls_workspace_bytes(); it carries what backward needs
+ * (rank, NHWC features), so keep it alive and untouched between ls_forward and
+ * ls_backward of the same step. */
+size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward);
+
+/* feat [B*N,C,fh,fw], logits [B*N,D,fh,fw] of `dtype` (contiguous NCHW, as CamEncoder
+ * returns them, model/cam_encoder.py:102-111); M/t from ls_camera_transform or from the
+ * caller's own torch.inverse; frustum f32[D,fh,fw,3] (BevModel.frustum).
+ * Outputs: bev f32[B,C,X,Y] (strided), prob [B*N,D,fh,fw] of `dtype` (= pred_depth). */
+int ls_forward(const void* feat, const void* logits, int dtype, const float* M, const float* t,
+               const float* frustum, const LsShape* s, void* ws, size_t ws_bytes, float* bev,
+               const LsBevStrides* bev_strides, void* prob, ls_stream_t stream);
+
+/* grad_bev f32 (strided), grad_prob_ext (`dtype`, may be NULL), prob = forward's output.
+ * Outputs grad_feat [B*N,C,fh,fw], grad_logits [B*N,D,fh,fw] of `dtype`. */
+int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext,
+                const void* prob, int dtype, const LsShape* s, void* ws, size_t ws_bytes,
+                void* grad_feat, void* grad_logits, ls_stream_t stream);
+
+/* Number of kernel launches (and memsets) issued by this library since load; bench.py
+ * reads it around the timed region to report gpu_launches. */
+int64_t ls_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_B200_H_ */
