@@ -7,6 +7,7 @@ runs the projection in hand-written sm_100a CUDA kernels (``libls_b200.so``, C A
 Python cannot import a hyphenated name.
 """
 from .bev_model import BevModel, calculate_birds_eye_view_parameters  # noqa: F401
-from .lift_splat import GridSpec, LiftSplatFunction, lift_splat  # noqa: F401
+from . import lift_splat  # noqa: F401  (module: lift_splat.lift_splat(...) is the functional entry point)
+from .lift_splat import GridSpec, LiftSplatFunction  # noqa: F401
 
 __all__ = ["BevModel", "calculate_birds_eye_view_parameters", "GridSpec", "LiftSplatFunction", "lift_splat"]
