@@ -192,7 +192,7 @@ class Stepper:
                                          self._p(self.M), self._p(self.t), stream), "ls_camera_transform")
         ls.check(lib.ls_forward(self._p(d["feat"]), self._p(d["logits"]), self.code, self._p(self.M),
                                 self._p(self.t), self._p(self.frustum), C.byref(self.s), self._p(self.ws),
-                                self.ws.numel(), self._p(self.bev), C.byref(self.st), self._p(self.prob), stream),
+                                self.ws.numel(), 1, self._p(self.bev), C.byref(self.st), self._p(self.prob), stream),
                  "ls_forward")
         ls.check(lib.ls_backward(self._p(d["gbev"]), C.byref(self.gst), self._p(d["gprob"]), self._p(self.prob),
                                  self.code, C.byref(self.s), self._p(self.ws), self.ws.numel(), self._p(self.gfeat),
@@ -220,16 +220,19 @@ class Stepper:
         ABI's individual entry points (same kernels, same order as ls_forward/ls_backward)."""
         ls, lib, d, s = self.ls, self.lib, self.dev, self.s
         sh = self.shape
-        tiles, cells = ls.grid_cells(s)
+        tiles, cells, stride = ls.grid_cells(s)
         dev = self.device
         npts = sh.cams * sh.depth_bins * sh.fh * sh.fw
-        rank = torch.empty(sh.batch, npts, dtype=torch.int32, device=dev)
+        cp = ls.padded_channels(sh.channels)
+        cell = torch.empty(sh.batch, npts, dtype=torch.int32, device=dev)
+        within = torch.empty_like(cell)
         counts = torch.zeros(sh.batch, cells, dtype=torch.int32, device=dev)
-        seg = torch.empty(sh.batch, cells + 1, dtype=torch.int32, device=dev)
-        order = torch.empty_like(rank)
-        otmp = torch.empty_like(rank)
-        featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, sh.channels, dtype=self.dtype, device=dev)
-        gT = torch.empty(sh.batch, cells, sh.channels, device=dev)
+        seg = torch.empty(sh.batch, stride, dtype=torch.int32, device=dev)
+        recs = torch.empty(sh.batch, npts, 2, dtype=torch.int32, device=dev)
+        recs2 = torch.empty_like(recs)
+        pix = torch.empty(sh.batch * sh.cams * sh.fh * sh.fw, sh.depth_bins, 2, dtype=torch.int32, device=dev)
+        featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, cp, dtype=self.dtype, device=dev)
+        gT = torch.empty(sh.batch, cells, cp, device=dev)
         gprob = torch.empty(sh.batch * npts, device=dev)
         gfeatT = torch.empty_like(featT)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -237,12 +240,12 @@ class Stepper:
         P = self._p
         stages = [
             ("camera_transform", lambda: lib.ls_camera_transform(P(d["intr"]), P(d["extr"]), bn, P(self.M), P(self.t), stream)),
-            ("index+hist", lambda: (counts.zero_(), lib.ls_index(P(self.M), P(self.t), P(self.frustum), C.byref(s), P(rank), P(counts), stream))[1]),
-            ("sort(scan+place)", lambda: lib.ls_sort(P(rank), C.byref(s), P(counts), 1, P(seg), P(order), stream)),
+            ("index+hist", lambda: (counts.zero_(), lib.ls_index(P(self.M), P(self.t), P(self.frustum), C.byref(s), None, P(cell), P(within), P(counts), stream))[1]),
             ("softmax", lambda: lib.ls_softmax(P(d["logits"]), self.code, C.byref(s), P(self.prob), stream)),
+            ("sort(scan+place)", lambda: lib.ls_sort(P(cell), P(within), P(counts), P(self.prob), self.code, C.byref(s), P(seg), P(recs), P(pix), stream)),
             ("nchw_to_nhwc", lambda: lib.ls_nchw_to_nhwc(P(d["feat"]), self.code, bn, sh.channels, hw, P(featT), stream)),
-            ("splat_fwd", lambda: lib.ls_splat_fwd(P(featT), P(self.prob), self.code, P(order), P(seg), P(otmp), C.byref(s), P(self.bev), C.byref(self.st), stream)),
-            ("splat_bwd(transpose+gather)", lambda: lib.ls_splat_bwd(P(d["gbev"]), C.byref(self.gst), P(featT), P(self.prob), self.code, P(rank), C.byref(s), P(gT), P(gprob), P(gfeatT), stream)),
+            ("splat_fwd", lambda: lib.ls_splat_fwd(P(featT), self.code, P(recs), P(seg), P(recs2), C.byref(s), P(self.bev), C.byref(self.st), stream)),
+            ("splat_bwd(transpose+gather)", lambda: lib.ls_splat_bwd(P(d["gbev"]), C.byref(self.gst), P(featT), self.code, P(pix), P(seg), C.byref(s), P(gT), P(gprob), P(gfeatT), stream)),
             ("nhwc_to_nchw", lambda: lib.ls_nhwc_to_nchw(P(gfeatT), self.code, bn, sh.channels, hw, P(self.gfeat), stream)),
             ("softmax_bwd", lambda: lib.ls_softmax_bwd(P(self.prob), P(gprob), P(d["gprob"]), self.code, C.byref(s), P(self.glogits), stream)),
         ]

@@ -15,13 +15,13 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libls_b200.so")
-SOURCES = ["ls_kernels.cu"]
-HEADERS = ["ls_common.cuh", os.path.join(REPO_ROOT, "include", "ls_b200.h")]
+SOURCES = ["ls_index.cu", "ls_dense.cu", "ls_splat.cu", "ls_api.cu"]
+HEADERS = ["ls_common.cuh", "ls_internal.h", os.path.join(REPO_ROOT, "include", "ls_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     # no --use_fast_math: voxel indices must be bit-exact (IEEE divide, no FMA contraction
     # is enforced in the source with __fmul_rn/__fadd_rn/__fdiv_rn)
 ]
@@ -44,18 +44,32 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libls_b200.so (skipped when up to date)."""
+    """Compile csrc/*.cu (one nvcc per translation unit, in parallel) and link
+    libls_b200.so; skipped when up to date."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        base += ["-Xptxas", "-v"]
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = base + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for cmd, obj, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), err))
+        if verbose:
+            sys.stderr.write(err)
+        objs.append(obj)
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(link), res.stderr))
     return LIB_PATH
 
 

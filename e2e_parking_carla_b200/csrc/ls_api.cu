@@ -1,0 +1,260 @@
+// C ABI of libls_b200.so (include/ls_b200.h): argument checking, workspace carving and the
+// forward / backward pipelines.  No torch types, no exceptions, no allocation, no host sync.
+#include <atomic>
+#include <stdio.h>
+#include <string.h>
+
+#include "ls_internal.h"
+
+static std::atomic<long long> g_launches{0};
+static thread_local char g_cuda_err[256] = "";
+
+void ls_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int ls_note_cuda_error(cudaError_t e, const char* file, int line) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d", cudaGetErrorString(e), file, line);
+  return LS_ERR_CUDA;
+}
+
+static int ls_check_shape(const LsShape* s) {
+  if (!s) return LS_ERR_BAD_ARG;
+  if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fh <= 0 || s->fw <= 0 || s->C <= 0) return LS_ERR_BAD_ARG;
+  if (s->X <= 0 || s->Y <= 0 || s->Z <= 0) return LS_ERR_BAD_ARG;
+  if ((long long)s->X * s->Y * s->Z >= (1LL << 28)) return LS_ERR_UNSUPPORTED;
+  if ((long long)s->B * s->N * s->D * s->fh * s->fw >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
+  return LS_OK;
+}
+static int ls_check_splat_shape(const LsShape* s) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (s->Z != 1) return LS_ERR_UNSUPPORTED;   // reference: squeeze(0) needs Z == 1 (bev_model.py:104)
+  if (s->C > 4 * LS_CCHUNK) return LS_ERR_UNSUPPORTED;
+  LsDims dm = ls_dims(s);
+  // sort key: 8 bits cell-in-tile | (pixel << dbits | d) must fit 24 bits
+  if (((long long)s->N * dm.HW) << dm.dbits > (1LL << 24)) return LS_ERR_UNSUPPORTED;
+  if ((long long)s->N * dm.HW * dm.Cp >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
+  return LS_OK;
+}
+static bool ls_dtype_ok(int dtype) { return dtype == LS_F32 || dtype == LS_BF16; }
+
+// ---- workspace carving -------------------------------------------------------------
+struct LsWs {
+  int *cell, *within, *counts, *seg_start;
+  int2 *recs, *recs_sorted, *pix_recs;
+  void* featT;
+  float *gT, *gprob_pm;
+  void* gfeatT;
+  size_t bytes;
+};
+static inline size_t ls_align(size_t v) { return (v + 255) & ~(size_t)255; }
+static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base) {
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  const size_t es = dtype == LS_BF16 ? 2 : 4;
+  const size_t pts = (size_t)dm.B * dm.Npts;
+  const size_t feat = (size_t)dm.B * dm.N * dm.HW * dm.Cp * es;
+  char* p = (char*)base;
+  size_t off = 0;
+  LsWs w;
+  memset(&w, 0, sizeof(w));
+  auto take = [&](size_t n) { void* r = p ? (void*)(p + off) : nullptr; off += ls_align(n); return r; };
+  w.featT = take(feat);                       // kept for backward
+  w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);   // kept for backward
+  w.counts = (int*)take((size_t)dm.B * g.Vc * 4);
+  w.cell = (int*)take(pts * 4);
+  w.within = (int*)take(pts * 4);
+  w.recs = (int2*)take(pts * 8);
+  w.recs_sorted = (int2*)take(pts * 8);
+  if (with_backward) {
+    w.pix_recs = (int2*)take(pts * 8);        // kept for backward
+    w.gT = (float*)take((size_t)dm.B * g.Vc * dm.Cp * 4);
+    w.gprob_pm = (float*)take(pts * 4);
+    w.gfeatT = take(feat);
+  }
+  w.bytes = off;
+  return w;
+}
+
+extern "C" {
+
+const char* ls_version(void) { return "ls_b200 0.2 (sm_100a)"; }
+
+const char* ls_strerror(int status) {
+  switch (status) {
+    case LS_OK: return "ok";
+    case LS_ERR_BAD_ARG: return "bad argument";
+    case LS_ERR_UNSUPPORTED: return "unsupported configuration";
+    case LS_ERR_WORKSPACE: return "workspace too small";
+    case LS_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+const char* ls_last_cuda_error(void) { return g_cuda_err; }
+int64_t ls_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32_t* seg_stride) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  LsGrid g = ls_grid(s);
+  if (tiles) *tiles = g.tiles;
+  if (cells_padded) *cells_padded = g.Vc;
+  if (seg_stride) *seg_stride = g.seg_stride;
+  return LS_OK;
+}
+
+int32_t ls_padded_channels(int32_t C) { return (C + 3) & ~3; }
+
+int ls_camera_transform(const float* intrinsics, const float* extrinsics, int32_t BN, float* M, float* t,
+                        ls_stream_t stream) {
+  if (!intrinsics || !extrinsics || !M || !t || BN <= 0) return LS_ERR_BAD_ARG;
+  return ls_launch_camera_transform(intrinsics, extrinsics, BN, M, t, (cudaStream_t)stream);
+}
+
+int ls_geometry(const float* M, const float* t, const float* frustum, const LsShape* s, float* geom,
+                ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!M || !t || !frustum || !geom) return LS_ERR_BAD_ARG;
+  return ls_launch_export(M, t, frustum, ls_dims(s), ls_grid(s), geom, nullptr, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int ls_export_indices(const float* M, const float* t, const float* frustum, const LsShape* s, int64_t* vox,
+                      uint8_t* keep, int64_t* rank, ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!M || !t || !frustum) return LS_ERR_BAD_ARG;
+  return ls_launch_export(M, t, frustum, ls_dims(s), ls_grid(s), nullptr, (long long*)vox, keep, (long long*)rank,
+                          (cudaStream_t)stream);
+}
+
+int ls_index(const float* M, const float* t, const float* frustum, const LsShape* s, int32_t* rank, int32_t* cell,
+             int32_t* within, int32_t* counts, ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!M || !t || !frustum) return LS_ERR_BAD_ARG;
+  const bool sorting = cell || within || counts;
+  if (sorting && !(cell && within && counts)) return LS_ERR_BAD_ARG;
+  if (!sorting && !rank) return LS_ERR_BAD_ARG;
+  if (sorting && (rc = ls_check_splat_shape(s))) return rc;
+  return ls_launch_index(M, t, frustum, ls_dims(s), ls_grid(s), rank, cell, within, counts, (cudaStream_t)stream);
+}
+
+int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob, int dtype,
+            const LsShape* s, int32_t* seg_start, void* recs, void* pix_recs, ls_stream_t stream) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!cell || !within || !counts || !prob || !seg_start || !recs || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  if ((rc = ls_launch_scan(counts, dm, g, seg_start, (cudaStream_t)stream))) return rc;
+  return ls_launch_place(cell, within, prob, dtype, dm, g, seg_start, (int2*)recs, (int2*)pix_recs,
+                         (cudaStream_t)stream);
+}
+
+int ls_export_cell_counts(const int32_t* seg_start, const LsShape* s, int32_t b, int64_t* out, int32_t* kept,
+                          ls_stream_t stream) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!seg_start || b < 0 || b >= s->B) return LS_ERR_BAD_ARG;
+  return ls_launch_export_cell_counts(seg_start, ls_grid(s), s->B, b, (long long*)out, kept, (cudaStream_t)stream);
+}
+
+int ls_softmax(const void* logits, int dtype, const LsShape* s, void* prob, ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!logits || !prob || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  return ls_launch_softmax(logits, dtype, ls_dims(s), prob, (cudaStream_t)stream);
+}
+
+int ls_softmax_bwd(const void* prob, const float* grad_prob_pm, const void* grad_prob_ext, int dtype,
+                   const LsShape* s, void* grad_logits, ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!prob || !grad_prob_pm || !grad_logits || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  return ls_launch_softmax_bwd(prob, grad_prob_pm, grad_prob_ext, dtype, ls_dims(s), grad_logits,
+                               (cudaStream_t)stream);
+}
+
+int ls_nchw_to_nhwc(const void* src, int dtype, int32_t images, int32_t C, int32_t HW, void* dst,
+                    ls_stream_t stream) {
+  if (!src || !dst || images <= 0 || C <= 0 || HW <= 0 || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  return ls_launch_to_nhwc(src, dtype, images, C, ls_padded_channels(C), HW, dst, (cudaStream_t)stream);
+}
+int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32_t HW, void* dst,
+                    ls_stream_t stream) {
+  if (!src || !dst || images <= 0 || C <= 0 || HW <= 0 || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  return ls_launch_from_nhwc(src, dtype, images, C, ls_padded_channels(C), HW, dst, (cudaStream_t)stream);
+}
+
+int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start, void* recs_scratch,
+                 const LsShape* s, float* bev, const LsBevStrides* st, ls_stream_t stream) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!feat_nhwc || !recs || !seg_start || !recs_scratch || !bev || !st || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  return ls_launch_splat_fwd(feat_nhwc, dtype, (const int2*)recs, seg_start, (int2*)recs_scratch, ls_dims(s),
+                             ls_grid(s), bev, *st, (cudaStream_t)stream);
+}
+
+int ls_splat_bwd(const float* grad_bev, const LsBevStrides* gst, const void* feat_nhwc, int dtype,
+                 const void* pix_recs, const int32_t* seg_start, const LsShape* s, float* gT_ws, float* grad_prob_pm,
+                 void* grad_feat_nhwc, ls_stream_t stream) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!grad_bev || !gst || !feat_nhwc || !pix_recs || !seg_start || !gT_ws || !grad_prob_pm || !grad_feat_nhwc ||
+      !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  if ((rc = ls_launch_bwd_transpose(grad_bev, *gst, seg_start, dm, g, gT_ws, (cudaStream_t)stream))) return rc;
+  return ls_launch_bwd_gather(gT_ws, feat_nhwc, dtype, (const int2*)pix_recs, dm, g, grad_prob_pm, grad_feat_nhwc,
+                              (cudaStream_t)stream);
+}
+
+size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward) {
+  if (ls_check_splat_shape(s) || !ls_dtype_ok(dtype)) return 0;
+  return ls_carve(s, dtype, with_backward, nullptr).bytes;
+}
+
+int ls_forward(const void* feat, const void* logits, int dtype, const float* M, const float* t, const float* frustum,
+               const LsShape* s, void* ws, size_t ws_bytes, int with_backward, float* bev,
+               const LsBevStrides* bev_strides, void* prob, ls_stream_t stream_) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!feat || !logits || !M || !t || !frustum || !ws || !bev || !bev_strides || !prob || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  if (ws_bytes < ls_carve(s, dtype, with_backward, nullptr).bytes) return LS_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LsWs w = ls_carve(s, dtype, with_backward, ws);
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  LS_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)dm.B * g.Vc * sizeof(int), stream));
+  ls_note_launch();
+  if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
+  if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, stream))) return rc;
+  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, stream))) return rc;
+  if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs,
+                            with_backward ? w.pix_recs : nullptr, stream)))
+    return rc;
+  if ((rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, stream))) return rc;
+  return ls_launch_splat_fwd(w.featT, dtype, w.recs, w.seg_start, w.recs_sorted, dm, g, bev, *bev_strides, stream);
+}
+
+int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext, const void* prob,
+                int dtype, const LsShape* s, void* ws, size_t ws_bytes, void* grad_feat, void* grad_logits,
+                ls_stream_t stream_) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!grad_bev || !grad_strides || !prob || !ws || !grad_feat || !grad_logits || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  if (ws_bytes < ls_carve(s, dtype, 1, nullptr).bytes) return LS_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LsWs w = ls_carve(s, dtype, 1, ws);
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, w.seg_start, dm, g, w.gT, stream))) return rc;
+  if ((rc = ls_launch_bwd_gather(w.gT, w.featT, dtype, w.pix_recs, dm, g, w.gprob_pm, w.gfeatT, stream))) return rc;
+  if ((rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, stream))) return rc;
+  return ls_launch_softmax_bwd(prob, w.gprob_pm, grad_prob_ext, dtype, dm, grad_logits, stream);
+}
+
+}  // extern "C"

@@ -7,19 +7,24 @@
 
 #include "ls_b200.h"
 
-#define LS_TX 8                      // BEV tile: 8 x-rows ...
-#define LS_TY 32                     // ... by 32 y-columns (128 B of fp32 along Y)
-#define LS_TILE (LS_TX * LS_TY)      // 256 cells per tile
-#define LS_TILE_PAD (LS_TILE + 1)    // odd smem row stride -> conflict-free column walks
-#define LS_CCHUNK 64                 // channels handled per pass by one warp (float2 per lane)
-#define LS_WARPS 8
-#define LS_THREADS (LS_WARPS * 32)
+// ---- BEV tiling ---------------------------------------------------------------------
+// The grid is cut into LS_TX x LS_TY voxel tiles; cells are numbered tile-major
+// (cell = tile*256 + lx*LS_TY + ly).  Square tiles keep ~6 consecutive depth bins of a
+// crossing camera ray inside one tile, which is what gives the feature gather its L1 reuse.
+#define LS_TX 16
+#define LS_TY 16
+#define LS_TILE (LS_TX * LS_TY)      // 256 cells per tile (cell-in-tile fits 8 bits)
+#define LS_CCHUNK 64                 // channels per pass: a half-warp holds 16 x float4
+#define LS_THREADS 256
+#define LS_HALFWARPS (LS_THREADS / 16)
+#define LS_SEG_PAD 4                 // seg_start row stride = Vc + LS_SEG_PAD (16 B aligned rows)
 
 // Everything a kernel needs to know about the BEV grid, derived once on the host.
 struct LsGrid {
   int X, Y, Z;
   int tiles_x, tiles_y, tiles;
   int Vc;          // padded cell count = tiles * LS_TILE
+  int seg_stride;  // Vc + LS_SEG_PAD
   float off[3];    // bev_start_pos - bev_res / 2   (float32 ops, model/bev_model.py:85)
   float res[3];
   float fdim[3];   // (float)dim, exact (dim < 2^24)
@@ -27,17 +32,22 @@ struct LsGrid {
 
 struct LsDims {
   int B, N, D, fh, fw, C;
+  int Cp;      // channels padded to a multiple of 4 (internal NHWC staging rows)
   int HW;      // fh*fw
   int DHW;     // D*fh*fw   points per camera
   int Npts;    // N*D*fh*fw points per sample
+  int dbits;   // ceil(log2(D)): sort key = cell_in_tile<<24 | (pix << dbits | d)
 };
 
 static inline LsDims ls_dims(const LsShape* s) {
   LsDims d;
   d.B = s->B; d.N = s->N; d.D = s->D; d.fh = s->fh; d.fw = s->fw; d.C = s->C;
+  d.Cp = (s->C + 3) & ~3;
   d.HW = s->fh * s->fw;
   d.DHW = s->D * d.HW;
   d.Npts = s->N * d.DHW;
+  d.dbits = 0;
+  while ((1 << d.dbits) < s->D) ++d.dbits;
   return d;
 }
 
@@ -48,6 +58,7 @@ static inline LsGrid ls_grid(const LsShape* s) {
   g.tiles_y = (s->Y + LS_TY - 1) / LS_TY;
   g.tiles = g.tiles_x * g.tiles_y;
   g.Vc = g.tiles * LS_TILE;
+  g.seg_stride = g.Vc + LS_SEG_PAD;
   for (int i = 0; i < 3; ++i) {
     // x86-64 float arithmetic is IEEE single (SSE), same bits as torch's float32 ops.
     volatile float half = s->res[i] / 2.0f;
@@ -59,15 +70,17 @@ static inline LsGrid ls_grid(const LsShape* s) {
   return g;
 }
 
-// rank (reference convention, Z == 1) -> tile-major cell id
-__device__ __forceinline__ int ls_cell_of_xy(int gx, int gy, int tiles_y) {
+// (gx, gy) -> tile-major cell id (Z == 1)
+__host__ __device__ __forceinline__ int ls_cell_of_xy(int gx, int gy, int tiles_y) {
   const int tile = (gx / LS_TX) * tiles_y + (gy / LS_TY);
   return tile * LS_TILE + (gx % LS_TX) * LS_TY + (gy % LS_TY);
 }
-__device__ __forceinline__ int ls_cell_of_rank(int r, int Y, int tiles_y) {
-  const int gx = r / Y;
-  const int gy = r - gx * Y;
-  return ls_cell_of_xy(gx, gy, tiles_y);
+// tile-major cell id -> reference rank gx*Y + gy (-1 for padding cells outside the grid)
+__host__ __device__ __forceinline__ int ls_rank_of_cell(int cell, const LsGrid& g) {
+  const int tile = cell / LS_TILE, local = cell % LS_TILE;
+  const int gx = (tile / g.tiles_y) * LS_TX + local / LS_TY;
+  const int gy = (tile % g.tiles_y) * LS_TY + local % LS_TY;
+  return (gx < g.X && gy < g.Y) ? gx * g.Y + gy : -1;
 }
 
 // Voxel coordinate of one frustum point, operation by operation as torch-CPU does it
@@ -105,24 +118,44 @@ template <typename T> __device__ __forceinline__ T ls_from_float(float v);
 template <> __device__ __forceinline__ float ls_from_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 ls_from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// two consecutive channels
-template <typename T> __device__ __forceinline__ float2 ls_load2(const T* p);
-template <> __device__ __forceinline__ float2 ls_load2<float>(const float* p) {
-  return *reinterpret_cast<const float2*>(p);
+// four consecutive channels (16 B of fp32 / 8 B of bf16), read-only path
+template <typename T> __device__ __forceinline__ float4 ls_load4(const T* p);
+template <> __device__ __forceinline__ float4 ls_load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
 }
-template <> __device__ __forceinline__ float2 ls_load2<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+template <> __device__ __forceinline__ float4 ls_load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  return make_float4(a.x, a.y, b.x, b.y);
 }
-template <typename T> __device__ __forceinline__ void ls_store2(T* p, float2 v);
-template <> __device__ __forceinline__ void ls_store2<float>(float* p, float2 v) {
-  *reinterpret_cast<float2*>(p) = v;
+template <typename T> __device__ __forceinline__ void ls_store4(T* p, float4 v);
+template <> __device__ __forceinline__ void ls_store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
 }
-template <> __device__ __forceinline__ void ls_store2<__nv_bfloat16>(__nv_bfloat16* p, float2 v) {
-  *reinterpret_cast<__nv_bfloat162*>(p) = __float22bfloat162_rn(v);
+template <> __device__ __forceinline__ void ls_store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __float22bfloat162_rn(make_float2(v.x, v.y));
+  __nv_bfloat162 b = __float22bfloat162_rn(make_float2(v.z, v.w));
+  uint2 raw;
+  raw.x = *reinterpret_cast<unsigned*>(&a);
+  raw.y = *reinterpret_cast<unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = raw;
 }
 
-__device__ __forceinline__ float ls_warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// Shared-memory tile [cell][channel] with row stride (cc + 4) floats; the channel quad of a
+// cell is XOR-swizzled with bits of the cell index so that BOTH the row-wise float4 accesses
+// (one cell, 16 quads) and the column-wise scalar walks (fixed channel, consecutive cells)
+// are bank-conflict free.  nq = number of quads per row (power of two <= 16).
+__device__ __forceinline__ int ls_tile_quad(int cl, int q, int nq) {
+  return q ^ ((cl >> 3) & (nq - 1));
 }
+
+// ---- launch bookkeeping (defined in ls_api.cu) ----------------------------------------
+void ls_note_launch();
+int ls_note_cuda_error(cudaError_t e, const char* file, int line);
+#define LS_CUDA(call)                                                     \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) return ls_note_cuda_error(e__, __FILE__, __LINE__); \
+  } while (0)
+#define LS_LAUNCHED() do { ls_note_launch(); LS_CUDA(cudaGetLastError()); } while (0)

@@ -1,0 +1,227 @@
+// Dense helpers around the splat: depth softmax (model/bev_model.py:64) forward/backward and
+// the NCHW <-> padded-NHWC staging transposes.  All bandwidth-bound, coalesced both ways.
+#include "ls_internal.h"
+
+#define LS_SM_MAXK 16   // depth bins per thread held in registers: D <= 8 * 16
+
+// =====================================================================================
+// softmax over depth.  CTA = (image, 32 pixels); thread (lane = pixel, dg = depth group 0..7)
+// owns bins dg, dg+8, ... in registers; max and sum are combined through shared memory.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ prob) {
+  __shared__ float red[8][33];
+  const int img = blockIdx.y;
+  const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int rc = blockIdx.x * 32 + lane;
+  const bool on = rc < HW;
+  const T* src = logits + (size_t)img * D * HW + rc;
+  T* dst = prob + (size_t)img * D * HW + rc;
+  float x[LS_SM_MAXK];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < LS_SM_MAXK; ++k) {
+    const int d = dg + 8 * k;
+    x[k] = (on && d < D) ? ls_to_float(src[(size_t)d * HW]) : -INFINITY;
+    m = fmaxf(m, x[k]);
+  }
+  red[dg][lane] = m;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m = fmaxf(m, red[j][lane]);
+  __syncthreads();
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < LS_SM_MAXK; ++k) {
+    const int d = dg + 8 * k;
+    x[k] = (on && d < D) ? expf(x[k] - m) : 0.0f;
+    s += x[k];
+  }
+  red[dg][lane] = s;
+  __syncthreads();
+  s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += red[j][lane];
+#pragma unroll
+  for (int k = 0; k < LS_SM_MAXK; ++k) {
+    const int d = dg + 8 * k;
+    if (on && d < D) dst[(size_t)d * HW] = ls_from_float<T>(__fdiv_rn(x[k], s));
+  }
+}
+
+// generic fallback for D > 128: one thread per pixel, three passes
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_softmax_serial_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ prob) {
+  const int img = blockIdx.y;
+  const int rc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rc >= HW) return;
+  const T* src = logits + (size_t)img * D * HW + rc;
+  T* dst = prob + (size_t)img * D * HW + rc;
+  float m = -INFINITY;
+  for (int d = 0; d < D; ++d) m = fmaxf(m, ls_to_float(src[(size_t)d * HW]));
+  float s = 0.0f;
+  for (int d = 0; d < D; ++d) s += expf(ls_to_float(src[(size_t)d * HW]) - m);
+  for (int d = 0; d < D; ++d)
+    dst[(size_t)d * HW] = ls_from_float<T>(__fdiv_rn(expf(ls_to_float(src[(size_t)d * HW]) - m), s));
+}
+
+int ls_launch_softmax(const void* logits, int dtype, const LsDims& dm, void* prob, cudaStream_t s) {
+  const int images = dm.B * dm.N;
+  if (dm.D <= 8 * LS_SM_MAXK) {
+    dim3 grid((dm.HW + 31) / 32, images);
+    if (dtype == LS_F32)
+      ls_softmax_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, dm.D, dm.HW, (float*)prob);
+    else
+      ls_softmax_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, dm.D, dm.HW,
+                                                            (__nv_bfloat16*)prob);
+  } else {
+    dim3 grid((dm.HW + 255) / 256, images);
+    if (dtype == LS_F32)
+      ls_softmax_serial_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, dm.D, dm.HW, (float*)prob);
+    else
+      ls_softmax_serial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, dm.D, dm.HW,
+                                                                   (__nv_bfloat16*)prob);
+  }
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// softmax backward: gl = prob * (g - sum_d prob*g),  g = grad_prob (+ ext).
+// grad_prob arrives PIXEL-major [image][pixel][D] from the gather kernel; it is staged through
+// shared memory so that both its reads and the depth-major writes are coalesced.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_softmax_bwd_kernel(const T* __restrict__ prob, const float* __restrict__ gprob_pm, const T* __restrict__ gext,
+                      int D, int HW, T* __restrict__ glogits) {
+  extern __shared__ float sm[];
+  const int Dp = D | 1;
+  float* stage = sm;                   // [32][Dp]
+  float* red = sm + 32 * Dp;           // [8][33]
+  const int img = blockIdx.y, rc0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int valid = min(32, HW - rc0);
+  const float* gsrc = gprob_pm + ((size_t)img * HW + rc0) * D;
+  for (int r = dg; r < valid; r += 8)
+    for (int d = lane; d < D; d += 32) stage[r * Dp + d] = gsrc[(size_t)r * D + d];
+  __syncthreads();
+  const int rc = rc0 + lane;
+  const bool on = rc < HW;
+  const size_t base = (size_t)img * D * HW + rc;
+  float dot = 0.0f;
+  for (int d = dg; d < D; d += 8) {
+    if (on) {
+      float g = stage[lane * Dp + d];
+      if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
+      dot = fmaf(ls_to_float(prob[base + (size_t)d * HW]), g, dot);
+    }
+  }
+  red[dg * 33 + lane] = dot;
+  __syncthreads();
+  dot = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dot += red[j * 33 + lane];
+  for (int d = dg; d < D; d += 8) {
+    if (on) {
+      float g = stage[lane * Dp + d];
+      if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
+      glogits[base + (size_t)d * HW] = ls_from_float<T>(ls_to_float(prob[base + (size_t)d * HW]) * (g - dot));
+    }
+  }
+}
+
+int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* gext, int dtype, const LsDims& dm,
+                          void* glogits, cudaStream_t s) {
+  dim3 grid((dm.HW + 31) / 32, dm.B * dm.N);
+  const size_t smem = ((size_t)32 * (dm.D | 1) + 8 * 33) * sizeof(float);
+  if (smem > 48 * 1024) return LS_ERR_UNSUPPORTED;
+  if (dtype == LS_F32)
+    ls_softmax_bwd_kernel<float><<<grid, 256, smem, s>>>((const float*)prob, gprob_pm, (const float*)gext, dm.D,
+                                                         dm.HW, (float*)glogits);
+  else
+    ls_softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)prob, gprob_pm,
+                                                                 (const __nv_bfloat16*)gext, dm.D, dm.HW,
+                                                                 (__nv_bfloat16*)glogits);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// [image][C][HW] -> [image][HW][Cp]  (Cp = C rounded up to 4, zero padded), 64x64 tiles.
+// Reads are 128-byte rows over HW; writes are 16-byte channel quads (256 B per pixel at C=64).
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_to_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restrict__ dst) {
+  __shared__ float tile[64][65];
+  const int img = blockIdx.z, hw0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const T* in = src + (size_t)img * C * HW;
+  T* out = dst + (size_t)img * HW * Cp;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = w; c < 64; c += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int hw = hw0 + lane + 32 * h;
+      float v = 0.0f;
+      if (c0 + c < C && hw < HW) v = ls_to_float(in[(size_t)(c0 + c) * HW + hw]);
+      tile[c][lane + 32 * h] = v;
+    }
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 15;
+  for (int h = threadIdx.x >> 4; h < 64; h += 16) {
+    const int hw = hw0 + h, c = c0 + 4 * q;
+    if (hw < HW && c < Cp)
+      ls_store4<T>(out + (size_t)hw * Cp + c,
+                   make_float4(tile[4 * q][h], tile[4 * q + 1][h], tile[4 * q + 2][h], tile[4 * q + 3][h]));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_from_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restrict__ dst) {
+  __shared__ float tile[64][65];
+  const int img = blockIdx.z, hw0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const T* in = src + (size_t)img * HW * Cp;
+  T* out = dst + (size_t)img * C * HW;
+  const int q = threadIdx.x & 15;
+  for (int h = threadIdx.x >> 4; h < 64; h += 16) {
+    const int hw = hw0 + h, c = c0 + 4 * q;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hw < HW && c < Cp) v = ls_load4<T>(in + (size_t)hw * Cp + c);
+    tile[4 * q][h] = v.x; tile[4 * q + 1][h] = v.y; tile[4 * q + 2][h] = v.z; tile[4 * q + 3][h] = v.w;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = w; c < 64; c += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int hw = hw0 + lane + 32 * h;
+      if (c0 + c < C && hw < HW) out[(size_t)(c0 + c) * HW + hw] = ls_from_float<T>(tile[c][lane + 32 * h]);
+    }
+  }
+}
+
+int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s) {
+  dim3 grid((HW + 63) / 64, (Cp + 63) / 64, images);
+  if (dtype == LS_F32)
+    ls_to_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)src, C, Cp, HW, (float*)dst);
+  else
+    ls_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, C, Cp, HW, (__nv_bfloat16*)dst);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s) {
+  dim3 grid((HW + 63) / 64, (Cp + 63) / 64, images);
+  if (dtype == LS_F32)
+    ls_from_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)src, C, Cp, HW, (float*)dst);
+  else
+    ls_from_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, C, Cp, HW,
+                                                            (__nv_bfloat16*)dst);
+  LS_LAUNCHED();
+  return LS_OK;
+}

@@ -1,0 +1,287 @@
+// Index side of the lift-splat path: camera transform, fused geometry -> voxel -> rank,
+// counting sort (histogram with ticket, scan, placement).  Integer work is bit-exact with
+// the reference (model/bev_model.py:45-57,85-97); see include/ls_b200.h.
+#include "ls_internal.h"
+
+// =====================================================================================
+// camera transform: E^-1, K^-1 (fp64 Gauss-Jordan, partial pivoting), M = R . K^-1
+// reference: model/bev_model.py:46-47,53     oracle: camera_transform
+// =====================================================================================
+template <int n>
+__device__ void ls_gauss_jordan(double (*a)[2 * n]) {
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = fabs(a[k][k]);
+    for (int i = k + 1; i < n; ++i) {
+      const double v = fabs(a[i][k]);
+      if (v > best) { best = v; p = i; }   // first maximum wins (numpy argmax)
+    }
+    if (p != k) {
+      for (int j = 0; j < 2 * n; ++j) { const double tmp = a[k][j]; a[k][j] = a[p][j]; a[p][j] = tmp; }
+    }
+    const double piv = a[k][k];
+    for (int j = 0; j < 2 * n; ++j) a[k][j] = __ddiv_rn(a[k][j], piv);
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      for (int j = 0; j < 2 * n; ++j) a[i][j] = __dsub_rn(a[i][j], __dmul_rn(f, a[k][j]));
+    }
+  }
+}
+
+__global__ void ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr,
+                                           int BN, float* __restrict__ M, float* __restrict__ t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BN) return;
+  double e[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) { e[r][c] = (double)extr[i * 16 + r * 4 + c]; e[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+  ls_gauss_jordan<4>(e);
+  double k[3][6];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) { k[r][c] = (double)intr[i * 9 + r * 3 + c]; k[r][3 + c] = (r == c) ? 1.0 : 0.0; }
+  ls_gauss_jordan<3>(k);
+  float rot[3][3], kin[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) { rot[r][c] = (float)e[r][4 + c]; kin[r][c] = (float)k[r][3 + c]; }
+  for (int r = 0; r < 3; ++r) {
+    t[i * 3 + r] = (float)e[r][7];
+    for (int c = 0; c < 3; ++c) {
+      float acc = 0.0f;  // aten's small-matrix bmm: unfused, k ascending, from +0
+      for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn(rot[r][q], kin[q][c]));
+      M[i * 9 + r * 3 + c] = acc;
+    }
+  }
+}
+
+int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s) {
+  ls_camera_transform_kernel<<<(BN + 31) / 32, 32, 0, s>>>(intr, extr, BN, M, t);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// K1: fused lift geometry -> voxel index -> keep -> rank  (+ histogram ticket)
+// reference: model/bev_model.py:49-55 (get_geometry), :85-95 (voxelise, mask, rank)
+// One thread per frustum point; geom never leaves registers.  The per-cell histogram is one
+// integer atomicAdd per kept point whose return value ("ticket") is the point's slot inside
+// its cell, so placement later needs no second atomic pass.
+// =====================================================================================
+template <bool kExport>
+__global__ void __launch_bounds__(256)
+ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const float* __restrict__ frustum,
+                LsDims dm, LsGrid grid, int* __restrict__ rank, int* __restrict__ cell, int* __restrict__ within,
+                int* __restrict__ counts, float* __restrict__ geom_out, long long* __restrict__ vox_out,
+                unsigned char* __restrict__ keep_out, long long* __restrict__ rank64_out) {
+  __shared__ float cam[12];
+  const int b = blockIdx.z, n = blockIdx.y;
+  if (threadIdx.x < 9) cam[threadIdx.x] = M[(b * dm.N + n) * 9 + threadIdx.x];
+  else if (threadIdx.x < 12) cam[threadIdx.x] = t[(b * dm.N + n) * 3 + threadIdx.x - 9];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.DHW) return;
+  const float u = __ldg(frustum + 3 * i + 0), v = __ldg(frustum + 3 * i + 1), d = __ldg(frustum + 3 * i + 2);
+  float g[3], c[3];
+  int vx[3];
+  ls_point_geom(cam, cam + 9, u, v, d, g);
+  const bool keep = ls_point_voxel(g, grid, c, vx);
+  const size_t p = (size_t)b * dm.Npts + (size_t)n * dm.DHW + i;
+  if (kExport) {
+    const int r = keep ? (vx[0] * (grid.Y * grid.Z) + vx[1] * grid.Z + vx[2]) : -1;
+    if (geom_out) { geom_out[3 * p + 0] = g[0]; geom_out[3 * p + 1] = g[1]; geom_out[3 * p + 2] = g[2]; }
+    if (vox_out) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        // Tensor.long() on x86: cvttss2si -> INT64_MIN for NaN / out of range
+        const bool ok = fabsf(c[a]) < 9.2e18f;
+        vox_out[3 * p + a] = ok ? __float2ll_rz(c[a]) : (long long)0x8000000000000000ULL;
+      }
+    }
+    if (keep_out) keep_out[p] = keep ? 1 : 0;
+    if (rank64_out) rank64_out[p] = (long long)r;
+  } else {
+    if (rank) rank[p] = keep ? (vx[0] * (grid.Y * grid.Z) + vx[1] * grid.Z + vx[2]) : -1;
+    if (cell) {
+      int cid = -1, tk = 0;
+      if (keep) {
+        cid = ls_cell_of_xy(vx[0], vx[1], grid.tiles_y);
+        tk = atomicAdd(&counts[(size_t)b * grid.Vc + cid], 1);
+      }
+      cell[p] = cid;
+      within[p] = tk;
+    }
+  }
+}
+
+int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
+                    int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
+  dim3 grid((dm.DHW + 255) / 256, dm.N, dm.B);
+  ls_index_kernel<false><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, rank, cell, within, counts, nullptr, nullptr,
+                                              nullptr, nullptr);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
+                     float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s) {
+  dim3 grid((dm.DHW + 255) / 256, dm.N, dm.B);
+  ls_index_kernel<true><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, nullptr, nullptr, nullptr, nullptr, geom, vox,
+                                             keep, rank64);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// K2a: exclusive scan of the per-cell histogram -> CSR offsets (one CTA per sample).
+// Replaces the boundary mask of tool/geometry.py:295-296.  Three phases per chunk of 1024
+// tiles: per-tile totals (one warp per tile, 8 cells per lane), block scan of the totals,
+// then in-tile scans written as 16-byte stores.
+// =====================================================================================
+__device__ __forceinline__ int ls_warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += y;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(1024)
+ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_start) {
+  __shared__ int tile_base[1024];
+  __shared__ int warp_tot[32];
+  __shared__ int chunk_total;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* cnt = counts + (size_t)b * g.Vc;
+  int* seg = seg_start + (size_t)b * g.seg_stride;
+  int carry = 0;
+  for (int t0 = 0; t0 < g.tiles; t0 += 1024) {
+    const int tend = min(g.tiles, t0 + 1024);
+    for (int t = t0 + warp; t < tend; t += 32) {
+      const int4* q = reinterpret_cast<const int4*>(cnt + (size_t)t * LS_TILE) + lane * 2;
+      const int4 a = q[0], c = q[1];
+      int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) tile_base[t - t0] = s;
+    }
+    __syncthreads();
+    const int v = (t0 + tid < tend) ? tile_base[tid] : 0;
+    const int incl = ls_warp_incl_scan(v, lane);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      const int wi = ls_warp_incl_scan(w, lane);
+      warp_tot[lane] = wi - w;
+      if (lane == 31) chunk_total = wi;
+    }
+    __syncthreads();
+    tile_base[tid] = carry + warp_tot[warp] + incl - v;
+    __syncthreads();
+    for (int t = t0 + warp; t < tend; t += 32) {
+      const int4* q = reinterpret_cast<const int4*>(cnt + (size_t)t * LS_TILE) + lane * 2;
+      const int4 a = q[0], c = q[1];
+      const int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+      const int base = tile_base[t - t0] + ls_warp_incl_scan(s, lane) - s;
+      int4 o0, o1;
+      o0.x = base; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
+      o1.x = o0.w + a.w; o1.y = o1.x + c.x; o1.z = o1.y + c.y; o1.w = o1.z + c.z;
+      int4* dst = reinterpret_cast<int4*>(seg + (size_t)t * LS_TILE) + lane * 2;
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+    carry += chunk_total;
+    __syncthreads();
+  }
+  if (tid == 0) seg[g.Vc] = carry;
+}
+
+int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, cudaStream_t s) {
+  ls_scan_kernel<<<dm.B, 1024, 0, s>>>(counts, g, seg_start);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// K2b: placement.  Replaces argsort + gathers of model/bev_model.py:96-97: every kept point
+// writes one 8-byte record (sort key, prob) into slot seg_start[cell] + ticket.  The ticket
+// order inside a cell is arbitrary (atomics); ls_splat_fwd re-orders each cell by key, so the
+// sums are deterministic.  key = cell_in_tile << 24 | (pixel << dbits | d).
+// With pix_recs != NULL it also emits, pixel-major, the (cell, prob) pair of every depth bin
+// of every pixel - the index the pixel-stationary backward walks.
+// CTA = (sample, camera, 32 consecutive pixels) x all depth bins; loads are coalesced over
+// pixels, the pixel-major rows are transposed through shared memory.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, const T* __restrict__ prob, LsDims dm,
+                LsGrid grid, const int* __restrict__ seg_start, int2* __restrict__ recs, int2* __restrict__ pix_recs) {
+  extern __shared__ int2 stage[];                 // [32][Dp], Dp odd
+  const int Dp = dm.D | 1;
+  const int b = blockIdx.z, n = blockIdx.y, rc0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int rc = rc0 + lane;
+  const int* seg = seg_start + (size_t)b * grid.seg_stride;
+  if (rc < dm.HW) {
+    const int pix = n * dm.HW + rc;
+    for (int d = dg; d < dm.D; d += 8) {
+      const size_t idx = (size_t)b * dm.Npts + (size_t)(n * dm.D + d) * dm.HW + rc;
+      const int c = cell[idx];
+      const int wbits = __float_as_int(ls_to_float(prob[idx]));
+      if (c >= 0) {
+        const int slot = seg[c] + within[idx];
+        const int key = ((c & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
+        recs[(size_t)b * dm.Npts + slot] = make_int2(key, wbits);
+      }
+      if (pix_recs) stage[lane * Dp + d] = make_int2(c, wbits);
+    }
+  }
+  if (!pix_recs) return;
+  __syncthreads();
+  const int valid = min(32, dm.HW - rc0);
+  int2* dst = pix_recs + ((size_t)(b * dm.N + n) * dm.HW + rc0) * dm.D;
+  for (int r = dg; r < valid; r += 8)
+    for (int d = lane; d < dm.D; d += 32) dst[(size_t)r * dm.D + d] = stage[r * Dp + d];
+}
+
+int ls_launch_place(const int* cell, const int* within, const void* prob, int dtype, const LsDims& dm,
+                    const LsGrid& g, const int* seg_start, int2* recs, int2* pix_recs, cudaStream_t s) {
+  dim3 grid((dm.HW + 31) / 32, dm.N, dm.B);
+  const size_t smem = pix_recs ? (size_t)32 * (dm.D | 1) * sizeof(int2) : 0;
+  if (smem > 48 * 1024) return LS_ERR_UNSUPPORTED;
+  if (dtype == LS_F32)
+    ls_place_kernel<float><<<grid, 256, smem, s>>>(cell, within, (const float*)prob, dm, g, seg_start, recs, pix_recs);
+  else
+    ls_place_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(cell, within, (const __nv_bfloat16*)prob, dm, g,
+                                                            seg_start, recs, pix_recs);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// (row-major rank, point count) of every cell of sample b, from the CSR (test export)
+__global__ void ls_export_cell_counts_kernel(const int* __restrict__ seg_start, LsGrid grid, int b,
+                                             long long* __restrict__ out) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= grid.Vc) return;
+  const int* seg = seg_start + (size_t)b * grid.seg_stride;
+  const int r = ls_rank_of_cell(cell, grid);
+  const int k = seg[cell + 1] - seg[cell];
+  out[2 * (size_t)cell + 0] = (r >= 0 && k > 0) ? r : 0;
+  out[2 * (size_t)cell + 1] = (r >= 0) ? k : 0;
+}
+
+int ls_launch_export_cell_counts(const int* seg_start, const LsGrid& g, int B, int b, long long* out, int* kept,
+                                 cudaStream_t s) {
+  if (out) {
+    ls_export_cell_counts_kernel<<<(g.Vc + 255) / 256, 256, 0, s>>>(seg_start, g, b, out);
+    LS_LAUNCHED();
+  }
+  if (kept) {
+    LS_CUDA(cudaMemcpy2DAsync(kept, sizeof(int), seg_start + g.Vc, (size_t)g.seg_stride * sizeof(int), sizeof(int), B,
+                              cudaMemcpyDeviceToDevice, s));
+    ls_note_launch();
+  }
+  return LS_OK;
+}

@@ -1,0 +1,31 @@
+// Host-side launchers shared between translation units (not part of the C ABI).
+#pragma once
+#include "ls_common.cuh"
+
+// ls_index.cu
+int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s);
+int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
+                    int* rank, int* cell, int* within, int* counts, cudaStream_t s);
+int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
+                     float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s);
+int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, cudaStream_t s);
+int ls_launch_place(const int* cell, const int* within, const void* prob, int dtype, const LsDims& dm,
+                    const LsGrid& g, const int* seg_start, int2* recs, int2* pix_recs, cudaStream_t s);
+int ls_launch_export_cell_counts(const int* seg_start, const LsGrid& g, int B, int b, long long* out, int* kept,
+                                 cudaStream_t s);
+
+// ls_dense.cu
+int ls_launch_softmax(const void* logits, int dtype, const LsDims& dm, void* prob, cudaStream_t s);
+int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* gext, int dtype, const LsDims& dm,
+                          void* glogits, cudaStream_t s);
+// [images][C][HW] -> [images][HW][Cp] (zero padded) and back (drops the padding)
+int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
+int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
+
+// ls_splat.cu
+int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, int2* recs_sorted,
+                        const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
+int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
+                            const LsGrid& g, float* gT, cudaStream_t s);
+int ls_launch_bwd_gather(const float* gT, const void* featT, int dtype, const int2* pix_recs, const LsDims& dm,
+                         const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s);

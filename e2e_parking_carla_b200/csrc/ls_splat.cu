@@ -1,0 +1,399 @@
+// The splat itself: deterministic ranked segment-reduce (forward) and its gradient
+// (cell-major gradient staging + pixel-stationary gather).  Reference semantics:
+// model/bev_model.py:66-72,99-105 and VoxelsSumming (tool/geometry.py:285-317).
+#include "ls_internal.h"
+
+#define LS_WIN 8   // points whose feature rows a half-warp keeps in flight
+
+__device__ __forceinline__ unsigned ls_half_mask() { return 0xFFFFu << (threadIdx.x & 16); }
+
+struct LsTileGeom {
+  int cc;       // channels of this pass (<= 64, multiple of 4)
+  int nqp;      // quads per smem row rounded to a power of two
+  int stride;   // smem row stride in floats = 4*nqp + 4
+};
+__host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
+  LsTileGeom t;
+  t.cc = Cp < LS_CCHUNK ? Cp : LS_CCHUNK;
+  int nq = t.cc / 4;
+  t.nqp = 1;
+  while (t.nqp < nq) t.nqp <<= 1;
+  t.stride = 4 * t.nqp + 4;
+  return t;
+}
+
+// =====================================================================================
+// K3: forward splat.  One CTA per (sample, 16x16-voxel tile), three phases:
+//  A  canonicalise: one thread per point record of the tile; its position inside its cell =
+//     number of records of that cell with a smaller key (keys are unique), which makes the
+//     summation order independent of the atomics that placed the records.  The re-ordered
+//     records (feature row offset, prob) go to a scratch array.
+//  B  reduce: a half-warp owns 16 consecutive cells (one x-row of the tile) = one contiguous
+//     run of records; it streams them with LS_WIN feature rows (16 B per lane, 256 B per point)
+//     in flight, accumulates prob*feat in registers and drops each finished cell into the
+//     shared-memory tile [cell][channel] (swizzled, conflict-free).
+//  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
+//     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
+// =====================================================================================
+template <typename T, bool VEC4>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
+                    int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid, float* __restrict__ bev,
+                    LsBevStrides st) {
+  extern __shared__ float smem[];
+  const LsTileGeom tg = ls_tile_geom(dm.Cp);
+  float* tile = smem;                                               // [LS_TILE][tg.stride]
+  int* seg = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);    // [LS_TILE + 1]
+
+  const int b = blockIdx.y, tile_id = blockIdx.x, tid = threadIdx.x;
+  const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
+  const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
+  __syncthreads();
+  const int s0 = seg[0], s1 = seg[LS_TILE];
+  const bool tile_empty = (s0 == s1);
+  const int2* rin = recs + (size_t)b * dm.Npts;
+  int2* rso = recs_sorted + (size_t)b * dm.Npts;
+
+  // ---- phase A ----------------------------------------------------------------------
+  if (!tile_empty) {
+    for (int i = s0 + tid; i < s1; i += LS_THREADS) {
+      const int2 r = rin[i];
+      const int cl = (unsigned)r.x >> 24;
+      const int a = seg[cl], e = seg[cl + 1];
+      int pos = a;
+      for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
+      const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
+      rso[pos] = make_int2(pix * dm.Cp, r.y);
+    }
+    __syncthreads();   // scratch records written by this CTA are visible to this CTA
+  }
+
+  const int hw = tid >> 4, hl = tid & 15;
+  const unsigned hmask = ls_half_mask();
+  const T* fbase = featT + (size_t)b * dm.N * dm.HW * dm.Cp;
+
+  for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
+    const int cc = min(tg.cc, dm.Cp - cbase);
+    // ---- phase B --------------------------------------------------------------------
+    if (!tile_empty) {
+      const bool lane_on = 4 * hl < cc;
+      const T* fb = fbase + cbase + 4 * hl;
+      int cl = hw * 16;
+      const int cl_end = cl + 16;
+      int i = seg[cl];
+      const int iend = seg[cl_end];
+      int next_b = seg[cl + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      while (i < iend) {
+        const int n = min(LS_WIN, iend - i);
+        int2 r = make_int2(0, 0);
+        if (hl < n) r = rso[i + hl];
+        float4 f[LS_WIN];
+        float w[LS_WIN];
+#pragma unroll
+        for (int u = 0; u < LS_WIN; ++u) {
+          const int off = __shfl_sync(hmask, r.x, u, 16);
+          w[u] = __int_as_float(__shfl_sync(hmask, r.y, u, 16));
+          f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < n && lane_on) f[u] = ls_load4<T>(fb + off);
+        }
+#pragma unroll
+        for (int u = 0; u < LS_WIN; ++u) {
+          if (u < n) {
+            while (i + u >= next_b) {      // the run moved on to the next (possibly empty) cell
+              if (lane_on)
+                *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              ++cl;
+              next_b = seg[cl + 1];
+            }
+            acc.x = fmaf(w[u], f[u].x, acc.x);
+            acc.y = fmaf(w[u], f[u].y, acc.y);
+            acc.z = fmaf(w[u], f[u].z, acc.z);
+            acc.w = fmaf(w[u], f[u].w, acc.w);
+          }
+        }
+        i += n;
+      }
+      for (; cl < cl_end; ++cl) {
+        if (lane_on) *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    // ---- phase C --------------------------------------------------------------------
+    const int nquads = (cc + 3) / 4;
+    if (VEC4) {
+      for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
+        const int y4 = idx & 3, cq = (idx >> 2) & 3, x = (idx >> 4) & 15, q = idx >> 8;
+        const int c = cbase + 4 * q + cq;
+        const int gx = tx0 + x, gy = ty0 + 4 * y4;
+        if (c < dm.C && gx < grid.X && gy < grid.Y) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!tile_empty) {
+            const int cl = x * LS_TY + 4 * y4;
+            const float* src = tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp) + cq;
+            v.x = src[0]; v.y = src[tg.stride]; v.z = src[2 * tg.stride]; v.w = src[3 * tg.stride];
+          }
+          *reinterpret_cast<float4*>(bev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy) = v;
+        }
+      }
+    } else {
+      for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
+        const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
+        const int c = cbase + cr;
+        const int gx = tx0 + x, gy = ty0 + y;
+        if (c < dm.C && gx < grid.X && gy < grid.Y) {
+          const int cl = x * LS_TY + y;
+          const float v = tile_empty ? 0.0f
+                                     : tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)];
+          bev[(size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t ls_tile_smem_bytes(const LsDims& dm) {
+  const LsTileGeom tg = ls_tile_geom(dm.Cp);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 1) * sizeof(int);
+}
+static size_t ls_tile_smem_max() {
+  LsDims d;
+  d.Cp = LS_CCHUNK;
+  return ls_tile_smem_bytes(d);
+}
+
+static bool ls_bev_vec4(const float* p, const LsBevStrides& st, const LsGrid& g) {
+  return ((uintptr_t)p % 16 == 0) && (st.b % 4 == 0) && (st.c % 4 == 0) && (st.x % 4 == 0) && (g.Y % 4 == 0);
+}
+
+int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, int2* recs_sorted,
+                        const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int m = (int)ls_tile_smem_max();
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<__nv_bfloat16, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<__nv_bfloat16, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    attr_done = true;
+  }
+  const size_t smem = ls_tile_smem_bytes(dm);
+  dim3 grid(g.tiles, dm.B);
+  const bool v4 = ls_bev_vec4(bev, st, g);
+#define LS_SPLAT(TT, VV)                                                                                   \
+  ls_splat_fwd_kernel<TT, VV><<<grid, LS_THREADS, smem, s>>>((const TT*)featT, recs, seg_start, recs_sorted, dm, g, \
+                                                             bev, st)
+  if (dtype == LS_F32) { if (v4) LS_SPLAT(float, true); else LS_SPLAT(float, false); }
+  else { if (v4) LS_SPLAT(__nv_bfloat16, true); else LS_SPLAT(__nv_bfloat16, false); }
+#undef LS_SPLAT
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
+// (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
+// =====================================================================================
+template <bool VEC4>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const int* __restrict__ seg_start,
+                        LsDims dm, LsGrid grid, float* __restrict__ gT) {
+  extern __shared__ float smem[];
+  const LsTileGeom tg = ls_tile_geom(dm.Cp);
+  float* tile = smem;
+  int* seg = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);
+  const int b = blockIdx.y, tile_id = blockIdx.x, tid = threadIdx.x;
+  const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
+  const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
+  __syncthreads();
+  if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
+  float* dst = gT + ((size_t)b * grid.Vc + (size_t)tile_id * LS_TILE) * dm.Cp;
+  for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
+    const int cc = min(tg.cc, dm.Cp - cbase);
+    const int nquads = (cc + 3) / 4;
+    if (VEC4) {
+      for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
+        const int y4 = idx & 3, cq = (idx >> 2) & 3, x = (idx >> 4) & 15, q = idx >> 8;
+        const int c = cbase + 4 * q + cq;
+        const int gx = tx0 + x, gy = ty0 + 4 * y4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < dm.C && gx < grid.X && gy < grid.Y)
+          v = __ldg(reinterpret_cast<const float4*>(gbev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy));
+        const int cl = x * LS_TY + 4 * y4;
+        float* d = tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp) + cq;
+        d[0] = v.x; d[tg.stride] = v.y; d[2 * tg.stride] = v.z; d[3 * tg.stride] = v.w;
+      }
+    } else {
+      for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
+        const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
+        const int c = cbase + cr;
+        const int gx = tx0 + x, gy = ty0 + y;
+        float v = 0.0f;
+        if (c < dm.C && gx < grid.X && gy < grid.Y)
+          v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy];
+        const int cl = x * LS_TY + y;
+        tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
+      const int q = idx % nquads, cl = idx / nquads;
+      if (seg[cl + 1] != seg[cl])
+        *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + cbase + 4 * q) =
+            *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
+    }
+    __syncthreads();
+  }
+}
+
+int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
+                            const LsGrid& g, float* gT, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int m = (int)ls_tile_smem_max();
+    LS_CUDA(cudaFuncSetAttribute(ls_bwd_transpose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_bwd_transpose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    attr_done = true;
+  }
+  const size_t smem = ls_tile_smem_bytes(dm);
+  dim3 grid(g.tiles, dm.B);
+  if (ls_bev_vec4(gbev, st, g))
+    ls_bwd_transpose_kernel<true><<<grid, LS_THREADS, smem, s>>>(gbev, st, seg_start, dm, g, gT);
+  else
+    ls_bwd_transpose_kernel<false><<<grid, LS_THREADS, smem, s>>>(gbev, st, seg_start, dm, g, gT);
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+// =====================================================================================
+// K4b: gradient gather, pixel-stationary (deterministic, no atomics).
+// reference: VoxelsSumming.backward tool/geometry.py:307-317 + autograd of
+// model/bev_model.py:66,91-97.  CTA = one feature-map column of one camera (its rays sweep one
+// radial line of the BEV, so the cell-major gradient rows it gathers are re-used from L1);
+// a half-warp owns a pixel: 16 lanes x float4 channels, depth bins in windows of 16:
+//   gf[c]  += prob[d] * g[cell(d), c]                     (registers, d ascending)
+//   gp[d]   = sum_c feat[c] * g[cell(d), c]               (16 dots reduced together by a
+//                                                          transposing butterfly: 15 shuffles)
+// Outputs: grad_feat NHWC-padded [pix][Cp] and grad_prob PIXEL-major [pix][D].
+// =====================================================================================
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
+                     LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+  const int col = blockIdx.x, bn = blockIdx.y;
+  const int b = bn / dm.N;
+  const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const unsigned hmask = ls_half_mask();
+  const float* gTb = gT + (size_t)b * grid.Vc * dm.Cp + 4 * hl;
+  bool on[NCH];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) on[q] = (q * LS_CCHUNK + 4 * hl) < dm.Cp;
+
+  for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
+    const size_t pix = (size_t)bn * dm.HW + (size_t)row * dm.fw + col;
+    const T* frow = featT + pix * dm.Cp + 4 * hl;
+    float4 f[NCH], gf[NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+      f[q] = on[q] ? ls_load4<T>(frow + q * LS_CCHUNK) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int2* pr = pix_recs + pix * dm.D;
+    for (int d0 = 0; d0 < dm.D; d0 += 16) {
+      const int n = min(16, dm.D - d0);
+      int2 r = make_int2(-1, 0);
+      if (hl < n) r = __ldg(pr + d0 + hl);
+      float dot[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) dot[u] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        float4 g[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int cell = __shfl_sync(hmask, r.x, u, 16);
+          g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cell >= 0 && on[q])
+            g[u] = __ldg(reinterpret_cast<const float4*>(gTb + (size_t)cell * dm.Cp + q * LS_CCHUNK));
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float w = __int_as_float(__shfl_sync(hmask, r.y, u, 16));
+          dot[u] = fmaf(f[q].x, g[u].x, dot[u]);
+          dot[u] = fmaf(f[q].y, g[u].y, dot[u]);
+          dot[u] = fmaf(f[q].z, g[u].z, dot[u]);
+          dot[u] = fmaf(f[q].w, g[u].w, dot[u]);
+          gf[q].x = fmaf(w, g[u].x, gf[q].x);
+          gf[q].y = fmaf(w, g[u].y, gf[q].y);
+          gf[q].z = fmaf(w, g[u].z, gf[q].z);
+          gf[q].w = fmaf(w, g[u].w, gf[q].w);
+        }
+      }
+      // transposing butterfly: lane hl ends up with sum over the 16 lanes of dot[hl]
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool hi = hl & 8;
+        const float send = hi ? dot[u] : dot[u + 8];
+        const float keep = hi ? dot[u + 8] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool hi = hl & 4;
+        const float send = hi ? dot[u] : dot[u + 4];
+        const float keep = hi ? dot[u + 4] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool hi = hl & 2;
+        const float send = hi ? dot[u] : dot[u + 2];
+        const float keep = hi ? dot[u + 2] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 2, 16);
+      }
+      {
+        const bool hi = hl & 1;
+        const float send = hi ? dot[0] : dot[1];
+        const float keep = hi ? dot[1] : dot[0];
+        dot[0] = keep + __shfl_xor_sync(hmask, send, 1, 16);
+      }
+      if (hl < n) gprob_pm[pix * dm.D + d0 + hl] = dot[0];
+    }
+    T* grow = gfeatT + pix * dm.Cp + 4 * hl;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+      if (on[q]) ls_store4<T>(grow + q * LS_CCHUNK, gf[q]);
+  }
+}
+
+template <typename T>
+static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pix_recs, const LsDims& dm,
+                              const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
+  const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
+  dim3 grid(dm.fw, dm.B * dm.N);
+#define LS_GATHER(NCH) \
+  ls_bwd_gather_kernel<T, NCH><<<grid, LS_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, gprob_pm, (T*)gfeatT)
+  switch (nch) {
+    case 1: LS_GATHER(1); break;
+    case 2: LS_GATHER(2); break;
+    case 3: LS_GATHER(3); break;
+    case 4: LS_GATHER(4); break;
+    default: return LS_ERR_UNSUPPORTED;
+  }
+#undef LS_GATHER
+  LS_LAUNCHED();
+  return LS_OK;
+}
+
+int ls_launch_bwd_gather(const float* gT, const void* featT, int dtype, const int2* pix_recs, const LsDims& dm,
+                         const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
+  if (dtype == LS_F32) return ls_gather_dispatch<float>(gT, featT, pix_recs, dm, g, gprob_pm, gfeatT, s);
+  return ls_gather_dispatch<__nv_bfloat16>(gT, featT, pix_recs, dm, g, gprob_pm, gfeatT, s);
+}

@@ -68,10 +68,16 @@ def _bev_strides(t: torch.Tensor) -> LsBevStrides:
     return LsBevStrides(t.stride(0), t.stride(1), t.stride(2))
 
 
-def grid_cells(shape: LsShape) -> Tuple[int, int]:
-    tiles, cells = C.c_int32(), C.c_int32()
-    check(_lib.load().ls_grid_cells(C.byref(shape), C.byref(tiles), C.byref(cells)), "ls_grid_cells")
-    return tiles.value, cells.value
+def grid_cells(shape: LsShape) -> Tuple[int, int, int]:
+    """(tiles, padded cell count, seg_start row stride) of the internal BEV tiling."""
+    tiles, cells, stride = C.c_int32(), C.c_int32(), C.c_int32()
+    check(_lib.load().ls_grid_cells(C.byref(shape), C.byref(tiles), C.byref(cells), C.byref(stride)),
+          "ls_grid_cells")
+    return tiles.value, cells.value, stride.value
+
+
+def padded_channels(c: int) -> int:
+    return int(_lib.load().ls_padded_channels(c))
 
 
 # --------------------------------------------------------------------------------------
@@ -99,17 +105,21 @@ def geometry(M, t, frustum, shape: LsShape) -> torch.Tensor:
     return geom
 
 
-def index(M, t, frustum, shape: LsShape, with_hist: bool = False):
-    """rank i32[B,Npts] (-1 dropped) and optionally the per-cell histogram."""
+def index(M, t, frustum, shape: LsShape, for_sort: bool = False):
+    """rank i32[B,Npts] (-1 dropped); with ``for_sort`` also (cell, within, counts)."""
     _need_cuda(M, t, frustum)
     npts = shape.N * shape.D * shape.fh * shape.fw
-    rank = torch.empty(shape.B, npts, dtype=torch.int32, device=M.device)
-    counts = None
-    if with_hist:
-        counts = torch.zeros(shape.B, grid_cells(shape)[1], dtype=torch.int32, device=M.device)
+    dev = M.device
+    rank = torch.empty(shape.B, npts, dtype=torch.int32, device=dev)
+    cell = within = counts = None
+    if for_sort:
+        cell = torch.empty_like(rank)
+        within = torch.empty_like(rank)
+        counts = torch.zeros(shape.B, grid_cells(shape)[1], dtype=torch.int32, device=dev)
     check(_lib.load().ls_index(_ptr(M.contiguous()), _ptr(t.contiguous()), _ptr(frustum.contiguous()),
-                               C.byref(shape), _ptr(rank), _ptr(counts), _stream(M)), "ls_index")
-    return (rank, counts) if with_hist else rank
+                               C.byref(shape), _ptr(rank), _ptr(cell), _ptr(within), _ptr(counts), _stream(M)),
+          "ls_index")
+    return (rank, cell, within, counts) if for_sort else rank
 
 
 def export_indices(M, t, frustum, shape: LsShape):
@@ -127,18 +137,31 @@ def export_indices(M, t, frustum, shape: LsShape):
     return vox, keep.bool(), rank
 
 
-def sort(rank: torch.Tensor, shape: LsShape, counts: Optional[torch.Tensor] = None):
-    """(seg_start i32[B,cells+1], order i32[B,Npts]) - counting sort by cell."""
-    _need_cuda(rank)
-    cells = grid_cells(shape)[1]
-    have = counts is not None
-    if counts is None:
-        counts = torch.empty(shape.B, cells, dtype=torch.int32, device=rank.device)
-    seg = torch.empty(shape.B, cells + 1, dtype=torch.int32, device=rank.device)
-    order = torch.empty_like(rank)
-    check(_lib.load().ls_sort(_ptr(rank), C.byref(shape), _ptr(counts), int(have), _ptr(seg), _ptr(order),
-                              _stream(rank)), "ls_sort")
-    return seg, order
+def softmax(logits: torch.Tensor, shape: LsShape) -> torch.Tensor:
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    prob = torch.empty_like(logits)
+    check(_lib.load().ls_softmax(_ptr(logits), _dtype_code(logits), C.byref(shape), _ptr(prob), _stream(logits)),
+          "ls_softmax")
+    return prob
+
+
+def sort(cell, within, counts, prob, shape: LsShape, with_pixel_index: bool = False):
+    """Counting sort by cell: (seg_start i32[B,seg_stride], recs i32[B,Npts,2] = {key, prob
+    bits}, pix_recs i32[B*N*HW, D, 2] or None)."""
+    _need_cuda(cell, within, counts, prob)
+    _, _, stride = grid_cells(shape)
+    dev = cell.device
+    npts = cell.shape[1]
+    seg = torch.empty(shape.B, stride, dtype=torch.int32, device=dev)
+    recs = torch.zeros(shape.B, npts, 2, dtype=torch.int32, device=dev)
+    pix = None
+    if with_pixel_index:
+        pix = torch.empty(shape.B * shape.N * shape.fh * shape.fw, shape.D, 2, dtype=torch.int32, device=dev)
+    prob = prob.contiguous()
+    check(_lib.load().ls_sort(_ptr(cell), _ptr(within), _ptr(counts), _ptr(prob), _dtype_code(prob), C.byref(shape),
+                              _ptr(seg), _ptr(recs), _ptr(pix), _stream(cell)), "ls_sort")
+    return seg, recs, pix
 
 
 def export_sorted_ranks(seg_start: torch.Tensor, shape: LsShape, b: int) -> torch.Tensor:
@@ -162,7 +185,7 @@ def kept_counts(seg_start: torch.Tensor, shape: LsShape) -> torch.Tensor:
 def workspace_bytes(shape: LsShape, dtype_code: int, with_backward: bool) -> int:
     n = _lib.load().ls_workspace_bytes(C.byref(shape), dtype_code, int(with_backward))
     if n == 0:
-        raise ValueError("unsupported lift-splat shape (need Z == 1, even C <= 256)")
+        raise ValueError("unsupported lift-splat shape (need Z == 1, C <= 256, N*fh*fw*2^ceil(log2 D) <= 2^24)")
     return n
 
 
@@ -191,7 +214,8 @@ class LiftSplatFunction(torch.autograd.Function):
         st = _bev_strides(bev)
         check(_lib.load().ls_forward(_ptr(feat_c), _ptr(logits_c), code, _ptr(M.contiguous()),
                                      _ptr(t.contiguous()), _ptr(frustum.contiguous()), C.byref(shape), _ptr(ws),
-                                     ws.numel(), _ptr(bev), C.byref(st), _ptr(prob), _stream(feat)), "ls_forward")
+                                     ws.numel(), int(need_bwd), _ptr(bev), C.byref(st), _ptr(prob), _stream(feat)),
+              "ls_forward")
         ctx.shape, ctx.code, ctx.ws = shape, code, ws
         ctx.feat_shape, ctx.logits_shape = feat.shape, logits.shape
         ctx.save_for_backward(prob)

@@ -59,9 +59,12 @@ const char* ls_version(void);
 const char* ls_strerror(int status);
 const char* ls_last_cuda_error(void);
 
-/* Internal BEV tiling: the grid is cut in tiles of tile_x * tile_y voxels; cells are
- * numbered tile-major.  cells_padded = tiles * tile_x * tile_y  (>= X*Y). */
-int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded);
+/* Internal BEV tiling: the grid is cut in 16 x 16-voxel tiles; cells are numbered
+ * tile-major.  cells_padded = tiles * 256 (>= X*Y); seg_stride = row stride of seg_start. */
+int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32_t* seg_stride);
+
+/* Channel count of the internal NHWC staging rows: C rounded up to a multiple of 4. */
+int32_t ls_padded_channels(int32_t C);
 
 /* a4 first half - model/bev_model.py:46-47,53:  E^-1 = inverse(extrinsics),
  * M = E^-1[:3,:3] . inverse(intrinsics),  t = E^-1[:3,3].
@@ -78,11 +81,13 @@ int ls_geometry(const float* M, const float* t, const float* frustum, const LsSh
                 float* geom, ls_stream_t stream);
 
 /* a4+a6.1-a6.3 fused - model/bev_model.py:49-55,85-95: per-point voxel index in
- * registers, keep test, rank.  rank i32[B,Npts] (-1 = dropped), may be NULL.
- * counts i32[B,cells_padded] (may be NULL): per-cell histogram, accumulated with
- * integer atomics - must be zero on entry. */
+ * registers, keep test, rank.
+ *   rank   i32[B,Npts]  reference rank, -1 = dropped (may be NULL)
+ *   cell   i32[B,Npts]  tile-major cell id, -1 = dropped       } all three or none;
+ *   within i32[B,Npts]  ticket of the point inside its cell    } counts must be zero
+ *   counts i32[B,cells_padded] per-cell histogram (int atomics)} on entry            */
 int ls_index(const float* M, const float* t, const float* frustum, const LsShape* s,
-             int32_t* rank, int32_t* counts, ls_stream_t stream);
+             int32_t* rank, int32_t* cell, int32_t* within, int32_t* counts, ls_stream_t stream);
 
 /* Debug/test export in the reference's own convention (model/bev_model.py:85-97):
  * vox i64[B,Npts,3] = .long() of the voxel coordinate (INT64_MIN where x86 gives
@@ -91,14 +96,15 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
                       int64_t* vox, uint8_t* keep, int64_t* rank, ls_stream_t stream);
 
 /* a6.3 - model/bev_model.py:96-97 (argsort + gathers) and the segment boundaries of
- * tool/geometry.py:295-296, as a counting sort by cell.
- * counts: the histogram from ls_index (have_hist=1) or scratch (have_hist=0, then it
- * is zeroed and built here).  Outputs: seg_start i32[B,cells_padded+1] (CSR offsets
- * into order), order i32[B,Npts] (point ids grouped by cell; entries past the kept
- * count are unspecified).  The order of ids inside one cell is made canonical
- * (ascending) by the consumer, ls_splat_fwd. */
-int ls_sort(const int32_t* rank, const LsShape* s, int32_t* counts, int have_hist,
-            int32_t* seg_start, int32_t* order, ls_stream_t stream);
+ * tool/geometry.py:295-296, as a counting sort by cell: exclusive scan of counts ->
+ * seg_start i32[B,seg_stride] (CSR offsets, entry [cells_padded] = kept count), then every
+ * kept point writes an 8-byte record {key, prob bits} to recs[B,Npts] at
+ * seg_start[cell] + within;  key = cell_in_tile << 24 | (pixel << ceil(log2 D) | d).
+ * pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell, prob bits} per depth bin of every
+ * pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
+int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
+            int dtype, const LsShape* s, int32_t* seg_start, void* recs, void* pix_recs,
+            ls_stream_t stream);
 
 /* Test export: for sample b, out i64[cells_padded,2] = (row-major rank, number of kept
  * points) of every cell, zeros for empty / padding cells; from it the reference's
@@ -112,7 +118,8 @@ int ls_export_cell_counts(const int32_t* seg_start, const LsShape* s, int32_t b,
  * logits/prob: [B*N, D, fh, fw] of `dtype`. */
 int ls_softmax(const void* logits, int dtype, const LsShape* s, void* prob, ls_stream_t stream);
 
-/* Layout helpers: [images, C, HW] <-> [images, HW, C]  (coalesced smem transposes). */
+/* Layout staging: [images, C, HW] -> [images, HW, Cp] (Cp = ls_padded_channels(C), zero
+ * padded) and back (padding dropped); coalesced shared-memory transposes. */
 int ls_nchw_to_nhwc(const void* src, int dtype, int32_t images, int32_t C, int32_t HW,
                     void* dst, ls_stream_t stream);
 int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32_t HW,
@@ -121,33 +128,35 @@ int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32
 /* a5(outer product)+a6.4-a6.5 fused - model/bev_model.py:66-72,99-105 and
  * VoxelsSumming.forward (tool/geometry.py:289-305): deterministic segment sum of
  * prob[p]*feat[pix(p),:] per cell, written (zeros included) to bev f32[B,C,X,Y].
- * feat_nhwc: [B*N, fh, fw, C] of `dtype`; prob: [B*N, D, fh, fw] of `dtype`.
- * order_tmp i32[B,Npts]: scratch used to canonicalise cells with >32 points. */
-int ls_splat_fwd(const void* feat_nhwc, const void* prob, int dtype, const int32_t* order,
-                 const int32_t* seg_start, int32_t* order_tmp, const LsShape* s, float* bev,
-                 const LsBevStrides* bev_strides, ls_stream_t stream);
+ * feat_nhwc: [B*N, fh, fw, Cp] of `dtype`; recs/seg_start from ls_sort;
+ * recs_scratch: 8 B x [B,Npts], receives the records re-ordered by key inside each cell
+ * (this is what makes the sums independent of the atomics' arrival order). */
+int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start,
+                 void* recs_scratch, const LsShape* s, float* bev, const LsBevStrides* bev_strides,
+                 ls_stream_t stream);
 
 /* a7 + autograd of a5/a6 - VoxelsSumming.backward (tool/geometry.py:307-317) and the
  * backward of the outer product: every kept point receives its cell's gradient;
  *   grad_prob[p]      = sum_c feat[pix,c] * g[c, cell(p)]
  *   grad_feat[pix, c] = sum_d prob[d,pix] * g[c, cell(d,pix)]      (pixel-stationary,
  * no atomics, fixed order).  grad_bev f32 [B,C,X,Y] with strides; gT_ws
- * f32[B,cells_padded,C] scratch; grad_prob f32[B*N,D,fh,fw] (always float);
- * grad_feat_nhwc [B*N,fh,fw,C] of `dtype`. */
+ * f32[B,cells_padded,Cp] scratch (cell-major gradient); outputs grad_prob_pm
+ * f32[B*N*fh*fw, D] (PIXEL-major, consumed by ls_softmax_bwd) and grad_feat_nhwc
+ * [B*N,fh,fw,Cp] of `dtype`. */
 int ls_splat_bwd(const float* grad_bev, const LsBevStrides* grad_strides, const void* feat_nhwc,
-                 const void* prob, int dtype, const int32_t* rank, const LsShape* s, float* gT_ws,
-                 float* grad_prob, void* grad_feat_nhwc, ls_stream_t stream);
+                 int dtype, const void* pix_recs, const int32_t* seg_start, const LsShape* s,
+                 float* gT_ws, float* grad_prob_pm, void* grad_feat_nhwc, ls_stream_t stream);
 
 /* backward of a5's softmax (model/bev_model.py:64): grad_logits = prob * (g - sum_d prob*g),
- * g = grad_prob (+ grad_prob_ext: the gradient arriving on the returned pred_depth,
- * `dtype`, may be NULL). */
-int ls_softmax_bwd(const void* prob, const float* grad_prob, const void* grad_prob_ext, int dtype,
+ * g = grad_prob_pm (pixel-major, from ls_splat_bwd) + grad_prob_ext (the gradient arriving
+ * on the returned pred_depth, [B*N,D,fh,fw] of `dtype`, may be NULL). */
+int ls_softmax_bwd(const void* prob, const float* grad_prob_pm, const void* grad_prob_ext, int dtype,
                    const LsShape* s, void* grad_logits, ls_stream_t stream);
 
 /* ---- one-call pipelines (what BevModel.calc_bev_feature uses) -------------------
  * Workspace: one device blob, >= ls_workspace_bytes(); it carries what backward needs
- * (rank, NHWC features), so keep it alive and untouched between ls_forward and
- * ls_backward of the same step. */
+ * (NHWC features, CSR offsets, pixel-major index), so keep it alive and untouched between
+ * ls_forward(with_backward=1) and ls_backward of the same step. */
 size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward);
 
 /* feat [B*N,C,fh,fw], logits [B*N,D,fh,fw] of `dtype` (contiguous NCHW, as CamEncoder
@@ -155,8 +164,8 @@ size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward);
  * caller's own torch.inverse; frustum f32[D,fh,fw,3] (BevModel.frustum).
  * Outputs: bev f32[B,C,X,Y] (strided), prob [B*N,D,fh,fw] of `dtype` (= pred_depth). */
 int ls_forward(const void* feat, const void* logits, int dtype, const float* M, const float* t,
-               const float* frustum, const LsShape* s, void* ws, size_t ws_bytes, float* bev,
-               const LsBevStrides* bev_strides, void* prob, ls_stream_t stream);
+               const float* frustum, const LsShape* s, void* ws, size_t ws_bytes, int with_backward,
+               float* bev, const LsBevStrides* bev_strides, void* prob, ls_stream_t stream);
 
 /* grad_bev f32 (strided), grad_prob_ext (`dtype`, may be NULL), prob = forward's output.
  * Outputs grad_feat [B*N,C,fh,fw], grad_logits [B*N,D,fh,fw] of `dtype`. */

@@ -98,23 +98,36 @@ def test_sorted_ranks_bit_exact(lib, name):
     ls = _ls()
     g = Golden(name)
     s = _ls_shape(g.shape)
-    rank, counts = ls.index(_dev(g["M_ref"]), _dev(g["t_ref"]), _dev(frustum_of(g.shape)), s, with_hist=True)
-    seg, order = ls.sort(rank, s, counts)
-    assert int(counts.abs().sum()) == 0, "placement must leave the histogram zeroed"
+    sh = g.shape
+    rank, cell, within, counts = ls.index(_dev(g["M_ref"]), _dev(g["t_ref"]), _dev(frustum_of(sh)), s, for_sort=True)
+    assert np.array_equal(rank.cpu().numpy(), g["rank_ref"])
+    assert torch.equal(cell >= 0, rank >= 0)
+    _, logits, _, _ = g.inputs()
+    prob = ls.softmax(logits.to(DEV), s)
+    seg, recs, pix = ls.sort(cell, within, counts, prob, s, with_pixel_index=True)
     kept = ls.kept_counts(seg, s).cpu().numpy()
     assert np.array_equal(kept, g["kept_per_cam"].sum(-1))
-    for b in range(g.shape.batch):
+    hw, D = sh.fh * sh.fw, sh.depth_bins
+    dbits = int(np.ceil(np.log2(D)))
+    for b in range(sh.batch):
         sr = ls.export_sorted_ranks(seg, s, b).cpu().numpy()
         assert sr.dtype == np.int64
         assert sha(sr) == str(g["sorted_rank_sha"][b])
         assert np.unique(sr).size == int(g["segments"][b])
-        # order is a permutation of exactly the kept point ids, grouped by cell
-        o = order[b, :kept[b]].cpu().numpy()
+        # the records are a permutation of exactly the kept points, each carrying its prob
+        key = recs[b, :kept[b], 0].cpu().numpy().astype(np.int64) & 0xFFFFFF
+        pixel, d = key >> dbits, key & ((1 << dbits) - 1)
+        n, rc = pixel // hw, pixel % hw
+        p = (n * D + d) * hw + rc
         r = g["rank_ref"][b]
-        assert np.array_equal(np.sort(o), np.nonzero(r >= 0)[0])
-    # same CSR without the fused histogram
-    seg2, _ = ls.sort(rank, s, None)
-    assert torch.equal(seg, seg2)
+        assert np.array_equal(np.sort(p), np.nonzero(r >= 0)[0])
+        w = recs[b, :kept[b], 1].cpu().numpy().view(np.float32)
+        assert np.array_equal(w, prob.view(sh.batch, -1)[b].cpu().numpy()[p])
+    # pixel-major index: {cell, prob} of every depth bin of every pixel
+    pc = pix[..., 0].view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
+    assert torch.equal(pc, cell)
+    pw = pix[..., 1].contiguous().view(torch.float32).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2)
+    assert torch.equal(pw.reshape(-1), prob.view(sh.batch, sh.cams, D, hw).reshape(-1))
 
 
 def test_camera_transform_bit_exact_vs_oracle(lib):
