@@ -232,7 +232,7 @@ class Stepper:
         recs2 = torch.empty_like(recs)
         pix = torch.empty(sh.batch * sh.cams * sh.fh * sh.fw, sh.depth_bins, 2, dtype=torch.int32, device=dev)
         featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, cp, dtype=self.dtype, device=dev)
-        gT = torch.empty(sh.batch, cells, cp, device=dev)
+        gT = torch.empty(sh.batch, cells + 1, cp, device=dev)
         gprob = torch.empty(sh.batch * npts, device=dev)
         gfeatT = torch.empty_like(featT)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

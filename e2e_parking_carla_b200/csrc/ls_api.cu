@@ -31,6 +31,7 @@ static int ls_check_splat_shape(const LsShape* s) {
   LsDims dm = ls_dims(s);
   // sort key: 8 bits cell-in-tile | (pixel << dbits | d) must fit 24 bits
   if (((long long)s->N * dm.HW) << dm.dbits > (1LL << 24)) return LS_ERR_UNSUPPORTED;
+  if ((long long)s->N * dm.HW > (1LL << 20)) return LS_ERR_UNSUPPORTED;   // pixel id field of a sorted record
   if ((long long)s->N * dm.HW * dm.Cp >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
   return LS_OK;
 }
@@ -66,7 +67,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base)
   w.recs_sorted = (int2*)take(pts * 8);
   if (with_backward) {
     w.pix_recs = (int2*)take(pts * 8);        // kept for backward
-    w.gT = (float*)take((size_t)dm.B * g.Vc * dm.Cp * 4);
+    w.gT = (float*)take((size_t)dm.B * (g.Vc + 1) * dm.Cp * 4);
     w.gprob_pm = (float*)take(pts * 4);
     w.gfeatT = take(feat);
   }

@@ -210,7 +210,8 @@ int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* se
 // order inside a cell is arbitrary (atomics); ls_splat_fwd re-orders each cell by key, so the
 // sums are deterministic.  key = cell_in_tile << 24 | (pixel << dbits | d).
 // With pix_recs != NULL it also emits, pixel-major, the (cell, prob) pair of every depth bin
-// of every pixel - the index the pixel-stationary backward walks.
+// of every pixel - the index the pixel-stationary backward walks (dropped points point at
+// row Vc, an all-zero row of the cell-major gradient).
 // CTA = (sample, camera, 32 consecutive pixels) x all depth bins; loads are coalesced over
 // pixels, the pixel-major rows are transposed through shared memory.
 // =====================================================================================
@@ -235,7 +236,7 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
         const int key = ((c & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
         recs[(size_t)b * dm.Npts + slot] = make_int2(key, wbits);
       }
-      if (pix_recs) stage[lane * Dp + d] = make_int2(c, wbits);
+      if (pix_recs) stage[lane * Dp + d] = make_int2(c >= 0 ? c : grid.Vc, wbits);   // Vc = zero row
     }
   }
   if (!pix_recs) return;

@@ -27,16 +27,19 @@ __host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
 //  A  canonicalise: one thread per point record of the tile; its position inside its cell =
 //     number of records of that cell with a smaller key (keys are unique), which makes the
 //     summation order independent of the atomics that placed the records.  The re-ordered
-//     records (feature row offset, prob) go to a scratch array.
+//     records {pixel | cell_in_tile<<20 | last_of_cell<<28, prob} go to a scratch array.
 //  B  reduce: a half-warp owns 16 consecutive cells (one x-row of the tile) = one contiguous
 //     run of records; it streams them with LS_WIN feature rows (16 B per lane, 256 B per point)
-//     in flight, accumulates prob*feat in registers and drops each finished cell into the
-//     shared-memory tile [cell][channel] (swizzled, conflict-free).
+//     in flight, accumulates prob*feat in registers and drops the sum into the shared-memory
+//     tile [cell][channel] (swizzled, conflict-free) when a record carries the last-of-cell flag.
 //  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
 //     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
 // =====================================================================================
+#define LS_REC_PIX_MASK 0xFFFFF
+#define LS_REC_LAST (1 << 28)
+
 template <typename T, bool VEC4>
-__global__ void __launch_bounds__(LS_THREADS, 2)
+__global__ void __launch_bounds__(LS_THREADS, 3)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
                     int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid, float* __restrict__ bev,
                     LsBevStrides st) {
@@ -64,91 +67,92 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       int pos = a;
       for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
       const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
-      rso[pos] = make_int2(pix * dm.Cp, r.y);
+      rso[pos] = make_int2(pix | (cl << 20) | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
     }
-    __syncthreads();   // scratch records written by this CTA are visible to this CTA
   }
 
   const int hw = tid >> 4, hl = tid & 15;
-  const unsigned hmask = ls_half_mask();
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * dm.Cp;
+  // phase C geometry of this thread (fixed): 4 consecutive y, one channel of a quad, one x-row
+  const int y4 = tid & 3, cq = (tid >> 2) & 3, xr = (tid >> 4) & 15;
+  const int gx = tx0 + xr, gy = ty0 + 4 * y4;
+  const bool inb = gx < grid.X && gy < grid.Y;
+  const int clc = xr * LS_TY + 4 * y4;
 
   for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
     const int cc = min(tg.cc, dm.Cp - cbase);
+    const int nquads = cc >> 2;
+    if (!tile_empty) {
+      // zero the tile: cells nobody hits are never touched by phase B
+      for (int i = tid; i < LS_TILE * tg.stride / 4; i += LS_THREADS)
+        reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();   // also orders phase A's scratch records before phase B's reads
     // ---- phase B --------------------------------------------------------------------
     if (!tile_empty) {
       const bool lane_on = 4 * hl < cc;
       const T* fb = fbase + cbase + 4 * hl;
-      int cl = hw * 16;
-      const int cl_end = cl + 16;
-      int i = seg[cl];
-      const int iend = seg[cl_end];
-      int next_b = seg[cl + 1];
+      int i = seg[hw * 16];
+      const int iend = seg[hw * 16 + 16];
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       while (i < iend) {
         const int n = min(LS_WIN, iend - i);
-        int2 r = make_int2(0, 0);
-        if (hl < n) r = rso[i + hl];
+        int2 r[LS_WIN];
+#pragma unroll
+        for (int u = 0; u < LS_WIN; ++u) r[u] = (u < n) ? rso[i + u] : make_int2(0, 0);   // half-warp-uniform
         float4 f[LS_WIN];
-        float w[LS_WIN];
 #pragma unroll
         for (int u = 0; u < LS_WIN; ++u) {
-          const int off = __shfl_sync(hmask, r.x, u, 16);
-          w[u] = __int_as_float(__shfl_sync(hmask, r.y, u, 16));
           f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (u < n && lane_on) f[u] = ls_load4<T>(fb + off);
+          if (u < n && lane_on) f[u] = ls_load4<T>(fb + (size_t)(r[u].x & LS_REC_PIX_MASK) * dm.Cp);
         }
 #pragma unroll
         for (int u = 0; u < LS_WIN; ++u) {
-          if (u < n) {
-            while (i + u >= next_b) {      // the run moved on to the next (possibly empty) cell
-              if (lane_on)
-                *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
-              acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              ++cl;
-              next_b = seg[cl + 1];
-            }
-            acc.x = fmaf(w[u], f[u].x, acc.x);
-            acc.y = fmaf(w[u], f[u].y, acc.y);
-            acc.z = fmaf(w[u], f[u].z, acc.z);
-            acc.w = fmaf(w[u], f[u].w, acc.w);
+          const float w = __int_as_float(r[u].y);          // 0 for u >= n
+          acc.x = fmaf(w, f[u].x, acc.x);
+          acc.y = fmaf(w, f[u].y, acc.y);
+          acc.z = fmaf(w, f[u].z, acc.z);
+          acc.w = fmaf(w, f[u].w, acc.w);
+          if (r[u].x & LS_REC_LAST) {
+            const int cl = (r[u].x >> 20) & 255;
+            if (lane_on)
+              *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         i += n;
       }
-      for (; cl < cl_end; ++cl) {
-        if (lane_on) *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
-        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
     }
     __syncthreads();
     // ---- phase C --------------------------------------------------------------------
-    const int nquads = (cc + 3) / 4;
     if (VEC4) {
-      for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
-        const int y4 = idx & 3, cq = (idx >> 2) & 3, x = (idx >> 4) & 15, q = idx >> 8;
-        const int c = cbase + 4 * q + cq;
-        const int gx = tx0 + x, gy = ty0 + 4 * y4;
-        if (c < dm.C && gx < grid.X && gy < grid.Y) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!tile_empty) {
-            const int cl = x * LS_TY + 4 * y4;
-            const float* src = tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp) + cq;
-            v.x = src[0]; v.y = src[tg.stride]; v.z = src[2 * tg.stride]; v.w = src[3 * tg.stride];
+      if (inb) {
+        const int swz = (clc >> 3) & (tg.nqp - 1);
+        const float* srow = tile + clc * tg.stride + cq;
+        float* gptr = bev + (size_t)b * st.b + (size_t)(cbase + cq) * st.c + (size_t)gx * st.x + gy;
+        const size_t qstep = (size_t)4 * st.c;
+#pragma unroll 4
+        for (int q = 0; q < nquads; ++q) {
+          if (cbase + 4 * q + cq < dm.C) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!tile_empty) {
+              const float* src = srow + 4 * (q ^ swz);
+              v.x = src[0]; v.y = src[tg.stride]; v.z = src[2 * tg.stride]; v.w = src[3 * tg.stride];
+            }
+            *reinterpret_cast<float4*>(gptr + q * qstep) = v;
           }
-          *reinterpret_cast<float4*>(bev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy) = v;
         }
       }
     } else {
       for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
         const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
         const int c = cbase + cr;
-        const int gx = tx0 + x, gy = ty0 + y;
-        if (c < dm.C && gx < grid.X && gy < grid.Y) {
+        const int ox = tx0 + x, oy = ty0 + y;
+        if (c < dm.C && ox < grid.X && oy < grid.Y) {
           const int cl = x * LS_TY + y;
           const float v = tile_empty ? 0.0f
                                      : tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)];
-          bev[(size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy] = v;
+          bev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy] = v;
         }
       }
     }
@@ -201,7 +205,7 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
 // =====================================================================================
 template <bool VEC4>
-__global__ void __launch_bounds__(LS_THREADS, 2)
+__global__ void __launch_bounds__(LS_THREADS, 3)
 ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const int* __restrict__ seg_start,
                         LsDims dm, LsGrid grid, float* __restrict__ gT) {
   extern __shared__ float smem[];
@@ -212,42 +216,53 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
+  if (tile_id == 0) {   // row Vc of every sample = zeros: where dropped points gather from
+    float* zrow = gT + ((size_t)b * (grid.Vc + 1) + grid.Vc) * dm.Cp;
+    for (int i = tid; i < dm.Cp; i += LS_THREADS) zrow[i] = 0.0f;
+  }
   __syncthreads();
   if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
-  float* dst = gT + ((size_t)b * grid.Vc + (size_t)tile_id * LS_TILE) * dm.Cp;
+  float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp;
+  const int y4 = tid & 3, cq = (tid >> 2) & 3, xr = (tid >> 4) & 15;
+  const int gx = tx0 + xr, gy = ty0 + 4 * y4;
+  const bool inb = gx < grid.X && gy < grid.Y;
+  const int clc = xr * LS_TY + 4 * y4;
   for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
     const int cc = min(tg.cc, dm.Cp - cbase);
-    const int nquads = (cc + 3) / 4;
+    const int nquads = cc >> 2;
     if (VEC4) {
-      for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
-        const int y4 = idx & 3, cq = (idx >> 2) & 3, x = (idx >> 4) & 15, q = idx >> 8;
-        const int c = cbase + 4 * q + cq;
-        const int gx = tx0 + x, gy = ty0 + 4 * y4;
+      const int swz = (clc >> 3) & (tg.nqp - 1);
+      float* drow = tile + clc * tg.stride + cq;
+      const float* gptr = gbev + (size_t)b * st.b + (size_t)(cbase + cq) * st.c + (size_t)gx * st.x + gy;
+      const size_t qstep = (size_t)4 * st.c;
+#pragma unroll 4
+      for (int q = 0; q < nquads; ++q) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < dm.C && gx < grid.X && gy < grid.Y)
-          v = __ldg(reinterpret_cast<const float4*>(gbev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy));
-        const int cl = x * LS_TY + 4 * y4;
-        float* d = tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp) + cq;
+        if (inb && cbase + 4 * q + cq < dm.C) v = __ldg(reinterpret_cast<const float4*>(gptr + q * qstep));
+        float* d = drow + 4 * (q ^ swz);
         d[0] = v.x; d[tg.stride] = v.y; d[2 * tg.stride] = v.z; d[3 * tg.stride] = v.w;
       }
     } else {
       for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
         const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
         const int c = cbase + cr;
-        const int gx = tx0 + x, gy = ty0 + y;
+        const int ox = tx0 + x, oy = ty0 + y;
         float v = 0.0f;
-        if (c < dm.C && gx < grid.X && gy < grid.Y)
-          v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy];
+        if (c < dm.C && ox < grid.X && oy < grid.Y)
+          v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy];
         const int cl = x * LS_TY + y;
         tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < nquads * LS_TILE; idx += LS_THREADS) {
-      const int q = idx % nquads, cl = idx / nquads;
-      if (seg[cl + 1] != seg[cl])
-        *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + cbase + 4 * q) =
-            *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
+    // rows of non-empty cells, 16 B per lane: thread = (quad, cell mod 16)
+    if ((tid & 15) < nquads) {
+      const int q = tid & 15;
+      for (int cl = tid >> 4; cl < LS_TILE; cl += LS_THREADS / 16) {
+        if (seg[cl + 1] != seg[cl])
+          *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + cbase + 4 * q) =
+              *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
+      }
     }
     __syncthreads();
   }
@@ -291,7 +306,8 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const unsigned hmask = ls_half_mask();
-  const float* gTb = gT + (size_t)b * grid.Vc * dm.Cp + 4 * hl;
+  // dropped points carry row index Vc: the all-zero row written by the transpose kernel
+  const float* gTb = gT + (size_t)b * (grid.Vc + 1) * dm.Cp + 4 * hl;
   bool on[NCH];
 #pragma unroll
   for (int q = 0; q < NCH; ++q) on[q] = (q * LS_CCHUNK + 4 * hl) < dm.Cp;
@@ -308,8 +324,9 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
     const int2* pr = pix_recs + pix * dm.D;
     for (int d0 = 0; d0 < dm.D; d0 += 16) {
       const int n = min(16, dm.D - d0);
-      int2 r = make_int2(-1, 0);
-      if (hl < n) r = __ldg(pr + d0 + hl);
+      int2 r[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) r[u] = (u < n) ? __ldg(pr + d0 + u) : make_int2(grid.Vc, 0);  // uniform
       float dot[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) dot[u] = 0.0f;
@@ -318,14 +335,12 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
         float4 g[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int cell = __shfl_sync(hmask, r.x, u, 16);
           g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cell >= 0 && on[q])
-            g[u] = __ldg(reinterpret_cast<const float4*>(gTb + (size_t)cell * dm.Cp + q * LS_CCHUNK));
+          if (on[q]) g[u] = __ldg(reinterpret_cast<const float4*>(gTb + (size_t)r[u].x * dm.Cp + q * LS_CCHUNK));
         }
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const float w = __int_as_float(__shfl_sync(hmask, r.y, u, 16));
+          const float w = __int_as_float(r[u].y);
           dot[u] = fmaf(f[q].x, g[u].x, dot[u]);
           dot[u] = fmaf(f[q].y, g[u].y, dot[u]);
           dot[u] = fmaf(f[q].z, g[u].z, dot[u]);

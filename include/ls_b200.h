@@ -100,8 +100,8 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
  * seg_start i32[B,seg_stride] (CSR offsets, entry [cells_padded] = kept count), then every
  * kept point writes an 8-byte record {key, prob bits} to recs[B,Npts] at
  * seg_start[cell] + within;  key = cell_in_tile << 24 | (pixel << ceil(log2 D) | d).
- * pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell, prob bits} per depth bin of every
- * pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
+* pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell (cells_padded for a dropped point),
+ * prob bits} per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
             int dtype, const LsShape* s, int32_t* seg_start, void* recs, void* pix_recs,
             ls_stream_t stream);
@@ -140,7 +140,7 @@ int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32
  *   grad_prob[p]      = sum_c feat[pix,c] * g[c, cell(p)]
  *   grad_feat[pix, c] = sum_d prob[d,pix] * g[c, cell(d,pix)]      (pixel-stationary,
  * no atomics, fixed order).  grad_bev f32 [B,C,X,Y] with strides; gT_ws
- * f32[B,cells_padded,Cp] scratch (cell-major gradient); outputs grad_prob_pm
+ * f32[B,cells_padded+1,Cp] scratch (cell-major gradient, last row of each sample zero); outputs grad_prob_pm
  * f32[B*N*fh*fw, D] (PIXEL-major, consumed by ls_softmax_bwd) and grad_feat_nhwc
  * [B*N,fh,fw,Cp] of `dtype`. */
 int ls_splat_bwd(const float* grad_bev, const LsBevStrides* grad_strides, const void* feat_nhwc,

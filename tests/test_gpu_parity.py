@@ -125,7 +125,8 @@ def test_sorted_ranks_bit_exact(lib, name):
         assert np.array_equal(w, prob.view(sh.batch, -1)[b].cpu().numpy()[p])
     # pixel-major index: {cell, prob} of every depth bin of every pixel
     pc = pix[..., 0].view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
-    assert torch.equal(pc, cell)
+    cells_padded = ls.grid_cells(s)[1]
+    assert torch.equal(pc, torch.where(cell >= 0, cell, torch.full_like(cell, cells_padded)))   # dropped -> zero row
     pw = pix[..., 1].contiguous().view(torch.float32).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2)
     assert torch.equal(pw.reshape(-1), prob.view(sh.batch, sh.cams, D, hw).reshape(-1))
 
