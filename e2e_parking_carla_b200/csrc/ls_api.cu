@@ -39,7 +39,7 @@ static bool ls_dtype_ok(int dtype) { return dtype == LS_F32 || dtype == LS_BF16;
 
 // ---- workspace carving -------------------------------------------------------------
 struct LsWs {
-  int *cell, *within, *counts, *seg_start;
+  int *cell, *within, *counts, *seg_start, *tile_order;
   int2 *recs, *recs_sorted, *pix_recs;
   void* featT;
   float *gT, *gprob_pm;
@@ -60,6 +60,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base)
   auto take = [&](size_t n) { void* r = p ? (void*)(p + off) : nullptr; off += ls_align(n); return r; };
   w.featT = take(feat);                       // kept for backward
   w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);   // kept for backward
+  w.tile_order = (int*)take((size_t)dm.B * g.tiles * 4);
   w.counts = (int*)take((size_t)dm.B * g.Vc * 4);
   w.cell = (int*)take(pts * 4);
   w.within = (int*)take(pts * 4);
@@ -141,13 +142,15 @@ int ls_index(const float* M, const float* t, const float* frustum, const LsShape
 }
 
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob, int dtype,
-            const LsShape* s, int32_t* seg_start, void* recs, void* pix_recs, ls_stream_t stream) {
+            const LsShape* s, int32_t* seg_start, int32_t* tile_order, void* recs, void* pix_recs,
+            ls_stream_t stream) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
-  if (!cell || !within || !counts || !prob || !seg_start || !recs || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
+  if (!cell || !within || !counts || !prob || !seg_start || !tile_order || !recs || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
-  if ((rc = ls_launch_scan(counts, dm, g, seg_start, (cudaStream_t)stream))) return rc;
+  if ((rc = ls_launch_scan(counts, dm, g, seg_start, tile_order, (cudaStream_t)stream))) return rc;
   return ls_launch_place(cell, within, prob, dtype, dm, g, seg_start, (int2*)recs, (int2*)pix_recs,
                          (cudaStream_t)stream);
 }
@@ -187,13 +190,15 @@ int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32
   return ls_launch_from_nhwc(src, dtype, images, C, ls_padded_channels(C), HW, dst, (cudaStream_t)stream);
 }
 
-int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start, void* recs_scratch,
-                 const LsShape* s, float* bev, const LsBevStrides* st, ls_stream_t stream) {
+int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start,
+                 const int32_t* tile_order, void* recs_scratch, const LsShape* s, float* bev, const LsBevStrides* st,
+                 ls_stream_t stream) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
-  if (!feat_nhwc || !recs || !seg_start || !recs_scratch || !bev || !st || !ls_dtype_ok(dtype)) return LS_ERR_BAD_ARG;
-  return ls_launch_splat_fwd(feat_nhwc, dtype, (const int2*)recs, seg_start, (int2*)recs_scratch, ls_dims(s),
-                             ls_grid(s), bev, *st, (cudaStream_t)stream);
+  if (!feat_nhwc || !recs || !seg_start || !tile_order || !recs_scratch || !bev || !st || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  return ls_launch_splat_fwd(feat_nhwc, dtype, (const int2*)recs, seg_start, tile_order, (int2*)recs_scratch,
+                             ls_dims(s), ls_grid(s), bev, *st, (cudaStream_t)stream);
 }
 
 int ls_splat_bwd(const float* grad_bev, const LsBevStrides* gst, const void* feat_nhwc, int dtype,
@@ -231,13 +236,14 @@ int ls_forward(const void* feat, const void* logits, int dtype, const float* M, 
   LS_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)dm.B * g.Vc * sizeof(int), stream));
   ls_note_launch();
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
-  if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, stream))) return rc;
+  if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, stream))) return rc;
   if ((rc = ls_launch_softmax(logits, dtype, dm, prob, stream))) return rc;
   if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs,
                             with_backward ? w.pix_recs : nullptr, stream)))
     return rc;
   if ((rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, stream))) return rc;
-  return ls_launch_splat_fwd(w.featT, dtype, w.recs, w.seg_start, w.recs_sorted, dm, g, bev, *bev_strides, stream);
+  return ls_launch_splat_fwd(w.featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, dm, g, bev,
+                             *bev_strides, stream);
 }
 
 int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext, const void* prob,

@@ -147,7 +147,7 @@ __device__ __forceinline__ int ls_warp_incl_scan(int v, int lane) {
 }
 
 __global__ void __launch_bounds__(1024)
-ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_start) {
+ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_start, int* __restrict__ tile_order) {
   __shared__ int tile_base[1024];
   __shared__ int warp_tot[32];
   __shared__ int chunk_total;
@@ -168,6 +168,23 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
     }
     __syncthreads();
     const int v = (t0 + tid < tend) ? tile_base[tid] : 0;
+    if (tile_order) {
+      // heaviest tile first (longest-processing-time order for the splat's CTAs); exact for
+      // up to 1024 tiles, identity beyond
+      int* ord = tile_order + (size_t)b * g.tiles;
+      if (g.tiles <= 1024) {
+        if (tid < g.tiles) {
+          int r = 0;
+          for (int j = 0; j < g.tiles; ++j) {
+            const int o = tile_base[j];
+            r += (o > v || (o == v && j < tid)) ? 1 : 0;
+          }
+          ord[r] = tid;
+        }
+      } else if (t0 + tid < tend) {
+        ord[t0 + tid] = t0 + tid;
+      }
+    }
     const int incl = ls_warp_incl_scan(v, lane);
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
@@ -198,8 +215,9 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
   if (tid == 0) seg[g.Vc] = carry;
 }
 
-int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, cudaStream_t s) {
-  ls_scan_kernel<<<dm.B, 1024, 0, s>>>(counts, g, seg_start);
+int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, int* tile_order,
+                   cudaStream_t s) {
+  ls_scan_kernel<<<dm.B, 1024, 0, s>>>(counts, g, seg_start, tile_order);
   LS_LAUNCHED();
   return LS_OK;
 }

@@ -8,7 +8,8 @@ int ls_launch_index(const float* M, const float* t, const float* frustum, const 
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s);
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                      float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s);
-int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, cudaStream_t s);
+int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, int* tile_order,
+                   cudaStream_t s);
 int ls_launch_place(const int* cell, const int* within, const void* prob, int dtype, const LsDims& dm,
                     const LsGrid& g, const int* seg_start, int2* recs, int2* pix_recs, cudaStream_t s);
 int ls_launch_export_cell_counts(const int* seg_start, const LsGrid& g, int B, int b, long long* out, int* kept,
@@ -23,8 +24,8 @@ int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int
 int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
 
 // ls_splat.cu
-int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, int2* recs_sorted,
-                        const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
+int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, const int* tile_order,
+                        int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
                             const LsGrid& g, float* gT, cudaStream_t s);
 int ls_launch_bwd_gather(const float* gT, const void* featT, int dtype, const int2* pix_recs, const LsDims& dm,

@@ -38,17 +38,37 @@ __host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
 #define LS_REC_PIX_MASK 0xFFFFF
 #define LS_REC_LAST (1 << 28)
 
-template <typename T, bool VEC4>
+#define LS_ITEM 64   // target records per work item of phase B
+
+__device__ __forceinline__ void ls_load_recs(const int2* __restrict__ rso, int i, int n, int2 (&r)[LS_WIN]) {
+#pragma unroll
+  for (int u = 0; u < LS_WIN; ++u) {
+    r[u] = rso[i + min(u, n - 1)];                          // half-warp-uniform 8-byte loads
+    if (u >= n) { r[u].x &= ~LS_REC_LAST; r[u].y = 0; }     // padding: weight 0, never flushes
+  }
+}
+
+// kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
+template <typename T, bool VEC4, int kCC>
 __global__ void __launch_bounds__(LS_THREADS, 3)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
-                    int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid, float* __restrict__ bev,
-                    LsBevStrides st) {
+                    const int* __restrict__ tile_order, int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
+                    float* __restrict__ bev, LsBevStrides st) {
   extern __shared__ float smem[];
-  const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  float* tile = smem;                                               // [LS_TILE][tg.stride]
-  int* seg = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);    // [LS_TILE + 1]
+  const LsTileGeom tgr = ls_tile_geom(dm.Cp);
+  const int Cp = kCC ? kCC : dm.Cp;
+  const int stride = kCC ? kCC + 4 : tgr.stride;
+  const int nqp = kCC ? kCC / 4 : tgr.nqp;
+  const int ccmax = kCC ? kCC : tgr.cc;
+  float* tile = smem;                                            // [LS_TILE][stride]
+  int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1]
+  int* heads = seg + LS_TILE + 1;                                // [LS_TILE + 1] first cell of each work item
+  int* ctl = heads + LS_TILE + 1;                                // [0] item count, [1] next item, [2..9] warp sums
 
-  const int b = blockIdx.y, tile_id = blockIdx.x, tid = threadIdx.x;
+  // heaviest tiles first, all samples interleaved: blockIdx.x = order_index * B + b
+  const int b = blockIdx.x % dm.B;
+  const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
@@ -58,8 +78,8 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const int2* rin = recs + (size_t)b * dm.Npts;
   int2* rso = recs_sorted + (size_t)b * dm.Npts;
 
-  // ---- phase A ----------------------------------------------------------------------
   if (!tile_empty) {
+    // ---- phase A --------------------------------------------------------------------
     for (int i = s0 + tid; i < s1; i += LS_THREADS) {
       const int2 r = rin[i];
       const int cl = (unsigned)r.x >> 24;
@@ -69,78 +89,109 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
       rso[pos] = make_int2(pix | (cl << 20) | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
     }
+    // ---- work items: runs of whole cells of about LS_ITEM records ----------------------
+    // cell `tid` opens an item when its first record falls in a new LS_ITEM-sized bucket
+    {
+      const int id = (seg[tid] - s0) / LS_ITEM;
+      const bool head = (tid == 0) || (id != (seg[tid - 1] - s0) / LS_ITEM);
+      const unsigned bal = __ballot_sync(0xffffffffu, head);
+      if (lane == 0) ctl[2 + warp] = __popc(bal);
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += ctl[2 + w];
+      if (head) heads[before + __popc(bal & ((1u << lane) - 1))] = tid;
+      if (tid == LS_THREADS - 1) {
+        const int nitems = before + __popc(bal);
+        heads[nitems] = LS_TILE;
+        ctl[0] = nitems;
+      }
+    }
   }
 
-  const int hw = tid >> 4, hl = tid & 15;
-  const T* fbase = featT + (size_t)b * dm.N * dm.HW * dm.Cp;
+  const int hl = tid & 15;
+  const unsigned hmask = ls_half_mask();
+  const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
+  const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
   // phase C geometry of this thread (fixed): 4 consecutive y, one channel of a quad, one x-row
   const int y4 = tid & 3, cq = (tid >> 2) & 3, xr = (tid >> 4) & 15;
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
   const bool inb = gx < grid.X && gy < grid.Y;
   const int clc = xr * LS_TY + 4 * y4;
 
-  for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
-    const int cc = min(tg.cc, dm.Cp - cbase);
+  for (int cbase = 0; cbase < Cp; cbase += LS_CCHUNK) {
+    const int cc = kCC ? kCC : min(ccmax, Cp - cbase);
     const int nquads = cc >> 2;
     if (!tile_empty) {
       // zero the tile: cells nobody hits are never touched by phase B
-      for (int i = tid; i < LS_TILE * tg.stride / 4; i += LS_THREADS)
+      for (int i = tid; i < LS_TILE * stride / 4; i += LS_THREADS)
         reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid == 0) ctl[1] = 0;
     }
-    __syncthreads();   // also orders phase A's scratch records before phase B's reads
+    __syncthreads();   // also orders phase A's scratch records / work items before phase B
     // ---- phase B --------------------------------------------------------------------
     if (!tile_empty) {
       const bool lane_on = 4 * hl < cc;
-      const T* fb = fbase + cbase + 4 * hl;
-      int i = seg[hw * 16];
-      const int iend = seg[hw * 16 + 16];
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      while (i < iend) {
-        const int n = min(LS_WIN, iend - i);
+      // lanes beyond the channel count read lane 0's (valid) bytes and never store
+      const char* fbytes = reinterpret_cast<const char*>(fbase + cbase + (lane_on ? 4 * hl : 0));
+      const int nitems = ctl[0];
+      for (;;) {
+        int it = 0;
+        if (hl == 0) it = atomicAdd(&ctl[1], 1);
+        it = __shfl_sync(hmask, it, 0, 16);
+        if (it >= nitems) break;
+        int i = seg[heads[it]];
+        const int iend = seg[heads[it + 1]];
+        if (i >= iend) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int2 r[LS_WIN];
+        ls_load_recs(rso, i, min(LS_WIN, iend - i), r);
+        while (i < iend) {
+          float4 f[LS_WIN];
 #pragma unroll
-        for (int u = 0; u < LS_WIN; ++u) r[u] = (u < n) ? rso[i + u] : make_int2(0, 0);   // half-warp-uniform
-        float4 f[LS_WIN];
+          for (int u = 0; u < LS_WIN; ++u)
+            f[u] = ls_load4<T>(reinterpret_cast<const T*>(
+                fbytes + (unsigned long long)(unsigned)(r[u].x & LS_REC_PIX_MASK) * row_bytes));
+          // records of the next window are fetched while this window's feature rows are in flight
+          i += LS_WIN;
+          int2 rn[LS_WIN];
+          if (i < iend) ls_load_recs(rso, i, min(LS_WIN, iend - i), rn);
 #pragma unroll
-        for (int u = 0; u < LS_WIN; ++u) {
-          f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (u < n && lane_on) f[u] = ls_load4<T>(fb + (size_t)(r[u].x & LS_REC_PIX_MASK) * dm.Cp);
-        }
-#pragma unroll
-        for (int u = 0; u < LS_WIN; ++u) {
-          const float w = __int_as_float(r[u].y);          // 0 for u >= n
-          acc.x = fmaf(w, f[u].x, acc.x);
-          acc.y = fmaf(w, f[u].y, acc.y);
-          acc.z = fmaf(w, f[u].z, acc.z);
-          acc.w = fmaf(w, f[u].w, acc.w);
-          if (r[u].x & LS_REC_LAST) {
-            const int cl = (r[u].x >> 20) & 255;
-            if (lane_on)
-              *reinterpret_cast<float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, hl, tg.nqp)) = acc;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < LS_WIN; ++u) {
+            const float w = __int_as_float(r[u].y);
+            acc.x = fmaf(w, f[u].x, acc.x);
+            acc.y = fmaf(w, f[u].y, acc.y);
+            acc.z = fmaf(w, f[u].z, acc.z);
+            acc.w = fmaf(w, f[u].w, acc.w);
+            if (r[u].x & LS_REC_LAST) {
+              const int cl = (r[u].x >> 20) & 255;
+              if (lane_on) *reinterpret_cast<float4*>(tile + cl * stride + 4 * ls_tile_quad(cl, hl, nqp)) = acc;
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
+#pragma unroll
+          for (int u = 0; u < LS_WIN; ++u) r[u] = rn[u];
         }
-        i += n;
       }
     }
     __syncthreads();
     // ---- phase C --------------------------------------------------------------------
     if (VEC4) {
       if (inb) {
-        const int swz = (clc >> 3) & (tg.nqp - 1);
-        const float* srow = tile + clc * tg.stride + cq;
+        const int swz4 = 4 * ((clc >> 3) & (nqp - 1));
+        const float* srow = tile + clc * stride + cq;
         float* gptr = bev + (size_t)b * st.b + (size_t)(cbase + cq) * st.c + (size_t)gx * st.x + gy;
         const size_t qstep = (size_t)4 * st.c;
-#pragma unroll 4
+#pragma unroll 8
         for (int q = 0; q < nquads; ++q) {
-          if (cbase + 4 * q + cq < dm.C) {
+          if (kCC || cbase + 4 * q + cq < dm.C) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!tile_empty) {
-              const float* src = srow + 4 * (q ^ swz);
-              v.x = src[0]; v.y = src[tg.stride]; v.z = src[2 * tg.stride]; v.w = src[3 * tg.stride];
+              const float* src = srow + ((4 * q) ^ swz4);
+              v.x = src[0]; v.y = src[stride]; v.z = src[2 * stride]; v.w = src[3 * stride];
             }
-            *reinterpret_cast<float4*>(gptr + q * qstep) = v;
+            *reinterpret_cast<float4*>(gptr) = v;
           }
+          gptr += qstep;
         }
       }
     } else {
@@ -150,8 +201,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
         const int ox = tx0 + x, oy = ty0 + y;
         if (c < dm.C && ox < grid.X && oy < grid.Y) {
           const int cl = x * LS_TY + y;
-          const float v = tile_empty ? 0.0f
-                                     : tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)];
+          const float v = tile_empty ? 0.0f : tile[cl * stride + 4 * ls_tile_quad(cl, cr >> 2, nqp) + (cr & 3)];
           bev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy] = v;
         }
       }
@@ -162,7 +212,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
 
 static size_t ls_tile_smem_bytes(const LsDims& dm) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 1) * sizeof(int);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (2 * (LS_TILE + 1) + 16) * sizeof(int);
 }
 static size_t ls_tile_smem_max() {
   LsDims d;
@@ -174,30 +224,39 @@ static bool ls_bev_vec4(const float* p, const LsBevStrides& st, const LsGrid& g)
   return ((uintptr_t)p % 16 == 0) && (st.b % 4 == 0) && (st.c % 4 == 0) && (st.x % 4 == 0) && (g.Y % 4 == 0);
 }
 
-int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, int2* recs_sorted,
-                        const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s) {
+template <typename T>
+static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg_start, const int* tile_order,
+                             int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     const int m = (int)ls_tile_smem_max();
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<__nv_bfloat16, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<__nv_bfloat16, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
     attr_done = true;
   }
   const size_t smem = ls_tile_smem_bytes(dm);
-  dim3 grid(g.tiles, dm.B);
+  dim3 grid(g.tiles * dm.B);
   const bool v4 = ls_bev_vec4(bev, st, g);
-#define LS_SPLAT(TT, VV)                                                                                   \
-  ls_splat_fwd_kernel<TT, VV><<<grid, LS_THREADS, smem, s>>>((const TT*)featT, recs, seg_start, recs_sorted, dm, g, \
-                                                             bev, st)
-  if (dtype == LS_F32) { if (v4) LS_SPLAT(float, true); else LS_SPLAT(float, false); }
-  else { if (v4) LS_SPLAT(__nv_bfloat16, true); else LS_SPLAT(__nv_bfloat16, false); }
-#undef LS_SPLAT
+  if (v4 && dm.Cp == 64 && dm.C == 64)
+    ls_splat_fwd_kernel<T, true, 64><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
+                                                                   dm, g, bev, st);
+  else if (v4)
+    ls_splat_fwd_kernel<T, true, 0><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
+                                                                  dm, g, bev, st);
+  else
+    ls_splat_fwd_kernel<T, false, 0><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
+                                                                   dm, g, bev, st);
   LS_LAUNCHED();
   return LS_OK;
+}
+
+int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, const int* tile_order,
+                        int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st,
+                        cudaStream_t s) {
+  if (dtype == LS_F32)
+    return ls_splat_dispatch<float>(featT, recs, seg_start, tile_order, recs_sorted, dm, g, bev, st, s);
+  return ls_splat_dispatch<__nv_bfloat16>(featT, recs, seg_start, tile_order, recs_sorted, dm, g, bev, st, s);
 }
 
 // =====================================================================================

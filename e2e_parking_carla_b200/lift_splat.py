@@ -147,21 +147,22 @@ def softmax(logits: torch.Tensor, shape: LsShape) -> torch.Tensor:
 
 
 def sort(cell, within, counts, prob, shape: LsShape, with_pixel_index: bool = False):
-    """Counting sort by cell: (seg_start i32[B,seg_stride], recs i32[B,Npts,2] = {key, prob
-    bits}, pix_recs i32[B*N*HW, D, 2] or None)."""
+    """Counting sort by cell: (seg_start i32[B,seg_stride], tile_order i32[B,tiles], recs
+    i32[B,Npts,2] = {key, prob bits}, pix_recs i32[B*N*HW, D, 2] or None)."""
     _need_cuda(cell, within, counts, prob)
-    _, _, stride = grid_cells(shape)
+    tiles, _, stride = grid_cells(shape)
     dev = cell.device
     npts = cell.shape[1]
     seg = torch.empty(shape.B, stride, dtype=torch.int32, device=dev)
+    order = torch.empty(shape.B, tiles, dtype=torch.int32, device=dev)
     recs = torch.zeros(shape.B, npts, 2, dtype=torch.int32, device=dev)
     pix = None
     if with_pixel_index:
         pix = torch.empty(shape.B * shape.N * shape.fh * shape.fw, shape.D, 2, dtype=torch.int32, device=dev)
     prob = prob.contiguous()
     check(_lib.load().ls_sort(_ptr(cell), _ptr(within), _ptr(counts), _ptr(prob), _dtype_code(prob), C.byref(shape),
-                              _ptr(seg), _ptr(recs), _ptr(pix), _stream(cell)), "ls_sort")
-    return seg, recs, pix
+                              _ptr(seg), _ptr(order), _ptr(recs), _ptr(pix), _stream(cell)), "ls_sort")
+    return seg, order, recs, pix
 
 
 def export_sorted_ranks(seg_start: torch.Tensor, shape: LsShape, b: int) -> torch.Tensor:

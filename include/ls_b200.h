@@ -97,14 +97,16 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
 
 /* a6.3 - model/bev_model.py:96-97 (argsort + gathers) and the segment boundaries of
  * tool/geometry.py:295-296, as a counting sort by cell: exclusive scan of counts ->
- * seg_start i32[B,seg_stride] (CSR offsets, entry [cells_padded] = kept count), then every
+ * seg_start i32[B,seg_stride] (CSR offsets, entry [cells_padded] = kept count) and
+ * tile_order i32[B,tiles] (tile ids by descending point count: the launch order of the
+ * splat's CTAs), then every
  * kept point writes an 8-byte record {key, prob bits} to recs[B,Npts] at
  * seg_start[cell] + within;  key = cell_in_tile << 24 | (pixel << ceil(log2 D) | d).
 * pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell (cells_padded for a dropped point),
  * prob bits} per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
-            int dtype, const LsShape* s, int32_t* seg_start, void* recs, void* pix_recs,
-            ls_stream_t stream);
+            int dtype, const LsShape* s, int32_t* seg_start, int32_t* tile_order, void* recs,
+            void* pix_recs, ls_stream_t stream);
 
 /* Test export: for sample b, out i64[cells_padded,2] = (row-major rank, number of kept
  * points) of every cell, zeros for empty / padding cells; from it the reference's
@@ -128,12 +130,12 @@ int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32
 /* a5(outer product)+a6.4-a6.5 fused - model/bev_model.py:66-72,99-105 and
  * VoxelsSumming.forward (tool/geometry.py:289-305): deterministic segment sum of
  * prob[p]*feat[pix(p),:] per cell, written (zeros included) to bev f32[B,C,X,Y].
- * feat_nhwc: [B*N, fh, fw, Cp] of `dtype`; recs/seg_start from ls_sort;
+ * feat_nhwc: [B*N, fh, fw, Cp] of `dtype`; recs/seg_start/tile_order from ls_sort;
  * recs_scratch: 8 B x [B,Npts], receives the records re-ordered by key inside each cell
  * (this is what makes the sums independent of the atomics' arrival order). */
 int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start,
-                 void* recs_scratch, const LsShape* s, float* bev, const LsBevStrides* bev_strides,
-                 ls_stream_t stream);
+                 const int32_t* tile_order, void* recs_scratch, const LsShape* s, float* bev,
+                 const LsBevStrides* bev_strides, ls_stream_t stream);
 
 /* a7 + autograd of a5/a6 - VoxelsSumming.backward (tool/geometry.py:307-317) and the
  * backward of the outer product: every kept point receives its cell's gradient;

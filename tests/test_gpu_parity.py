@@ -104,7 +104,12 @@ def test_sorted_ranks_bit_exact(lib, name):
     assert torch.equal(cell >= 0, rank >= 0)
     _, logits, _, _ = g.inputs()
     prob = ls.softmax(logits.to(DEV), s)
-    seg, recs, pix = ls.sort(cell, within, counts, prob, s, with_pixel_index=True)
+    seg, order, recs, pix = ls.sort(cell, within, counts, prob, s, with_pixel_index=True)
+    # launch order of the splat: every tile exactly once, heaviest first
+    tiles = ls.grid_cells(s)[0]
+    assert torch.equal(order.sort(dim=1).values, torch.arange(tiles, device=DEV, dtype=torch.int32).expand(sh.batch, -1))
+    tot = (seg[:, 256:tiles * 256 + 1:256] - seg[:, 0:tiles * 256:256]).long()
+    assert bool((torch.gather(tot, 1, order.long()).diff(dim=1) <= 0).all())
     kept = ls.kept_counts(seg, s).cpu().numpy()
     assert np.array_equal(kept, g["kept_per_cam"].sum(-1))
     hw, D = sh.fh * sh.fw, sh.depth_bins
