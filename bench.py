@@ -230,7 +230,7 @@ class Stepper:
         seg = torch.empty(sh.batch, stride, dtype=torch.int32, device=dev)
         order = torch.empty(sh.batch, tiles, dtype=torch.int32, device=dev)
         recs = torch.empty(sh.batch, npts, 2, dtype=torch.int32, device=dev)
-        recs2 = torch.empty_like(recs)
+        recs2 = torch.empty(sh.batch, int(lib.ls_sorted_records(C.byref(s))), 2, dtype=torch.int32, device=dev)
         pix = torch.empty(sh.batch * sh.cams * sh.fh * sh.fw, sh.depth_bins, 2, dtype=torch.int32, device=dev)
         featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, cp, dtype=self.dtype, device=dev)
         gT = torch.empty(sh.batch, cells + 1, cp, device=dev)

@@ -35,8 +35,10 @@ PROTOTYPES = {
     "ls_strerror": (C.c_char_p, [C.c_int]),
     "ls_last_cuda_error": (C.c_char_p, []),
     "ls_launch_count": (C.c_int64, []),
+    "ls_debug_phase_cycles": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ls_grid_cells": (C.c_int, [_SH, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ls_padded_channels": (C.c_int32, [C.c_int32]),
+    "ls_sorted_records": (C.c_size_t, [_SH]),
     "ls_camera_transform": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "ls_geometry": (C.c_int, [_P, _P, _P, _SH, _P, _P]),
     "ls_index": (C.c_int, [_P, _P, _P, _SH, _P, _P, _P, _P, _P]),

@@ -53,6 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
+    if os.environ.get("LS_PROFILE"):
+        base += ["-DLS_PROFILE"]      # developer build: per-phase clock64 accounting in the splat
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

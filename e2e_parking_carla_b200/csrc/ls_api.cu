@@ -65,7 +65,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base)
   w.cell = (int*)take(pts * 4);
   w.within = (int*)take(pts * 4);
   w.recs = (int2*)take(pts * 8);
-  w.recs_sorted = (int2*)take(pts * 8);
+  w.recs_sorted = (int2*)take((size_t)dm.B * ls_sorted_records_capacity(dm, g) * 8);
   if (with_backward) {
     w.pix_recs = (int2*)take(pts * 8);        // kept for backward
     w.gT = (float*)take((size_t)dm.B * (g.Vc + 1) * dm.Cp * 4);
@@ -92,6 +92,7 @@ const char* ls_strerror(int status) {
 }
 const char* ls_last_cuda_error(void) { return g_cuda_err; }
 int64_t ls_launch_count(void) { return (int64_t)g_launches.load(); }
+int ls_debug_phase_cycles(uint64_t* out8) { return out8 ? ls_debug_fetch_phase_cycles((unsigned long long*)out8) : LS_ERR_BAD_ARG; }
 
 int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32_t* seg_stride) {
   int rc = ls_check_shape(s);
@@ -104,6 +105,11 @@ int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32
 }
 
 int32_t ls_padded_channels(int32_t C) { return (C + 3) & ~3; }
+
+size_t ls_sorted_records(const LsShape* s) {
+  if (ls_check_splat_shape(s)) return 0;
+  return ls_sorted_records_capacity(ls_dims(s), ls_grid(s));
+}
 
 int ls_camera_transform(const float* intrinsics, const float* extrinsics, int32_t BN, float* M, float* t,
                         ls_stream_t stream) {

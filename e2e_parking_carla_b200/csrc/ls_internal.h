@@ -24,6 +24,8 @@ int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int
 int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
 
 // ls_splat.cu
+int ls_debug_fetch_phase_cycles(unsigned long long* out8);   // only with -DLS_PROFILE
+size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g);   // per sample, in 8-byte records
 int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, const int* tile_order,
                         int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,

@@ -1,9 +1,10 @@
 // The splat itself: deterministic ranked segment-reduce (forward) and its gradient
 // (cell-major gradient staging + pixel-stationary gather).  Reference semantics:
 // model/bev_model.py:66-72,99-105 and VoxelsSumming (tool/geometry.py:285-317).
+#include <stdio.h>
+
 #include "ls_internal.h"
 
-#define LS_WIN 8   // points whose feature rows a half-warp keeps in flight
 
 __device__ __forceinline__ unsigned ls_half_mask() { return 0xFFFFu << (threadIdx.x & 16); }
 
@@ -22,33 +23,59 @@ __host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
   return t;
 }
 
+// sorted record: x = pixel << 12 | last_of_cell << 11 | cell_in_tile,  y = prob bits
+#define LS_REC_LAST 0x800
+#ifndef LS_ITEM_SHIFT
+#define LS_ITEM_SHIFT 4
+#endif
+#define LS_ITEM (1 << LS_ITEM_SHIFT)   // target records per work item of phase B
+#define LS_QWIN 4    // records a quarter-warp keeps in flight (work items are padded to this)
+
+#ifdef LS_PROFILE
+__device__ unsigned long long ls_dbg_phase[8];
+__device__ int ls_dbg_cta[8192][8];   // per CTA: records, then cycles of each phase
+#define LS_TICK(k)                                                                  \
+  do {                                                                              \
+    if (threadIdx.x == 0) {                                                         \
+      const long long now__ = clock64();                                            \
+      atomicAdd(&ls_dbg_phase[k], (unsigned long long)(now__ - tick__));            \
+      if (blockIdx.x < 8192) ls_dbg_cta[blockIdx.x][k + 1] = (int)(now__ - tick__); \
+      tick__ = now__;                                                               \
+    }                                                                               \
+  } while (0)
+#define LS_TICK_INIT() long long tick__ = clock64()
+#else
+#define LS_TICK(k) do {} while (0)
+#define LS_TICK_INIT() do {} while (0)
+#endif
+
+__device__ __forceinline__ unsigned ls_quarter_mask() { return 0xFFu << (threadIdx.x & 24); }
+
+// Padded scratch layout of the re-ordered records: tile t of a sample starts at
+// s0 + (s0 >> (LS_ITEM_SHIFT-2)) + 4*t  (s0 = first record of the tile in the CSR); every work
+// item is padded to a multiple of LS_QWIN=4 records: at most 3*(n/LS_ITEM + 1) <=
+// (n >> (LS_ITEM_SHIFT-2)) + 3 extra records per tile, so the regions never overlap.
+#define LS_PAD_SHIFT (LS_ITEM_SHIFT - 2)
+__host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts, int tiles) {
+  return (size_t)Npts + ((size_t)Npts >> LS_PAD_SHIFT) + 4 * (size_t)tiles + 8;
+}
+
 // =====================================================================================
-// K3: forward splat.  One CTA per (sample, 16x16-voxel tile), three phases:
+// K3: forward splat.  One CTA per (sample, 16x16-voxel tile), heaviest tiles first:
+//  0  work items: the tile's record run is cut at cell boundaries into items of about
+//     LS_ITEM records, each padded to a multiple of LS_QWIN (dummy records weigh 0).
 //  A  canonicalise: one thread per point record of the tile; its position inside its cell =
 //     number of records of that cell with a smaller key (keys are unique), which makes the
 //     summation order independent of the atomics that placed the records.  The re-ordered
-//     records {pixel | cell_in_tile<<20 | last_of_cell<<28, prob} go to a scratch array.
-//  B  reduce: a half-warp owns 16 consecutive cells (one x-row of the tile) = one contiguous
-//     run of records; it streams them with LS_WIN feature rows (16 B per lane, 256 B per point)
-//     in flight, accumulates prob*feat in registers and drops the sum into the shared-memory
-//     tile [cell][channel] (swizzled, conflict-free) when a record carries the last-of-cell flag.
+//     records {pixel<<12 | last_of_cell<<11 | cell_in_tile, prob} go to the padded scratch.
+//  B  reduce: work items are dealt round-robin to the 32 quarter-warps.  A lane owns 8 channels
+//     (two 16-byte pieces of the 256-byte feature row); LS_QWIN rows are in flight while the
+//     next records are prefetched; prob*feat accumulates in registers and is dropped into the
+//     shared-memory tile [cell][channel] (swizzled, conflict-free) on a last-of-cell record.
 //  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
 //     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
-// =====================================================================================
-#define LS_REC_PIX_MASK 0xFFFFF
-#define LS_REC_LAST (1 << 28)
-
-#define LS_ITEM 64   // target records per work item of phase B
-
-__device__ __forceinline__ void ls_load_recs(const int2* __restrict__ rso, int i, int n, int2 (&r)[LS_WIN]) {
-#pragma unroll
-  for (int u = 0; u < LS_WIN; ++u) {
-    r[u] = rso[i + min(u, n - 1)];                          // half-warp-uniform 8-byte loads
-    if (u >= n) { r[u].x &= ~LS_REC_LAST; r[u].y = 0; }     // padding: weight 0, never flushes
-  }
-}
-
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
+// =====================================================================================
 template <typename T, bool VEC4, int kCC>
 __global__ void __launch_bounds__(LS_THREADS, 3)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
@@ -61,9 +88,11 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const int nqp = kCC ? kCC / 4 : tgr.nqp;
   const int ccmax = kCC ? kCC : tgr.cc;
   float* tile = smem;                                            // [LS_TILE][stride]
-  int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1]
+  int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1] CSR offsets of the tile
   int* heads = seg + LS_TILE + 1;                                // [LS_TILE + 1] first cell of each work item
-  int* ctl = heads + LS_TILE + 1;                                // [0] item count, [1] next item, [2..9] warp sums
+  int* pstart = heads + LS_TILE + 1;                             // [LS_TILE + 1] padded start of each work item
+  int* cell_item = pstart + LS_TILE + 1;                         // [LS_TILE]     work item of each cell
+  int* ctl = cell_item + LS_TILE;                                // [0] items, [1] next item, [2..17] warp sums
 
   // heaviest tiles first, all samples interleaved: blockIdx.x = order_index * B + b
   const int b = blockIdx.x % dm.B;
@@ -71,45 +100,84 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  LS_TICK_INIT();
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
   __syncthreads();
+  LS_TICK(0);
+#ifdef LS_PROFILE
+  if (threadIdx.x == 0 && blockIdx.x < 8192) ls_dbg_cta[blockIdx.x][0] = seg[LS_TILE] - seg[0];
+#endif
   const int s0 = seg[0], s1 = seg[LS_TILE];
   const bool tile_empty = (s0 == s1);
   const int2* rin = recs + (size_t)b * dm.Npts;
-  int2* rso = recs_sorted + (size_t)b * dm.Npts;
+  int2* rsp = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts, grid.tiles) + (s0 + (s0 >> LS_PAD_SHIFT) + 4 * tile_id);
 
   if (!tile_empty) {
-    // ---- phase A --------------------------------------------------------------------
+    // ---- work items: runs of whole cells of about LS_ITEM records ----------------------
+    // cell `tid` opens an item when its first record falls in a new LS_ITEM-sized bucket
+    const int id = (seg[tid] - s0) / LS_ITEM;
+    const bool head = (tid == 0) || (id != (seg[tid - 1] - s0) / LS_ITEM);
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) ctl[2 + warp] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += ctl[2 + w];
+    const int my_item = before + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
+    cell_item[tid] = my_item;
+    if (head) heads[my_item] = tid;
+    int nitems = 0;
+    for (int w = 0; w < LS_THREADS / 32; ++w) nitems += ctl[2 + w];
+    if (tid == 0) { heads[nitems] = LS_TILE; ctl[0] = nitems; }
+    __syncthreads();
+    // padded item starts: exclusive scan of the item lengths rounded up to LS_QWIN
+    int plen = 0;
+    if (tid < nitems) plen = (seg[heads[tid + 1]] - seg[heads[tid]] + LS_QWIN - 1) & ~(LS_QWIN - 1);
+    int incl = plen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) ctl[10 + warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += ctl[10 + w];
+    if (tid < nitems) pstart[tid] = wbase + incl - plen;
+    if (tid == LS_THREADS - 1) pstart[nitems] = wbase + incl;  // padded total (plen = 0 beyond the last item)
+    __syncthreads();
+    LS_TICK(1);
+    // ---- phase A: canonical order inside each cell, scattered into the padded layout ----
+    // The tile's records are staged in the (not yet used) accumulator tile so that the
+    // rank-by-counting loop reads shared memory; records beyond its capacity (never at the
+    // shipped grid sizes) are ranked straight from global memory.
+    int2* stage = reinterpret_cast<int2*>(tile);
+    const int cap = LS_TILE * stride / 2;
+    const int nst = min(s1 - s0, cap);
+    for (int i = tid; i < nst; i += LS_THREADS) stage[i] = rin[s0 + i];
+    __syncthreads();
     for (int i = s0 + tid; i < s1; i += LS_THREADS) {
-      const int2 r = rin[i];
+      const int2 r = (i - s0 < nst) ? stage[i - s0] : rin[i];
       const int cl = (unsigned)r.x >> 24;
       const int a = seg[cl], e = seg[cl + 1];
       int pos = a;
-      for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
-      const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
-      rso[pos] = make_int2(pix | (cl << 20) | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
-    }
-    // ---- work items: runs of whole cells of about LS_ITEM records ----------------------
-    // cell `tid` opens an item when its first record falls in a new LS_ITEM-sized bucket
-    {
-      const int id = (seg[tid] - s0) / LS_ITEM;
-      const bool head = (tid == 0) || (id != (seg[tid - 1] - s0) / LS_ITEM);
-      const unsigned bal = __ballot_sync(0xffffffffu, head);
-      if (lane == 0) ctl[2 + warp] = __popc(bal);
-      __syncthreads();
-      int before = 0;
-      for (int w = 0; w < warp; ++w) before += ctl[2 + w];
-      if (head) heads[before + __popc(bal & ((1u << lane) - 1))] = tid;
-      if (tid == LS_THREADS - 1) {
-        const int nitems = before + __popc(bal);
-        heads[nitems] = LS_TILE;
-        ctl[0] = nitems;
+      if (e - s0 <= nst) {
+        for (int j = a - s0; j < e - s0; ++j) pos += (stage[j].x < r.x) ? 1 : 0;
+      } else {
+        for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
       }
+      const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
+      const int it = cell_item[cl];
+      rsp[pstart[it] + pos - seg[heads[it]]] =
+          make_int2((pix << 12) | cl | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
     }
+    if (tid < nitems) {   // dummy records: pixel 0, weight 0, never flush
+      const int len = seg[heads[tid + 1]] - seg[heads[tid]];
+      for (int j = len; j < plen; ++j) rsp[pstart[tid] + j] = make_int2(0, 0);
+    }
+    __syncthreads();      // staging area is about to be zeroed and re-used as the accumulator tile
   }
 
-  const int hl = tid & 15;
-  const unsigned hmask = ls_half_mask();
+  const int ql = tid & 7;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
   const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
   // phase C geometry of this thread (fixed): 4 consecutive y, one channel of a quad, one x-row
@@ -125,55 +193,102 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       // zero the tile: cells nobody hits are never touched by phase B
       for (int i = tid; i < LS_TILE * stride / 4; i += LS_THREADS)
         reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tid == 0) ctl[1] = 0;
     }
-    __syncthreads();   // also orders phase A's scratch records / work items before phase B
-    // ---- phase B --------------------------------------------------------------------
+    __syncthreads();   // also orders phase A's scratch records before phase B's reads
+    LS_TICK(2);
+    // ---- phase B: a quarter-warp per work item; lane = channels [4ql,4ql+4) and [32+4ql,..) ----
     if (!tile_empty) {
-      const bool lane_on = 4 * hl < cc;
-      // lanes beyond the channel count read lane 0's (valid) bytes and never store
-      const char* fbytes = reinterpret_cast<const char*>(fbase + cbase + (lane_on ? 4 * hl : 0));
+      const bool on0 = 4 * ql < cc, on1 = 32 + 4 * ql < cc;
+      // lanes beyond the channel count read valid bytes (lane 0's) and never store
+      const char* f0 = reinterpret_cast<const char*>(fbase + cbase + (on0 ? 4 * ql : 0));
+      const unsigned f1off = (unsigned)((on1 ? 32 : 0) * sizeof(T));       // second 16-byte piece of the row
+      const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);    // 32-bit shared-window address
+      const unsigned row_sbytes = (unsigned)stride * 4u, ql16 = (unsigned)ql << 4, swz_mask = (unsigned)(nqp - 1) << 4;
       const int nitems = ctl[0];
-      for (;;) {
-        int it = 0;
-        if (hl == 0) it = atomicAdd(&ctl[1], 1);
-        it = __shfl_sync(hmask, it, 0, 16);
-        if (it >= nitems) break;
-        int i = seg[heads[it]];
-        const int iend = seg[heads[it + 1]];
-        if (i >= iend) continue;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int2 r[LS_WIN];
-        ls_load_recs(rso, i, min(LS_WIN, iend - i), r);
-        while (i < iend) {
-          float4 f[LS_WIN];
+      // Static round-robin of work items over the CTA's 32 quarter-warps.  A stream's items
+      // form one flat sequence of LS_QWIN-record windows: accumulators are flushed by the
+      // last-of-cell flags (every item ends on one), so nothing special happens between items
+      // and the next window's records are always prefetched one window ahead.
+      int it = tid >> 3;
+      const int2* p = nullptr;
+      int wleft = 0;
+      for (; it < nitems; it += LS_THREADS / 8) {
+        wleft = (pstart[it + 1] - pstart[it]) / LS_QWIN;
+        if (wleft > 0) { p = rsp + pstart[it]; break; }
+      }
+      if (wleft > 0) {
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int2 r[LS_QWIN];
 #pragma unroll
-          for (int u = 0; u < LS_WIN; ++u)
-            f[u] = ls_load4<T>(reinterpret_cast<const T*>(
-                fbytes + (unsigned long long)(unsigned)(r[u].x & LS_REC_PIX_MASK) * row_bytes));
-          // records of the next window are fetched while this window's feature rows are in flight
-          i += LS_WIN;
-          int2 rn[LS_WIN];
-          if (i < iend) ls_load_recs(rso, i, min(LS_WIN, iend - i), rn);
+        for (int u = 0; u < LS_QWIN; ++u) r[u] = p[u];          // quarter-warp-uniform 8-byte loads
+#ifdef LS_PROFILE
+        long long tb0 = clock64();
+        if (threadIdx.x == 0 && blockIdx.x < 8192) {
+          if (r[0].x + r[1].x + r[2].x + r[3].x == 0x7f123456) tb0 = 0;   // wait for the records
+          ls_dbg_cta[blockIdx.x][6] = (int)(clock64() - tick__);
+        }
+        bool first_win__ = true;
+#endif
+        for (;;) {
+          float4 fa[LS_QWIN], fb[LS_QWIN];
 #pragma unroll
-          for (int u = 0; u < LS_WIN; ++u) {
-            const float w = __int_as_float(r[u].y);
-            acc.x = fmaf(w, f[u].x, acc.x);
-            acc.y = fmaf(w, f[u].y, acc.y);
-            acc.z = fmaf(w, f[u].z, acc.z);
-            acc.w = fmaf(w, f[u].w, acc.w);
-            if (r[u].x & LS_REC_LAST) {
-              const int cl = (r[u].x >> 20) & 255;
-              if (lane_on) *reinterpret_cast<float4*>(tile + cl * stride + 4 * ls_tile_quad(cl, hl, nqp)) = acc;
-              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < LS_QWIN; ++u) {
+            // base + pixel * row_bytes as one 32x32+64 multiply-add
+            const char* row = f0 + (unsigned long long)((unsigned)r[u].x >> 12) * row_bytes;
+            fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));
+            fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));
+          }
+          // locate and fetch the next window while these feature rows are in flight
+          bool more = true;
+          if (--wleft > 0) {
+            p += LS_QWIN;
+          } else {
+            more = false;
+            for (it += LS_THREADS / 8; it < nitems; it += LS_THREADS / 8) {
+              wleft = (pstart[it + 1] - pstart[it]) / LS_QWIN;
+              if (wleft > 0) { p = rsp + pstart[it]; more = true; break; }
             }
           }
+          int2 rn[LS_QWIN];
 #pragma unroll
-          for (int u = 0; u < LS_WIN; ++u) r[u] = rn[u];
+          for (int u = 0; u < LS_QWIN; ++u) rn[u] = more ? p[u] : make_int2(0, 0);
+#ifdef LS_PROFILE
+          if (threadIdx.x == 0 && blockIdx.x < 8192 && first_win__) {
+            if (fa[0].x + fb[3].w == 1.2345e33f) tb0 = 0;                  // wait for the feature rows
+            ls_dbg_cta[blockIdx.x][7] = (int)(clock64() - tick__);
+            first_win__ = false;
+          }
+#endif
+#pragma unroll
+          for (int u = 0; u < LS_QWIN; ++u) {
+            const float wt = __int_as_float(r[u].y);
+            acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);
+            acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);
+            acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);
+            acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);
+            if (r[u].x & LS_REC_LAST) {
+              const unsigned cl = (unsigned)r[u].x & 255u;
+              // row of the cell + this lane's swizzled quads (q and q+8 differ by one address bit)
+              const unsigned rowb = tile_s + cl * row_sbytes, x0 = ql16 ^ ((cl << 1) & swz_mask);
+              const unsigned a0 = rowb + x0, a1 = rowb + (x0 ^ 0x80u);
+              if (on0)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(acc0.x), "f"(acc0.y),
+                             "f"(acc0.z), "f"(acc0.w) : "memory");
+              if (on1)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(acc1.x), "f"(acc1.y),
+                             "f"(acc1.z), "f"(acc1.w) : "memory");
+              acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
+              acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (!more) break;
+#pragma unroll
+          for (int u = 0; u < LS_QWIN; ++u) r[u] = rn[u];
         }
       }
     }
     __syncthreads();
+    LS_TICK(3);
     // ---- phase C --------------------------------------------------------------------
     if (VEC4) {
       if (inb) {
@@ -189,7 +304,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
               const float* src = srow + ((4 * q) ^ swz4);
               v.x = src[0]; v.y = src[stride]; v.z = src[2 * stride]; v.w = src[3 * stride];
             }
-            *reinterpret_cast<float4*>(gptr) = v;
+            __stcs(reinterpret_cast<float4*>(gptr), v);   // streaming: keep the features in L2, not the BEV
           }
           gptr += qstep;
         }
@@ -207,12 +322,32 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       }
     }
     __syncthreads();
+    LS_TICK(4);
   }
 }
 
+int ls_debug_fetch_phase_cycles(unsigned long long* out8) {
+#ifdef LS_PROFILE
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  LS_CUDA(cudaMemcpyFromSymbol(out8, ls_dbg_phase, sizeof(zero)));
+  LS_CUDA(cudaMemcpyToSymbol(ls_dbg_phase, zero, sizeof(zero)));
+  if (FILE* f = fopen("gpurun_out/cta_phases.bin", "wb")) {
+    static int host[8192][8];
+    if (cudaMemcpyFromSymbol(host, ls_dbg_cta, sizeof(host)) == cudaSuccess) fwrite(host, 1, sizeof(host), f);
+    fclose(f);
+  }
+  return LS_OK;
+#else
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  return LS_ERR_UNSUPPORTED;
+#endif
+}
+
+size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g) { return ls_sorted_capacity(dm.Npts, g.tiles); }
+
 static size_t ls_tile_smem_bytes(const LsDims& dm) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  return (size_t)LS_TILE * tg.stride * sizeof(float) + (2 * (LS_TILE + 1) + 16) * sizeof(int);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (4 * (LS_TILE + 1) + 32) * sizeof(int);
 }
 static size_t ls_tile_smem_max() {
   LsDims d;
@@ -297,7 +432,7 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
 #pragma unroll 4
       for (int q = 0; q < nquads; ++q) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb && cbase + 4 * q + cq < dm.C) v = __ldg(reinterpret_cast<const float4*>(gptr + q * qstep));
+        if (inb && cbase + 4 * q + cq < dm.C) v = __ldcs(reinterpret_cast<const float4*>(gptr + q * qstep));   // read once
         float* d = drow + 4 * (q ^ swz);
         d[0] = v.x; d[tg.stride] = v.y; d[2 * tg.stride] = v.z; d[3 * tg.stride] = v.w;
       }

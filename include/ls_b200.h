@@ -66,6 +66,10 @@ int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32
 /* Channel count of the internal NHWC staging rows: C rounded up to a multiple of 4. */
 int32_t ls_padded_channels(int32_t C);
 
+/* Per-sample capacity (in 8-byte records) of ls_splat_fwd's recs_scratch: the re-ordered
+ * records are stored with every work item padded to a multiple of 4 records. */
+size_t ls_sorted_records(const LsShape* s);
+
 /* a4 first half - model/bev_model.py:46-47,53:  E^-1 = inverse(extrinsics),
  * M = E^-1[:3,:3] . inverse(intrinsics),  t = E^-1[:3,3].
  * intrinsics f32[BN,3,3], extrinsics f32[BN,4,4] -> M f32[BN,3,3], t f32[BN,3].
@@ -131,7 +135,7 @@ int ls_nhwc_to_nchw(const void* src, int dtype, int32_t images, int32_t C, int32
  * VoxelsSumming.forward (tool/geometry.py:289-305): deterministic segment sum of
  * prob[p]*feat[pix(p),:] per cell, written (zeros included) to bev f32[B,C,X,Y].
  * feat_nhwc: [B*N, fh, fw, Cp] of `dtype`; recs/seg_start/tile_order from ls_sort;
- * recs_scratch: 8 B x [B,Npts], receives the records re-ordered by key inside each cell
+ * recs_scratch: 8 B x [B, ls_sorted_records()], receives the records re-ordered by key inside each cell
  * (this is what makes the sums independent of the atomics' arrival order). */
 int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32_t* seg_start,
                  const int32_t* tile_order, void* recs_scratch, const LsShape* s, float* bev,
@@ -174,6 +178,10 @@ int ls_forward(const void* feat, const void* logits, int dtype, const float* M, 
 int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext,
                 const void* prob, int dtype, const LsShape* s, void* ws, size_t ws_bytes,
                 void* grad_feat, void* grad_logits, ls_stream_t stream);
+
+/* Developer aid: per-phase clock64 totals of ls_splat_fwd (summed over CTAs) since the last
+ * call; LS_ERR_UNSUPPORTED unless the library was built with -DLS_PROFILE. */
+int ls_debug_phase_cycles(uint64_t* out8);
 
 /* Number of kernel launches (and memsets) issued by this library since load; bench.py
  * reads it around the timed region to report gpu_launches. */
