@@ -73,44 +73,52 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every
+    ~2 ms from a thread (the timed loop blocks in CUDA calls with the GIL released).  Falls
+    back to one nvidia-smi query when pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.stop_flag, self.thread, self.h = index, [], 0, False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.h = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        if self.h is None:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "samples": 1, "reasons": ["nvml unavailable: one nvidia-smi sample after the run"]}
             except Exception:
-                continue
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml/nvidia-smi unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------
@@ -375,6 +383,14 @@ def main():
         dom = max(cand, key=cand.get)
         dom_bytes = (ab["splat_fwd"] if dom == "splat_fwd" else ab["bwd_transpose"] + ab["bwd_gather"]) * shape.batch
         achieved = dom_bytes / (cand[dom] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes (read+write) per launch of that stage from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = "%s/%s" % (args.workload, args.dtype)
+            if key in tj and dom in tj[key]:
+                traffic, traffic_src = tj[key][dom], tj.get("source")
+        except Exception:
+            pass
         step_bytes = (ab["fwd"] + ab["bwd"]) * shape.batch
         step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -387,7 +403,8 @@ def main():
                                 "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": cand[dom]},
                 "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": step_gbs / peak},

@@ -1,0 +1,140 @@
+"""CPU-side checks of the boundary: the C-ABI library builds, loads and exports every
+symbol declared in include/ls_b200.h (no compute calls without a GPU), argument checking
+works across the ABI, and the host mirror of BevModel keeps the reference's contract."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from e2e_parking_carla_b200.synthetic import LiftSplatShape, make_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ls_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from e2e_parking_carla_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libls_b200.so does not export %s" % name
+    # and the ctypes prototypes cover exactly the header
+    assert sorted(_lib.PROTOTYPES) == declared
+    assert b"sm_100a" in lib.ls_version()
+
+
+def test_library_targets_sm100a_only():
+    """The shipped cubin is sm_100a: no multi-arch fatbin, no PTX for other vendors/archs."""
+    import subprocess
+    from e2e_parking_carla_b200.build import LIB_PATH, build
+    build()
+    out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_abi_argument_checking(lib):
+    """Bad arguments come back as status codes (never exceptions / crashes across the ABI)."""
+    from e2e_parking_carla_b200 import _lib
+    from e2e_parking_carla_b200 import lift_splat as ls
+    grid = ls.GridSpec((-9.95, -9.95, 0.0), (0.1, 0.1, 20.0), (200, 200, 1))
+    s = ls.make_shape(1, 4, 48, 32, 32, 64, grid)
+    tiles, cells, stride = ls.grid_cells(s)
+    assert (tiles, cells, stride) == (13 * 13, 13 * 13 * 256, 13 * 13 * 256 + 4)
+    assert ls.padded_channels(6) == 8 and ls.padded_channels(64) == 64
+    assert ls.workspace_bytes(s, ls.LS_F32, True) > ls.workspace_bytes(s, ls.LS_F32, False) > 0
+    # null pointers
+    assert lib.ls_camera_transform(None, None, 4, None, None, None) == -1
+    assert lib.ls_index(None, None, None, C.byref(s), None, None, None, None, None) == -1
+    # Z != 1 is unsupported for the splat (reference squeezes Z, model/bev_model.py:104)
+    bad = ls.make_shape(1, 4, 48, 32, 32, 64, ls.GridSpec(grid.start, grid.res, (200, 200, 2)))
+    assert lib.ls_workspace_bytes(C.byref(bad), ls.LS_F32, 1) == 0
+    with pytest.raises(ValueError):
+        ls.workspace_bytes(bad, ls.LS_F32, True)
+    # unknown dtype code
+    dummy = C.c_void_p(16)
+    assert lib.ls_softmax(dummy, 7, C.byref(s), dummy, None) == -1
+    assert lib.ls_strerror(-2) == b"unsupported configuration"
+    with pytest.raises(ValueError):
+        _lib.check(-1, "x")
+    with pytest.raises(_lib.LiftSplatLibraryError):
+        _lib.check(-3, "x")
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing on the host."""
+    from e2e_parking_carla_b200 import BevModel
+    from e2e_parking_carla_b200 import lift_splat as ls
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ls.camera_transform(torch.eye(3).expand(1, 4, 3, 3), torch.eye(4).expand(1, 4, 4, 4))
+    model = BevModel(make_cfg(LiftSplatShape()), cam_encoder=torch.nn.Identity())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.get_geometry(torch.eye(3).expand(1, 4, 3, 3), torch.eye(4).expand(1, 4, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, "e2e_parking_carla_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_bev_model_keeps_reference_contract():
+    """Constructor argument, attributes, state_dict entries and dtypes of the reference's
+    BevModel (model/bev_model.py:10-26)."""
+    from e2e_parking_carla_b200 import BevModel, calculate_birds_eye_view_parameters
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+
+    cfg = make_cfg(LiftSplatShape())
+    m = BevModel(cfg, cam_encoder=Enc())
+    sd = m.state_dict()
+    assert list(sd) == ["bev_res", "bev_start_pos", "bev_dim", "frustum", "cam_encoder.w"]
+    assert sd["bev_dim"].dtype == torch.int64 and sd["bev_dim"].tolist() == [200, 200, 1]
+    assert sd["bev_res"].dtype == torch.float32 and sd["frustum"].shape == (48, 32, 32, 3)
+    assert not any(p.requires_grad for n, p in m.named_parameters() if not n.startswith("cam_encoder"))
+    assert m.depth_channel == 48 and m.down_sample == 8 and m.cfg is cfg
+    for name in ("create_frustum", "get_geometry", "encoder_forward", "proj_bev_feature", "calc_bev_feature", "forward"):
+        assert callable(getattr(m, name))
+    res, start, dim = calculate_birds_eye_view_parameters([-10.0, 10.0, 0.05], [-10.0, 10.0, 0.05], [-10.0, 10.0, 20.0])
+    assert dim.tolist() == [400, 400, 1] and dim.dtype == torch.int64
+    # strict load of a reference-shaped checkpoint (agent/parking_agent.py:260-262)
+    m2 = BevModel(cfg, cam_encoder=Enc())
+    m2.load_state_dict(sd, strict=True)
+    # configurations the reference cannot run either are rejected up front
+    bad = make_cfg(LiftSplatShape())
+    bad.use_depth_distribution = 0
+    with pytest.raises(ValueError):
+        BevModel(bad, cam_encoder=Enc())
+    bad = make_cfg(LiftSplatShape(bev_z_bound=[-10.0, 10.0, 10.0]))
+    with pytest.raises(ValueError):
+        BevModel(bad, cam_encoder=Enc())
+
+
+def test_reference_state_dict_loads(tmp_path):
+    """A state_dict produced by the reference's own BevModel loads strictly (when the
+    reference tree is available in this container)."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    from e2e_parking_carla_b200 import BevModel
+    cfg = make_cfg(LiftSplatShape())
+    ref = rh.reference_bev_model(cfg)
+    ours = BevModel(cfg, cam_encoder=torch.nn.Identity())
+    sd = {k: v for k, v in ref.state_dict().items() if not k.startswith("cam_encoder")}
+    ours.load_state_dict(sd, strict=True)
+    for k, v in sd.items():
+        assert torch.equal(getattr(ours, k).data, v) and getattr(ours, k).dtype == v.dtype
