@@ -180,8 +180,8 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const int ql = tid & 7;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
   const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
-  // phase C geometry of this thread (fixed): 4 consecutive y, one channel of a quad, one x-row
-  const int y4 = tid & 3, cq = (tid >> 2) & 3, xr = (tid >> 4) & 15;
+  // phase C geometry of this thread (fixed): 4 consecutive y of one x-row; channel quads qg, qg+4, ...
+  const int y4 = tid & 3, xr = (tid >> 2) & 15, qg = tid >> 6;
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
   const bool inb = gx < grid.X && gy < grid.Y;
   const int clc = xr * LS_TY + 4 * y4;
@@ -292,21 +292,28 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
     // ---- phase C --------------------------------------------------------------------
     if (VEC4) {
       if (inb) {
-        const int swz4 = 4 * ((clc >> 3) & (nqp - 1));
-        const float* srow = tile + clc * stride + cq;
-        float* gptr = bev + (size_t)b * st.b + (size_t)(cbase + cq) * st.c + (size_t)gx * st.x + gy;
-        const size_t qstep = (size_t)4 * st.c;
-#pragma unroll 8
-        for (int q = 0; q < nquads; ++q) {
-          if (kCC || cbase + 4 * q + cq < dm.C) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!tile_empty) {
-              const float* src = srow + ((4 * q) ^ swz4);
-              v.x = src[0]; v.y = src[stride]; v.z = src[2 * stride]; v.w = src[3 * stride];
-            }
-            __stcs(reinterpret_cast<float4*>(gptr), v);   // streaming: keep the features in L2, not the BEV
+        // a thread reads one channel quad of 4 consecutive cells (4 x 16 B, conflict-free),
+        // transposes the 4x4 block in registers and writes 4 channels x 4 y as 16-byte
+        // streaming stores (the 164 MB output stream must not evict the feature rows from L2)
+        const int swz = (clc >> 3) & (nqp - 1);
+        const float* srow = tile + clc * stride;
+        float* gbase = bev + (size_t)b * st.b + (size_t)cbase * st.c + (size_t)gx * st.x + gy;
+#pragma unroll 4
+        for (int q = qg; q < nquads; q += LS_THREADS / 64) {
+          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
+          if (!tile_empty) {
+            const float* src = srow + 4 * (q ^ swz);
+            r0 = *reinterpret_cast<const float4*>(src);
+            r1 = *reinterpret_cast<const float4*>(src + stride);
+            r2 = *reinterpret_cast<const float4*>(src + 2 * stride);
+            r3 = *reinterpret_cast<const float4*>(src + 3 * stride);
           }
-          gptr += qstep;
+          float* g = gbase + (size_t)(4 * q) * st.c;
+          const int c = cbase + 4 * q;
+          if (kCC || c + 0 < dm.C) __stcs(reinterpret_cast<float4*>(g), make_float4(r0.x, r1.x, r2.x, r3.x));
+          if (kCC || c + 1 < dm.C) __stcs(reinterpret_cast<float4*>(g + st.c), make_float4(r0.y, r1.y, r2.y, r3.y));
+          if (kCC || c + 2 < dm.C) __stcs(reinterpret_cast<float4*>(g + 2 * st.c), make_float4(r0.z, r1.z, r2.z, r3.z));
+          if (kCC || c + 3 < dm.C) __stcs(reinterpret_cast<float4*>(g + 3 * st.c), make_float4(r0.w, r1.w, r2.w, r3.w));
         }
       }
     } else {
@@ -417,7 +424,7 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   __syncthreads();
   if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
   float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp;
-  const int y4 = tid & 3, cq = (tid >> 2) & 3, xr = (tid >> 4) & 15;
+  const int y4 = tid & 3, xr = (tid >> 2) & 15, qg = tid >> 6;
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
   const bool inb = gx < grid.X && gy < grid.Y;
   const int clc = xr * LS_TY + 4 * y4;
@@ -425,16 +432,27 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
     const int cc = min(tg.cc, dm.Cp - cbase);
     const int nquads = cc >> 2;
     if (VEC4) {
+      // 4 channels x 4 y per thread: four 16-byte loads, a 4x4 register transpose, four
+      // 16-byte conflict-free shared stores (rows of 4 consecutive cells, one channel quad)
       const int swz = (clc >> 3) & (tg.nqp - 1);
-      float* drow = tile + clc * tg.stride + cq;
-      const float* gptr = gbev + (size_t)b * st.b + (size_t)(cbase + cq) * st.c + (size_t)gx * st.x + gy;
-      const size_t qstep = (size_t)4 * st.c;
+      float* drow = tile + clc * tg.stride;
+      const float* gbase = gbev + (size_t)b * st.b + (size_t)cbase * st.c + (size_t)gx * st.x + gy;
 #pragma unroll 4
-      for (int q = 0; q < nquads; ++q) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb && cbase + 4 * q + cq < dm.C) v = __ldcs(reinterpret_cast<const float4*>(gptr + q * qstep));   // read once
+      for (int q = qg; q < nquads; q += LS_THREADS / 64) {
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+        const float* g = gbase + (size_t)(4 * q) * st.c;
+        const int c = cbase + 4 * q;
+        if (inb) {
+          if (c + 0 < dm.C) c0 = __ldg(reinterpret_cast<const float4*>(g));
+          if (c + 1 < dm.C) c1 = __ldg(reinterpret_cast<const float4*>(g + st.c));
+          if (c + 2 < dm.C) c2 = __ldg(reinterpret_cast<const float4*>(g + 2 * st.c));
+          if (c + 3 < dm.C) c3 = __ldg(reinterpret_cast<const float4*>(g + 3 * st.c));
+        }
         float* d = drow + 4 * (q ^ swz);
-        d[0] = v.x; d[tg.stride] = v.y; d[2 * tg.stride] = v.z; d[3 * tg.stride] = v.w;
+        *reinterpret_cast<float4*>(d) = make_float4(c0.x, c1.x, c2.x, c3.x);
+        *reinterpret_cast<float4*>(d + tg.stride) = make_float4(c0.y, c1.y, c2.y, c3.y);
+        *reinterpret_cast<float4*>(d + 2 * tg.stride) = make_float4(c0.z, c1.z, c2.z, c3.z);
+        *reinterpret_cast<float4*>(d + 3 * tg.stride) = make_float4(c0.w, c1.w, c2.w, c3.w);
       }
     } else {
       for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
