@@ -237,6 +237,7 @@ class Stepper:
         counts = torch.zeros(sh.batch, cells, dtype=torch.int32, device=dev)
         seg = torch.empty(sh.batch, stride, dtype=torch.int32, device=dev)
         order = torch.empty(sh.batch, tiles, dtype=torch.int32, device=dev)
+        tscr = torch.empty_like(order)
         recs = torch.empty(sh.batch, npts, 2, dtype=torch.int32, device=dev)
         recs2 = torch.empty(sh.batch, int(lib.ls_sorted_records(C.byref(s))), 2, dtype=torch.int32, device=dev)
         pix = torch.empty(sh.batch * sh.cams * sh.fh * sh.fw, sh.depth_bins, 2, dtype=torch.int32, device=dev)
@@ -251,7 +252,7 @@ class Stepper:
             ("camera_transform", lambda: lib.ls_camera_transform(P(d["intr"]), P(d["extr"]), bn, P(self.M), P(self.t), stream)),
             ("index+hist", lambda: (counts.zero_(), lib.ls_index(P(self.M), P(self.t), P(self.frustum), C.byref(s), None, P(cell), P(within), P(counts), stream))[1]),
             ("softmax", lambda: lib.ls_softmax(P(d["logits"]), self.code, C.byref(s), P(self.prob), stream)),
-            ("sort(scan+place)", lambda: lib.ls_sort(P(cell), P(within), P(counts), P(self.prob), self.code, C.byref(s), P(seg), P(order), P(recs), P(pix), stream)),
+            ("sort(scan+place)", lambda: lib.ls_sort(P(cell), P(within), P(counts), P(self.prob), self.code, C.byref(s), P(seg), P(order), P(tscr), P(recs), P(pix), stream)),
             ("nchw_to_nhwc", lambda: lib.ls_nchw_to_nhwc(P(d["feat"]), self.code, bn, sh.channels, hw, P(featT), stream)),
             ("splat_fwd", lambda: lib.ls_splat_fwd(P(featT), self.code, P(recs), P(seg), P(order), P(recs2), C.byref(s), P(self.bev), C.byref(self.st), stream)),
             ("splat_bwd(transpose+gather)", lambda: lib.ls_splat_bwd(P(d["gbev"]), C.byref(self.gst), P(featT), self.code, P(pix), P(seg), C.byref(s), P(gT), P(gprob), P(gfeatT), stream)),

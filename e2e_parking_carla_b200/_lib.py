@@ -43,7 +43,7 @@ PROTOTYPES = {
     "ls_geometry": (C.c_int, [_P, _P, _P, _SH, _P, _P]),
     "ls_index": (C.c_int, [_P, _P, _P, _SH, _P, _P, _P, _P, _P]),
     "ls_export_indices": (C.c_int, [_P, _P, _P, _SH, _P, _P, _P, _P]),
-    "ls_sort": (C.c_int, [_P, _P, _P, _P, C.c_int, _SH, _P, _P, _P, _P, _P]),
+    "ls_sort": (C.c_int, [_P, _P, _P, _P, C.c_int, _SH, _P, _P, _P, _P, _P, _P]),
     "ls_export_cell_counts": (C.c_int, [_P, _SH, C.c_int32, _P, _P, _P]),
     "ls_softmax": (C.c_int, [_P, C.c_int, _SH, _P, _P]),
     "ls_nchw_to_nhwc": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

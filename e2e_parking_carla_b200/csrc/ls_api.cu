@@ -39,7 +39,7 @@ static bool ls_dtype_ok(int dtype) { return dtype == LS_F32 || dtype == LS_BF16;
 
 // ---- workspace carving -------------------------------------------------------------
 struct LsWs {
-  int *cell, *within, *counts, *seg_start, *tile_order;
+  int *cell, *within, *counts, *seg_start, *tile_order, *tile_tot;
   int2 *recs, *recs_sorted, *pix_recs;
   void* featT;
   float *gT, *gprob_pm;
@@ -61,6 +61,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base)
   w.featT = take(feat);                       // kept for backward
   w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);   // kept for backward
   w.tile_order = (int*)take((size_t)dm.B * g.tiles * 4);
+  w.tile_tot = (int*)take((size_t)dm.B * g.tiles * 4);
   w.counts = (int*)take((size_t)dm.B * g.Vc * 4);
   w.cell = (int*)take(pts * 4);
   w.within = (int*)take(pts * 4);
@@ -148,15 +149,15 @@ int ls_index(const float* M, const float* t, const float* frustum, const LsShape
 }
 
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob, int dtype,
-            const LsShape* s, int32_t* seg_start, int32_t* tile_order, void* recs, void* pix_recs,
-            ls_stream_t stream) {
+            const LsShape* s, int32_t* seg_start, int32_t* tile_order, int32_t* tile_scratch, void* recs,
+            void* pix_recs, ls_stream_t stream) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
   if (!cell || !within || !counts || !prob || !seg_start || !tile_order || !recs || !ls_dtype_ok(dtype))
     return LS_ERR_BAD_ARG;
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
-  if ((rc = ls_launch_scan(counts, dm, g, seg_start, tile_order, (cudaStream_t)stream))) return rc;
+  if ((rc = ls_launch_scan(counts, dm, g, seg_start, tile_order, tile_scratch, (cudaStream_t)stream))) return rc;
   return ls_launch_place(cell, within, prob, dtype, dm, g, seg_start, (int2*)recs, (int2*)pix_recs,
                          (cudaStream_t)stream);
 }
@@ -242,7 +243,7 @@ int ls_forward(const void* feat, const void* logits, int dtype, const float* M, 
   LS_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)dm.B * g.Vc * sizeof(int), stream));
   ls_note_launch();
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
-  if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, stream))) return rc;
+  if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, w.tile_tot, stream))) return rc;
   if ((rc = ls_launch_softmax(logits, dtype, dm, prob, stream))) return rc;
   if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs,
                             with_backward ? w.pix_recs : nullptr, stream)))

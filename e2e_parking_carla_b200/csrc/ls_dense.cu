@@ -8,7 +8,7 @@
 // softmax over depth.  CTA = (image, 32 pixels); thread (lane = pixel, dg = depth group 0..7)
 // owns bins dg, dg+8, ... in registers; max and sum are combined through shared memory.
 // =====================================================================================
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ prob) {
   __shared__ float red[8][33];
@@ -18,10 +18,10 @@ ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ p
   const bool on = rc < HW;
   const T* src = logits + (size_t)img * D * HW + rc;
   T* dst = prob + (size_t)img * D * HW + rc;
-  float x[LS_SM_MAXK];
+  float x[K];
   float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < LS_SM_MAXK; ++k) {
+  for (int k = 0; k < K; ++k) {
     const int d = dg + 8 * k;
     x[k] = (on && d < D) ? ls_to_float(src[(size_t)d * HW]) : -INFINITY;
     m = fmaxf(m, x[k]);
@@ -33,7 +33,7 @@ ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ p
   __syncthreads();
   float s = 0.0f;
 #pragma unroll
-  for (int k = 0; k < LS_SM_MAXK; ++k) {
+  for (int k = 0; k < K; ++k) {
     const int d = dg + 8 * k;
     x[k] = (on && d < D) ? expf(x[k] - m) : 0.0f;
     s += x[k];
@@ -44,7 +44,7 @@ ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ p
 #pragma unroll
   for (int j = 0; j < 8; ++j) s += red[j][lane];
 #pragma unroll
-  for (int k = 0; k < LS_SM_MAXK; ++k) {
+  for (int k = 0; k < K; ++k) {
     const int d = dg + 8 * k;
     if (on && d < D) dst[(size_t)d * HW] = ls_from_float<T>(__fdiv_rn(x[k], s));
   }
@@ -67,15 +67,27 @@ ls_softmax_serial_kernel(const T* __restrict__ logits, int D, int HW, T* __restr
     dst[(size_t)d * HW] = ls_from_float<T>(__fdiv_rn(expf(ls_to_float(src[(size_t)d * HW]) - m), s));
 }
 
+template <typename T>
+static void ls_softmax_dispatch(const T* logits, const LsDims& dm, T* prob, dim3 grid, cudaStream_t s) {
+  const int k = (dm.D + 7) / 8;
+#define LS_SM(KK) ls_softmax_kernel<T, KK><<<grid, 256, 0, s>>>(logits, dm.D, dm.HW, prob)
+  if (k <= 2) LS_SM(2);
+  else if (k <= 4) LS_SM(4);
+  else if (k <= 6) LS_SM(6);
+  else if (k <= 8) LS_SM(8);
+  else if (k <= 12) LS_SM(12);
+  else LS_SM(16);
+#undef LS_SM
+}
+
 int ls_launch_softmax(const void* logits, int dtype, const LsDims& dm, void* prob, cudaStream_t s) {
   const int images = dm.B * dm.N;
   if (dm.D <= 8 * LS_SM_MAXK) {
     dim3 grid((dm.HW + 31) / 32, images);
     if (dtype == LS_F32)
-      ls_softmax_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, dm.D, dm.HW, (float*)prob);
+      ls_softmax_dispatch<float>((const float*)logits, dm, (float*)prob, grid, s);
     else
-      ls_softmax_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, dm.D, dm.HW,
-                                                            (__nv_bfloat16*)prob);
+      ls_softmax_dispatch<__nv_bfloat16>((const __nv_bfloat16*)logits, dm, (__nv_bfloat16*)prob, grid, s);
   } else {
     dim3 grid((dm.HW + 255) / 256, images);
     if (dtype == LS_F32)
@@ -93,7 +105,7 @@ int ls_launch_softmax(const void* logits, int dtype, const LsDims& dm, void* pro
 // grad_prob arrives PIXEL-major [image][pixel][D] from the gather kernel; it is staged through
 // shared memory so that both its reads and the depth-major writes are coalesced.
 // =====================================================================================
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_softmax_bwd_kernel(const T* __restrict__ prob, const float* __restrict__ gprob_pm, const T* __restrict__ gext,
                       int D, int HW, T* __restrict__ glogits) {
@@ -104,47 +116,99 @@ ls_softmax_bwd_kernel(const T* __restrict__ prob, const float* __restrict__ gpro
   const int img = blockIdx.y, rc0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
   const int valid = min(32, HW - rc0);
+  const int rc = rc0 + lane;
+  const bool on = rc < HW;
+  const size_t base = (size_t)img * D * HW + rc;
+  // depth-major operands first (independent loads, all in flight), pixel-major rows meanwhile
+  float p[K], g[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int d = dg + 8 * k;
+    p[k] = 0.0f; g[k] = 0.0f;
+    if (on && d < D) {
+      p[k] = ls_to_float(prob[base + (size_t)d * HW]);
+      if (gext) g[k] = ls_to_float(gext[base + (size_t)d * HW]);
+    }
+  }
   const float* gsrc = gprob_pm + ((size_t)img * HW + rc0) * D;
   for (int r = dg; r < valid; r += 8)
     for (int d = lane; d < D; d += 32) stage[r * Dp + d] = gsrc[(size_t)r * D + d];
   __syncthreads();
-  const int rc = rc0 + lane;
-  const bool on = rc < HW;
-  const size_t base = (size_t)img * D * HW + rc;
   float dot = 0.0f;
-  for (int d = dg; d < D; d += 8) {
-    if (on) {
-      float g = stage[lane * Dp + d];
-      if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
-      dot = fmaf(ls_to_float(prob[base + (size_t)d * HW]), g, dot);
-    }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int d = dg + 8 * k;
+    if (on && d < D) { g[k] += stage[lane * Dp + d]; dot = fmaf(p[k], g[k], dot); }
   }
   red[dg * 33 + lane] = dot;
   __syncthreads();
   dot = 0.0f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) dot += red[j * 33 + lane];
-  for (int d = dg; d < D; d += 8) {
-    if (on) {
-      float g = stage[lane * Dp + d];
-      if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
-      glogits[base + (size_t)d * HW] = ls_from_float<T>(ls_to_float(prob[base + (size_t)d * HW]) * (g - dot));
-    }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int d = dg + 8 * k;
+    if (on && d < D) glogits[base + (size_t)d * HW] = ls_from_float<T>(p[k] * (g[k] - dot));
   }
+}
+
+// generic fallback for D > 128
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_softmax_bwd_serial_kernel(const T* __restrict__ prob, const float* __restrict__ gprob_pm, const T* __restrict__ gext,
+                             int D, int HW, T* __restrict__ glogits) {
+  const int img = blockIdx.y;
+  const int rc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rc >= HW) return;
+  const size_t base = (size_t)img * D * HW + rc;
+  const float* gsrc = gprob_pm + ((size_t)img * HW + rc) * D;
+  float dot = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    float g = gsrc[d];
+    if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
+    dot = fmaf(ls_to_float(prob[base + (size_t)d * HW]), g, dot);
+  }
+  for (int d = 0; d < D; ++d) {
+    float g = gsrc[d];
+    if (gext) g += ls_to_float(gext[base + (size_t)d * HW]);
+    glogits[base + (size_t)d * HW] = ls_from_float<T>(ls_to_float(prob[base + (size_t)d * HW]) * (g - dot));
+  }
+}
+
+template <typename T>
+static void ls_softmax_bwd_dispatch(const T* prob, const float* gprob_pm, const T* gext, const LsDims& dm, T* glogits,
+                                    dim3 grid, size_t smem, cudaStream_t s) {
+  const int k = (dm.D + 7) / 8;
+#define LS_SB(KK) ls_softmax_bwd_kernel<T, KK><<<grid, 256, smem, s>>>(prob, gprob_pm, gext, dm.D, dm.HW, glogits)
+  if (k <= 2) LS_SB(2);
+  else if (k <= 4) LS_SB(4);
+  else if (k <= 6) LS_SB(6);
+  else if (k <= 8) LS_SB(8);
+  else if (k <= 12) LS_SB(12);
+  else LS_SB(16);
+#undef LS_SB
 }
 
 int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* gext, int dtype, const LsDims& dm,
                           void* glogits, cudaStream_t s) {
-  dim3 grid((dm.HW + 31) / 32, dm.B * dm.N);
   const size_t smem = ((size_t)32 * (dm.D | 1) + 8 * 33) * sizeof(float);
-  if (smem > 48 * 1024) return LS_ERR_UNSUPPORTED;
-  if (dtype == LS_F32)
-    ls_softmax_bwd_kernel<float><<<grid, 256, smem, s>>>((const float*)prob, gprob_pm, (const float*)gext, dm.D,
-                                                         dm.HW, (float*)glogits);
-  else
-    ls_softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)prob, gprob_pm,
-                                                                 (const __nv_bfloat16*)gext, dm.D, dm.HW,
-                                                                 (__nv_bfloat16*)glogits);
+  if (dm.D <= 8 * LS_SM_MAXK && smem <= 48 * 1024) {
+    dim3 grid((dm.HW + 31) / 32, dm.B * dm.N);
+    if (dtype == LS_F32)
+      ls_softmax_bwd_dispatch<float>((const float*)prob, gprob_pm, (const float*)gext, dm, (float*)glogits, grid, smem, s);
+    else
+      ls_softmax_bwd_dispatch<__nv_bfloat16>((const __nv_bfloat16*)prob, gprob_pm, (const __nv_bfloat16*)gext, dm,
+                                             (__nv_bfloat16*)glogits, grid, smem, s);
+  } else {
+    dim3 grid((dm.HW + 255) / 256, dm.B * dm.N);
+    if (dtype == LS_F32)
+      ls_softmax_bwd_serial_kernel<float><<<grid, 256, 0, s>>>((const float*)prob, gprob_pm, (const float*)gext, dm.D,
+                                                               dm.HW, (float*)glogits);
+    else
+      ls_softmax_bwd_serial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)prob, gprob_pm,
+                                                                       (const __nv_bfloat16*)gext, dm.D, dm.HW,
+                                                                       (__nv_bfloat16*)glogits);
+  }
   LS_LAUNCHED();
   return LS_OK;
 }

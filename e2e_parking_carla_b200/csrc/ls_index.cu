@@ -7,55 +7,72 @@
 // camera transform: E^-1, K^-1 (fp64 Gauss-Jordan, partial pivoting), M = R . K^-1
 // reference: model/bev_model.py:46-47,53     oracle: camera_transform
 // =====================================================================================
+// Fully unrolled (static register indexing: no local memory): the pivot row is swapped in
+// with predicated moves.  Same operation order as oracle/_gauss_jordan_f64.
 template <int n>
-__device__ void ls_gauss_jordan(double (*a)[2 * n]) {
+__device__ __forceinline__ void ls_gauss_jordan(double (&a)[n][2 * n]) {
+#pragma unroll
   for (int k = 0; k < n; ++k) {
     int p = k;
     double best = fabs(a[k][k]);
+#pragma unroll
     for (int i = k + 1; i < n; ++i) {
       const double v = fabs(a[i][k]);
       if (v > best) { best = v; p = i; }   // first maximum wins (numpy argmax)
     }
-    if (p != k) {
-      for (int j = 0; j < 2 * n; ++j) { const double tmp = a[k][j]; a[k][j] = a[p][j]; a[p][j] = tmp; }
+#pragma unroll
+    for (int i = k + 1; i < n; ++i) {
+      if (p == i) {
+#pragma unroll
+        for (int j = 0; j < 2 * n; ++j) { const double tmp = a[k][j]; a[k][j] = a[i][j]; a[i][j] = tmp; }
+      }
     }
     const double piv = a[k][k];
+#pragma unroll
     for (int j = 0; j < 2 * n; ++j) a[k][j] = __ddiv_rn(a[k][j], piv);
+#pragma unroll
     for (int i = 0; i < n; ++i) {
       if (i == k) continue;
       const double f = a[i][k];
+#pragma unroll
       for (int j = 0; j < 2 * n; ++j) a[i][j] = __dsub_rn(a[i][j], __dmul_rn(f, a[k][j]));
     }
   }
 }
 
-__global__ void ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr,
-                                           int BN, float* __restrict__ M, float* __restrict__ t) {
+__global__ void __launch_bounds__(32)
+ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr, int BN,
+                           float* __restrict__ M, float* __restrict__ t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BN) return;
   double e[4][8];
+#pragma unroll
   for (int r = 0; r < 4; ++r)
+#pragma unroll
     for (int c = 0; c < 4; ++c) { e[r][c] = (double)extr[i * 16 + r * 4 + c]; e[r][4 + c] = (r == c) ? 1.0 : 0.0; }
   ls_gauss_jordan<4>(e);
   double k[3][6];
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) { k[r][c] = (double)intr[i * 9 + r * 3 + c]; k[r][3 + c] = (r == c) ? 1.0 : 0.0; }
   ls_gauss_jordan<3>(k);
-  float rot[3][3], kin[3][3];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) { rot[r][c] = (float)e[r][4 + c]; kin[r][c] = (float)k[r][3 + c]; }
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     t[i * 3 + r] = (float)e[r][7];
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc = 0.0f;  // aten's small-matrix bmm: unfused, k ascending, from +0
-      for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn(rot[r][q], kin[q][c]));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn((float)e[r][4 + q], (float)k[q][3 + c]));
       M[i * 9 + r * 3 + c] = acc;
     }
   }
 }
 
 int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s) {
-  ls_camera_transform_kernel<<<(BN + 31) / 32, 32, 0, s>>>(intr, extr, BN, M, t);
+  // one camera per thread, spread thin (4 per CTA) so the serial fp64 chains run on many SMs
+  ls_camera_transform_kernel<<<(BN + 3) / 4, 4, 0, s>>>(intr, extr, BN, M, t);
   LS_LAUNCHED();
   return LS_OK;
 }
@@ -215,8 +232,67 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
   if (tid == 0) seg[g.Vc] = carry;
 }
 
+// Parallel form for grids of up to 2048 tiles: (1) one warp per tile sums its 256 counts;
+// (2) one warp per tile rebuilds its own base (sum of the totals of the tiles before it), its
+// place in the heaviest-first order, and the in-tile scan.  No cross-CTA dependency.
+__global__ void __launch_bounds__(256)
+ls_tile_totals_kernel(const int* __restrict__ counts, int ntiles_all, int* __restrict__ tile_tot) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= ntiles_all) return;
+  const int4* q = reinterpret_cast<const int4*>(counts + (size_t)t * LS_TILE) + lane * 2;
+  const int4 a = q[0], c = q[1];
+  int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) tile_tot[t] = s;
+}
+
+__global__ void __launch_bounds__(256)
+ls_tile_scan_kernel(const int* __restrict__ counts, const int* __restrict__ tile_tot, LsGrid g,
+                    int* __restrict__ seg_start, int* __restrict__ tile_order) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= g.tiles) return;
+  const int* tot = tile_tot + (size_t)b * g.tiles;
+  const int mine = tot[t];
+  int base = 0, rank = 0;
+  for (int j = lane; j < g.tiles; j += 32) {
+    const int o = tot[j];
+    base += (j < t) ? o : 0;
+    rank += (o > mine || (o == mine && j < t)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    base += __shfl_xor_sync(0xffffffffu, base, o);
+    rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  }
+  const int4* q = reinterpret_cast<const int4*>(counts + ((size_t)b * g.tiles + t) * LS_TILE) + lane * 2;
+  const int4 a = q[0], c = q[1];
+  const int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+  const int e0 = base + ls_warp_incl_scan(s, lane) - s;
+  int4 o0, o1;
+  o0.x = e0; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
+  o1.x = o0.w + a.w; o1.y = o1.x + c.x; o1.z = o1.y + c.y; o1.w = o1.z + c.z;
+  int* seg = seg_start + (size_t)b * g.seg_stride;
+  int4* dst = reinterpret_cast<int4*>(seg + (size_t)t * LS_TILE) + lane * 2;
+  dst[0] = o0;
+  dst[1] = o1;
+  if (lane == 0) {
+    if (tile_order) tile_order[(size_t)b * g.tiles + rank] = t;
+    if (t == g.tiles - 1) seg[g.Vc] = base + mine;
+  }
+}
+
 int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, int* tile_order,
-                   cudaStream_t s) {
+                   int* tile_tot, cudaStream_t s) {
+  if (g.tiles <= 2048 && tile_tot) {
+    const int all = g.tiles * dm.B;
+    ls_tile_totals_kernel<<<(all + 7) / 8, 256, 0, s>>>(counts, all, tile_tot);
+    LS_LAUNCHED();
+    ls_tile_scan_kernel<<<dim3((g.tiles + 7) / 8, dm.B), 256, 0, s>>>(counts, tile_tot, g, seg_start, tile_order);
+    LS_LAUNCHED();
+    return LS_OK;
+  }
   ls_scan_kernel<<<dm.B, 1024, 0, s>>>(counts, g, seg_start, tile_order);
   LS_LAUNCHED();
   return LS_OK;
@@ -233,7 +309,7 @@ int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* se
 // CTA = (sample, camera, 32 consecutive pixels) x all depth bins; loads are coalesced over
 // pixels, the pixel-major rows are transposed through shared memory.
 // =====================================================================================
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, const T* __restrict__ prob, LsDims dm,
                 LsGrid grid, const int* __restrict__ seg_start, int2* __restrict__ recs, int2* __restrict__ pix_recs) {
@@ -245,16 +321,32 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
   const int* seg = seg_start + (size_t)b * grid.seg_stride;
   if (rc < dm.HW) {
     const int pix = n * dm.HW + rc;
-    for (int d = dg; d < dm.D; d += 8) {
-      const size_t idx = (size_t)b * dm.Npts + (size_t)(n * dm.D + d) * dm.HW + rc;
-      const int c = cell[idx];
-      const int wbits = __float_as_int(ls_to_float(prob[idx]));
-      if (c >= 0) {
-        const int slot = seg[c] + within[idx];
-        const int key = ((c & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
-        recs[(size_t)b * dm.Npts + slot] = make_int2(key, wbits);
+    // K = ceil(D/8) depth bins per thread, unrolled: the three streams and the dependent
+    // seg_start lookups of all bins are in flight together
+    int c[K], tk[K], wb[K], sg[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int d = dg + 8 * k;
+      c[k] = -1; tk[k] = 0; wb[k] = 0;
+      if (d < dm.D) {
+        const size_t idx = (size_t)b * dm.Npts + (size_t)(n * dm.D + d) * dm.HW + rc;
+        c[k] = cell[idx];
+        tk[k] = within[idx];
+        wb[k] = __float_as_int(ls_to_float(prob[idx]));
       }
-      if (pix_recs) stage[lane * Dp + d] = make_int2(c >= 0 ? c : grid.Vc, wbits);   // Vc = zero row
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) sg[k] = (c[k] >= 0) ? __ldg(seg + c[k]) : 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int d = dg + 8 * k;
+      if (d < dm.D) {
+        if (c[k] >= 0) {
+          const int key = ((c[k] & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
+          recs[(size_t)b * dm.Npts + sg[k] + tk[k]] = make_int2(key, wb[k]);
+        }
+        if (pix_recs) stage[lane * Dp + d] = make_int2(c[k] >= 0 ? c[k] : grid.Vc, wb[k]);   // Vc = zero row
+      }
     }
   }
   if (!pix_recs) return;
@@ -265,16 +357,35 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
     for (int d = lane; d < dm.D; d += 32) dst[(size_t)r * dm.D + d] = stage[r * Dp + d];
 }
 
+template <typename T>
+static int ls_place_dispatch(const int* cell, const int* within, const T* prob, const LsDims& dm, const LsGrid& g,
+                             const int* seg_start, int2* recs, int2* pix_recs, dim3 grid, size_t smem, cudaStream_t s) {
+  const int k = (dm.D + 7) / 8;
+#define LS_PL(KK) ls_place_kernel<T, KK><<<grid, 256, smem, s>>>(cell, within, prob, dm, g, seg_start, recs, pix_recs)
+  if (k <= 2) LS_PL(2);
+  else if (k <= 4) LS_PL(4);
+  else if (k <= 6) LS_PL(6);
+  else if (k <= 8) LS_PL(8);
+  else if (k <= 12) LS_PL(12);
+  else if (k <= 16) LS_PL(16);
+  else if (k <= 32) LS_PL(32);
+  else return LS_ERR_UNSUPPORTED;
+#undef LS_PL
+  return LS_OK;
+}
+
 int ls_launch_place(const int* cell, const int* within, const void* prob, int dtype, const LsDims& dm,
                     const LsGrid& g, const int* seg_start, int2* recs, int2* pix_recs, cudaStream_t s) {
   dim3 grid((dm.HW + 31) / 32, dm.N, dm.B);
   const size_t smem = pix_recs ? (size_t)32 * (dm.D | 1) * sizeof(int2) : 0;
   if (smem > 48 * 1024) return LS_ERR_UNSUPPORTED;
+  int rc;
   if (dtype == LS_F32)
-    ls_place_kernel<float><<<grid, 256, smem, s>>>(cell, within, (const float*)prob, dm, g, seg_start, recs, pix_recs);
+    rc = ls_place_dispatch<float>(cell, within, (const float*)prob, dm, g, seg_start, recs, pix_recs, grid, smem, s);
   else
-    ls_place_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(cell, within, (const __nv_bfloat16*)prob, dm, g,
-                                                            seg_start, recs, pix_recs);
+    rc = ls_place_dispatch<__nv_bfloat16>(cell, within, (const __nv_bfloat16*)prob, dm, g, seg_start, recs, pix_recs,
+                                          grid, smem, s);
+  if (rc) return rc;
   LS_LAUNCHED();
   return LS_OK;
 }

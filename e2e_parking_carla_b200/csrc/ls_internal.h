@@ -9,7 +9,7 @@ int ls_launch_index(const float* M, const float* t, const float* frustum, const 
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                      float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s);
 int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, int* tile_order,
-                   cudaStream_t s);
+                   int* tile_tot /* scratch i32[B*tiles] or NULL */, cudaStream_t s);
 int ls_launch_place(const int* cell, const int* within, const void* prob, int dtype, const LsDims& dm,
                     const LsGrid& g, const int* seg_start, int2* recs, int2* pix_recs, cudaStream_t s);
 int ls_launch_export_cell_counts(const int* seg_start, const LsGrid& g, int B, int b, long long* out, int* kept,

@@ -146,7 +146,7 @@ def softmax(logits: torch.Tensor, shape: LsShape) -> torch.Tensor:
     return prob
 
 
-def sort(cell, within, counts, prob, shape: LsShape, with_pixel_index: bool = False):
+def sort(cell, within, counts, prob, shape: LsShape, with_pixel_index: bool = False, parallel_scan: bool = True):
     """Counting sort by cell: (seg_start i32[B,seg_stride], tile_order i32[B,tiles], recs
     i32[B,Npts,2] = {key, prob bits}, pix_recs i32[B*N*HW, D, 2] or None)."""
     _need_cuda(cell, within, counts, prob)
@@ -155,13 +155,14 @@ def sort(cell, within, counts, prob, shape: LsShape, with_pixel_index: bool = Fa
     npts = cell.shape[1]
     seg = torch.empty(shape.B, stride, dtype=torch.int32, device=dev)
     order = torch.empty(shape.B, tiles, dtype=torch.int32, device=dev)
+    scratch = torch.empty(shape.B, tiles, dtype=torch.int32, device=dev) if parallel_scan else None
     recs = torch.zeros(shape.B, npts, 2, dtype=torch.int32, device=dev)
     pix = None
     if with_pixel_index:
         pix = torch.empty(shape.B * shape.N * shape.fh * shape.fw, shape.D, 2, dtype=torch.int32, device=dev)
     prob = prob.contiguous()
     check(_lib.load().ls_sort(_ptr(cell), _ptr(within), _ptr(counts), _ptr(prob), _dtype_code(prob), C.byref(shape),
-                              _ptr(seg), _ptr(order), _ptr(recs), _ptr(pix), _stream(cell)), "ls_sort")
+                              _ptr(seg), _ptr(order), _ptr(scratch), _ptr(recs), _ptr(pix), _stream(cell)), "ls_sort")
     return seg, order, recs, pix
 
 

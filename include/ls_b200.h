@@ -109,7 +109,8 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
 * pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell (cells_padded for a dropped point),
  * prob bits} per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
-            int dtype, const LsShape* s, int32_t* seg_start, int32_t* tile_order, void* recs,
+            int dtype, const LsShape* s, int32_t* seg_start, int32_t* tile_order,
+            int32_t* tile_scratch /* i32[B,tiles] or NULL: enables the parallel scan */, void* recs,
             void* pix_recs, ls_stream_t stream);
 
 /* Test export: for sample b, out i64[cells_padded,2] = (row-major rank, number of kept
