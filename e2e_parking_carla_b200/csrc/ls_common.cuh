@@ -9,14 +9,17 @@
 
 // ---- BEV tiling ---------------------------------------------------------------------
 // The grid is cut into LS_TX x LS_TY voxel tiles; cells are numbered tile-major
-// (cell = tile*256 + lx*LS_TY + ly).  Square tiles keep ~6 consecutive depth bins of a
-// crossing camera ray inside one tile, which is what gives the feature gather its L1 reuse.
-#define LS_TX 16
-#define LS_TY 16
-#define LS_TILE (LS_TX * LS_TY)      // 256 cells per tile (cell-in-tile fits 8 bits)
-#define LS_CCHUNK 64                 // channels per pass: a half-warp holds 16 x float4
-#define LS_THREADS 256
-#define LS_HALFWARPS (LS_THREADS / 16)
+// (cell = tile*LS_TILE + lx*LS_TY + ly).  Tiles are small on purpose: a tile is one CTA of
+// the splat, and many small CTAs in different phases hide each other's latencies.
+#ifndef LS_TX
+#define LS_TX 8                      // 8 or 16 x-rows per tile
+#endif
+#define LS_TY 16                     // 16 y-columns = 64 B of fp32 along Y
+#define LS_TILE (LS_TX * LS_TY)      // cells per tile (cell-in-tile fits 8 bits)
+#define LS_CCHUNK 64                 // channels per pass
+#define LS_THREADS LS_TILE           // tile kernels: one thread per cell of the tile
+#define LS_GATHER_THREADS 256
+#define LS_HALFWARPS (LS_GATHER_THREADS / 16)
 #define LS_SEG_PAD 4                 // seg_start row stride = Vc + LS_SEG_PAD (16 B aligned rows)
 
 // Everything a kernel needs to know about the BEV grid, derived once on the host.

@@ -154,6 +154,19 @@ int ls_launch_export(const float* M, const float* t, const float* frustum, const
 // tiles: per-tile totals (one warp per tile, 8 cells per lane), block scan of the totals,
 // then in-tile scans written as 16-byte stores.
 // =====================================================================================
+// A warp covers one tile: LS_TILE/32 consecutive cells per lane (8 -> two int4, 4 -> one).
+__device__ __forceinline__ void ls_load_counts(const int* __restrict__ tile_counts, int lane, int4& a, int4& c) {
+  static_assert(LS_TILE == 256 || LS_TILE == 128, "tile must have 128 or 256 cells");
+  const int4* q = reinterpret_cast<const int4*>(tile_counts) + lane * (LS_TILE / 128);
+  a = q[0];
+  c = (LS_TILE == 256) ? q[LS_TILE == 256 ? 1 : 0] : make_int4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void ls_store_offsets(int* __restrict__ tile_seg, int lane, int4 o0, int4 o1) {
+  int4* dst = reinterpret_cast<int4*>(tile_seg) + lane * (LS_TILE / 128);
+  dst[0] = o0;
+  if (LS_TILE == 256) dst[1] = o1;
+}
+
 __device__ __forceinline__ int ls_warp_incl_scan(int v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -176,8 +189,8 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
   for (int t0 = 0; t0 < g.tiles; t0 += 1024) {
     const int tend = min(g.tiles, t0 + 1024);
     for (int t = t0 + warp; t < tend; t += 32) {
-      const int4* q = reinterpret_cast<const int4*>(cnt + (size_t)t * LS_TILE) + lane * 2;
-      const int4 a = q[0], c = q[1];
+      int4 a, c;
+      ls_load_counts(cnt + (size_t)t * LS_TILE, lane, a, c);
       int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -215,16 +228,14 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
     tile_base[tid] = carry + warp_tot[warp] + incl - v;
     __syncthreads();
     for (int t = t0 + warp; t < tend; t += 32) {
-      const int4* q = reinterpret_cast<const int4*>(cnt + (size_t)t * LS_TILE) + lane * 2;
-      const int4 a = q[0], c = q[1];
+      int4 a, c;
+      ls_load_counts(cnt + (size_t)t * LS_TILE, lane, a, c);
       const int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
       const int base = tile_base[t - t0] + ls_warp_incl_scan(s, lane) - s;
       int4 o0, o1;
       o0.x = base; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
       o1.x = o0.w + a.w; o1.y = o1.x + c.x; o1.z = o1.y + c.y; o1.w = o1.z + c.z;
-      int4* dst = reinterpret_cast<int4*>(seg + (size_t)t * LS_TILE) + lane * 2;
-      dst[0] = o0;
-      dst[1] = o1;
+      ls_store_offsets(seg + (size_t)t * LS_TILE, lane, o0, o1);
     }
     carry += chunk_total;
     __syncthreads();
@@ -239,8 +250,8 @@ __global__ void __launch_bounds__(256)
 ls_tile_totals_kernel(const int* __restrict__ counts, int ntiles_all, int* __restrict__ tile_tot) {
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (t >= ntiles_all) return;
-  const int4* q = reinterpret_cast<const int4*>(counts + (size_t)t * LS_TILE) + lane * 2;
-  const int4 a = q[0], c = q[1];
+  int4 a, c;
+  ls_load_counts(counts + (size_t)t * LS_TILE, lane, a, c);
   int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -266,17 +277,15 @@ ls_tile_scan_kernel(const int* __restrict__ counts, const int* __restrict__ tile
     base += __shfl_xor_sync(0xffffffffu, base, o);
     rank += __shfl_xor_sync(0xffffffffu, rank, o);
   }
-  const int4* q = reinterpret_cast<const int4*>(counts + ((size_t)b * g.tiles + t) * LS_TILE) + lane * 2;
-  const int4 a = q[0], c = q[1];
+  int4 a, c;
+  ls_load_counts(counts + ((size_t)b * g.tiles + t) * LS_TILE, lane, a, c);
   const int s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
   const int e0 = base + ls_warp_incl_scan(s, lane) - s;
   int4 o0, o1;
   o0.x = e0; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
   o1.x = o0.w + a.w; o1.y = o1.x + c.x; o1.z = o1.y + c.y; o1.w = o1.z + c.z;
   int* seg = seg_start + (size_t)b * g.seg_stride;
-  int4* dst = reinterpret_cast<int4*>(seg + (size_t)t * LS_TILE) + lane * 2;
-  dst[0] = o0;
-  dst[1] = o1;
+  ls_store_offsets(seg + (size_t)t * LS_TILE, lane, o0, o1);
   if (lane == 0) {
     if (tile_order) tile_order[(size_t)b * g.tiles + rank] = t;
     if (t == g.tiles - 1) seg[g.Vc] = base + mine;

@@ -77,7 +77,7 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts, int tile
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
 // =====================================================================================
 template <typename T, bool VEC4, int kCC>
-__global__ void __launch_bounds__(LS_THREADS, 3)
+__global__ void __launch_bounds__(LS_THREADS, 768 / LS_THREADS)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
                     const int* __restrict__ tile_order, int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
                     float* __restrict__ bev, LsBevStrides st) {
@@ -181,7 +181,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
   const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
   // phase C geometry of this thread (fixed): 4 consecutive y of one x-row; channel quads qg, qg+4, ...
-  const int y4 = tid & 3, xr = (tid >> 2) & 15, qg = tid >> 6;
+  const int y4 = tid & 3, xr = (tid >> 2) & (LS_TX - 1), qg = tid / (4 * LS_TX);
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
   const bool inb = gx < grid.X && gy < grid.Y;
   const int clc = xr * LS_TY + 4 * y4;
@@ -299,7 +299,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
         const float* srow = tile + clc * stride;
         float* gbase = bev + (size_t)b * st.b + (size_t)cbase * st.c + (size_t)gx * st.x + gy;
 #pragma unroll 4
-        for (int q = qg; q < nquads; q += LS_THREADS / 64) {
+        for (int q = qg; q < nquads; q += 4) {
           float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
           if (!tile_empty) {
             const float* src = srow + 4 * (q ^ swz);
@@ -318,7 +318,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       }
     } else {
       for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
-        const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
+        const int y = idx & 15, x = (idx >> 4) & (LS_TX - 1), cr = idx / LS_TILE;
         const int c = cbase + cr;
         const int ox = tx0 + x, oy = ty0 + y;
         if (c < dm.C && ox < grid.X && oy < grid.Y) {
@@ -405,92 +405,84 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 // K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
 // =====================================================================================
+#define LS_TCHUNK 16   // channels per CTA of the gradient transposer (small CTAs, many in flight)
+
 template <bool VEC4>
-__global__ void __launch_bounds__(LS_THREADS, 3)
+__global__ void __launch_bounds__(LS_THREADS)
 ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const int* __restrict__ seg_start,
                         LsDims dm, LsGrid grid, float* __restrict__ gT) {
   extern __shared__ float smem[];
-  const LsTileGeom tg = ls_tile_geom(dm.Cp);
+  const LsTileGeom tg = ls_tile_geom(min(dm.Cp, LS_TCHUNK));
   float* tile = smem;
   int* seg = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);
   const int b = blockIdx.y, tile_id = blockIdx.x, tid = threadIdx.x;
+  const int cbase = blockIdx.z * LS_TCHUNK;
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
-  if (tile_id == 0) {   // row Vc of every sample = zeros: where dropped points gather from
+  if (tile_id == 0 && blockIdx.z == 0) {   // row Vc of every sample = zeros: where dropped points gather from
     float* zrow = gT + ((size_t)b * (grid.Vc + 1) + grid.Vc) * dm.Cp;
     for (int i = tid; i < dm.Cp; i += LS_THREADS) zrow[i] = 0.0f;
   }
   __syncthreads();
   if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
-  float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp;
-  const int y4 = tid & 3, xr = (tid >> 2) & 15, qg = tid >> 6;
-  const int gx = tx0 + xr, gy = ty0 + 4 * y4;
-  const bool inb = gx < grid.X && gy < grid.Y;
-  const int clc = xr * LS_TY + 4 * y4;
-  for (int cbase = 0; cbase < dm.Cp; cbase += LS_CCHUNK) {
-    const int cc = min(tg.cc, dm.Cp - cbase);
-    const int nquads = cc >> 2;
-    if (VEC4) {
-      // 4 channels x 4 y per thread: four 16-byte loads, a 4x4 register transpose, four
-      // 16-byte conflict-free shared stores (rows of 4 consecutive cells, one channel quad)
+  float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp + cbase;
+  const int nquads = min(tg.cc, dm.Cp - cbase) >> 2;
+  if (VEC4) {
+    // thread = (4 consecutive y, x-row, channel quad): four 16-byte loads (4 channels), a 4x4
+    // register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
+    const int y4 = tid & 3, xr = (tid >> 2) & (LS_TX - 1), q = tid / (4 * LS_TX);
+    const int gx = tx0 + xr, gy = ty0 + 4 * y4;
+    if (q < nquads) {
+      const int clc = xr * LS_TY + 4 * y4;
       const int swz = (clc >> 3) & (tg.nqp - 1);
-      float* drow = tile + clc * tg.stride;
-      const float* gbase = gbev + (size_t)b * st.b + (size_t)cbase * st.c + (size_t)gx * st.x + gy;
-#pragma unroll 4
-      for (int q = qg; q < nquads; q += LS_THREADS / 64) {
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
-        const float* g = gbase + (size_t)(4 * q) * st.c;
+      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+      if (gx < grid.X && gy < grid.Y) {
         const int c = cbase + 4 * q;
-        if (inb) {
-          if (c + 0 < dm.C) c0 = __ldg(reinterpret_cast<const float4*>(g));
-          if (c + 1 < dm.C) c1 = __ldg(reinterpret_cast<const float4*>(g + st.c));
-          if (c + 2 < dm.C) c2 = __ldg(reinterpret_cast<const float4*>(g + 2 * st.c));
-          if (c + 3 < dm.C) c3 = __ldg(reinterpret_cast<const float4*>(g + 3 * st.c));
-        }
-        float* d = drow + 4 * (q ^ swz);
-        *reinterpret_cast<float4*>(d) = make_float4(c0.x, c1.x, c2.x, c3.x);
-        *reinterpret_cast<float4*>(d + tg.stride) = make_float4(c0.y, c1.y, c2.y, c3.y);
-        *reinterpret_cast<float4*>(d + 2 * tg.stride) = make_float4(c0.z, c1.z, c2.z, c3.z);
-        *reinterpret_cast<float4*>(d + 3 * tg.stride) = make_float4(c0.w, c1.w, c2.w, c3.w);
+        const float* g = gbev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy;
+        if (c + 0 < dm.C) c0 = __ldg(reinterpret_cast<const float4*>(g));
+        if (c + 1 < dm.C) c1 = __ldg(reinterpret_cast<const float4*>(g + st.c));
+        if (c + 2 < dm.C) c2 = __ldg(reinterpret_cast<const float4*>(g + 2 * st.c));
+        if (c + 3 < dm.C) c3 = __ldg(reinterpret_cast<const float4*>(g + 3 * st.c));
       }
-    } else {
-      for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
-        const int y = idx & 15, x = (idx >> 4) & 15, cr = idx >> 8;
-        const int c = cbase + cr;
-        const int ox = tx0 + x, oy = ty0 + y;
-        float v = 0.0f;
-        if (c < dm.C && ox < grid.X && oy < grid.Y)
-          v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy];
-        const int cl = x * LS_TY + y;
-        tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
-      }
+      float* d = tile + clc * tg.stride + 4 * (q ^ swz);
+      *reinterpret_cast<float4*>(d) = make_float4(c0.x, c1.x, c2.x, c3.x);
+      *reinterpret_cast<float4*>(d + tg.stride) = make_float4(c0.y, c1.y, c2.y, c3.y);
+      *reinterpret_cast<float4*>(d + 2 * tg.stride) = make_float4(c0.z, c1.z, c2.z, c3.z);
+      *reinterpret_cast<float4*>(d + 3 * tg.stride) = make_float4(c0.w, c1.w, c2.w, c3.w);
     }
-    __syncthreads();
-    // rows of non-empty cells, 16 B per lane: thread = (quad, cell mod 16)
-    if ((tid & 15) < nquads) {
-      const int q = tid & 15;
-      for (int cl = tid >> 4; cl < LS_TILE; cl += LS_THREADS / 16) {
+  } else {
+    for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
+      const int y = idx & 15, x = (idx >> 4) & (LS_TX - 1), cr = idx / LS_TILE;
+      const int c = cbase + cr;
+      const int ox = tx0 + x, oy = ty0 + y;
+      float v = 0.0f;
+      if (c < dm.C && ox < grid.X && oy < grid.Y)
+        v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy];
+      const int cl = x * LS_TY + y;
+      tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
+    }
+  }
+  __syncthreads();
+  // rows of non-empty cells: thread = (quad, cell), 16 B per lane, 64 B per cell
+  {
+    const int q = tid & 3;
+    if (q < nquads) {
+#pragma unroll
+      for (int cl = tid >> 2; cl < LS_TILE; cl += LS_THREADS / 4) {
         if (seg[cl + 1] != seg[cl])
-          *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + cbase + 4 * q) =
+          *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + 4 * q) =
               *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
       }
     }
-    __syncthreads();
   }
 }
 
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
                             const LsGrid& g, float* gT, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    const int m = (int)ls_tile_smem_max();
-    LS_CUDA(cudaFuncSetAttribute(ls_bwd_transpose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_bwd_transpose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    attr_done = true;
-  }
-  const size_t smem = ls_tile_smem_bytes(dm);
-  dim3 grid(g.tiles, dm.B);
+  const LsTileGeom tg = ls_tile_geom(dm.Cp < LS_TCHUNK ? dm.Cp : LS_TCHUNK);
+  const size_t smem = (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 1) * sizeof(int);
+  dim3 grid(g.tiles, dm.B, (dm.Cp + LS_TCHUNK - 1) / LS_TCHUNK);
   if (ls_bev_vec4(gbev, st, g))
     ls_bwd_transpose_kernel<true><<<grid, LS_THREADS, smem, s>>>(gbev, st, seg_start, dm, g, gT);
   else
@@ -511,7 +503,7 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
 // Outputs: grad_feat NHWC-padded [pix][Cp] and grad_prob PIXEL-major [pix][D].
 // =====================================================================================
 template <typename T, int NCH>
-__global__ void __launch_bounds__(LS_THREADS, 2)
+__global__ void __launch_bounds__(LS_GATHER_THREADS, 2)
 ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
                      LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
   const int col = blockIdx.x, bn = blockIdx.y;
@@ -606,7 +598,7 @@ static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pi
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
 #define LS_GATHER(NCH) \
-  ls_bwd_gather_kernel<T, NCH><<<grid, LS_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, gprob_pm, (T*)gfeatT)
+  ls_bwd_gather_kernel<T, NCH><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, gprob_pm, (T*)gfeatT)
   switch (nch) {
     case 1: LS_GATHER(1); break;
     case 2: LS_GATHER(2); break;

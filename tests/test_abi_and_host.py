@@ -47,7 +47,9 @@ def test_abi_argument_checking(lib):
     grid = ls.GridSpec((-9.95, -9.95, 0.0), (0.1, 0.1, 20.0), (200, 200, 1))
     s = ls.make_shape(1, 4, 48, 32, 32, 64, grid)
     tiles, cells, stride = ls.grid_cells(s)
-    assert (tiles, cells, stride) == (13 * 13, 13 * 13 * 256, 13 * 13 * 256 + 4)
+    tile_cells = cells // tiles
+    assert tile_cells in (128, 256)
+    assert tiles * tile_cells == cells >= 200 * 200 and stride == cells + 4
     assert ls.padded_channels(6) == 8 and ls.padded_channels(64) == 64
     assert ls.workspace_bytes(s, ls.LS_F32, True) > ls.workspace_bytes(s, ls.LS_F32, False) > 0
     # null pointers
