@@ -15,6 +15,38 @@ int ls_note_cuda_error(cudaError_t e, const char* file, int line) {
   return LS_ERR_CUDA;
 }
 
+// ---- side streams ---------------------------------------------------------------------
+// ls_forward / ls_backward fork independent stages (softmax, layout staging) onto two
+// library-owned non-blocking streams and join them back into the caller's stream with events:
+// still one asynchronous unit of work on `stream` for the caller (and capturable in a CUDA
+// graph as a fork/join), but the small kernels overlap instead of queueing behind each other.
+#include <mutex>
+#include <stdlib.h>
+struct LsAsync {
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t fork = nullptr, j1 = nullptr, j2 = nullptr;
+  bool ready = false;
+};
+static LsAsync g_async[64];
+static std::mutex g_async_mu;
+static LsAsync* ls_async() {
+  static const bool disabled = getenv("LS_NO_SIDE_STREAMS") != nullptr;
+  if (disabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_async_mu);
+  LsAsync& a = g_async[dev];
+  if (!a.ready) {
+    if (cudaStreamCreateWithFlags(&a.s1, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&a.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.j1, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.j2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a.ready = true;
+  }
+  return &a;
+}
+
 static int ls_check_shape(const LsShape* s) {
   if (!s) return LS_ERR_BAD_ARG;
   if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fh <= 0 || s->fw <= 0 || s->C <= 0) return LS_ERR_BAD_ARG;
@@ -240,15 +272,32 @@ int ls_forward(const void* feat, const void* logits, int dtype, const float* M, 
   LsWs w = ls_carve(s, dtype, with_backward, ws);
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
+  LsAsync* a = ls_async();
+  cudaStream_t s_soft = stream, s_feat = stream;
+  if (a) {
+    LS_CUDA(cudaEventRecord(a->fork, stream));
+    LS_CUDA(cudaStreamWaitEvent(a->s1, a->fork, 0));
+    LS_CUDA(cudaStreamWaitEvent(a->s2, a->fork, 0));
+    s_soft = a->s1;
+    s_feat = a->s2;
+  }
+  // side stream 1: depth softmax; side stream 2: NHWC staging of the features
+  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, s_soft))) return rc;
+  if ((rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, s_feat))) return rc;
+  if (a) {
+    LS_CUDA(cudaEventRecord(a->j1, a->s1));
+    LS_CUDA(cudaEventRecord(a->j2, a->s2));
+  }
+  // caller's stream: index -> scan, then (after softmax) placement, then (after staging) the splat
   LS_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)dm.B * g.Vc * sizeof(int), stream));
   ls_note_launch();
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
   if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, w.tile_tot, stream))) return rc;
-  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, stream))) return rc;
+  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j1, 0));
   if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs,
                             with_backward ? w.pix_recs : nullptr, stream)))
     return rc;
-  if ((rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, stream))) return rc;
+  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j2, 0));
   return ls_launch_splat_fwd(w.featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, dm, g, bev,
                              *bev_strides, stream);
 }
@@ -267,8 +316,19 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
   LsGrid g = ls_grid(s);
   if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, w.seg_start, dm, g, w.gT, stream))) return rc;
   if ((rc = ls_launch_bwd_gather(w.gT, w.featT, dtype, w.pix_recs, dm, g, w.gprob_pm, w.gfeatT, stream))) return rc;
-  if ((rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, stream))) return rc;
-  return ls_launch_softmax_bwd(prob, w.gprob_pm, grad_prob_ext, dtype, dm, grad_logits, stream);
+  // the two layout fix-ups are independent: grad_feat on a side stream, grad_logits on the caller's
+  LsAsync* a = ls_async();
+  cudaStream_t s_feat = stream;
+  if (a) {
+    LS_CUDA(cudaEventRecord(a->fork, stream));
+    LS_CUDA(cudaStreamWaitEvent(a->s1, a->fork, 0));
+    s_feat = a->s1;
+  }
+  if ((rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, s_feat))) return rc;
+  if (a) LS_CUDA(cudaEventRecord(a->j1, a->s1));
+  if ((rc = ls_launch_softmax_bwd(prob, w.gprob_pm, grad_prob_ext, dtype, dm, grad_logits, stream))) return rc;
+  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j1, 0));
+  return LS_OK;
 }
 
 }  // extern "C"

@@ -7,72 +7,83 @@
 // camera transform: E^-1, K^-1 (fp64 Gauss-Jordan, partial pivoting), M = R . K^-1
 // reference: model/bev_model.py:46-47,53     oracle: camera_transform
 // =====================================================================================
-// Fully unrolled (static register indexing: no local memory): the pivot row is swapped in
-// with predicated moves.  Same operation order as oracle/_gauss_jordan_f64.
+// Column-parallel Gauss-Jordan: lane `base + j` owns column j of the augmented matrix
+// [A | I] (n rows in registers); pivot column and factors travel by warp shuffles.  Every
+// element sees exactly the operations of oracle/_gauss_jordan_f64 (divide the pivot row, then
+// row_i -= a[i][k] * row_k with separate multiply and subtract), so results are bit-identical
+// to the serial form; the dependent chain is n pivots instead of n * 2n * n operations.
 template <int n>
-__device__ __forceinline__ void ls_gauss_jordan(double (&a)[n][2 * n]) {
+__device__ __forceinline__ void ls_gauss_jordan_cols(double (&col)[n], int base) {
 #pragma unroll
   for (int k = 0; k < n; ++k) {
+    double ck[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) ck[i] = __shfl_sync(0xffffffffu, col[i], base + k);
     int p = k;
-    double best = fabs(a[k][k]);
+    double best = fabs(ck[k]);
 #pragma unroll
     for (int i = k + 1; i < n; ++i) {
-      const double v = fabs(a[i][k]);
+      const double v = fabs(ck[i]);
       if (v > best) { best = v; p = i; }   // first maximum wins (numpy argmax)
     }
 #pragma unroll
     for (int i = k + 1; i < n; ++i) {
       if (p == i) {
-#pragma unroll
-        for (int j = 0; j < 2 * n; ++j) { const double tmp = a[k][j]; a[k][j] = a[i][j]; a[i][j] = tmp; }
+        double tmp = col[k]; col[k] = col[i]; col[i] = tmp;
+        tmp = ck[k]; ck[k] = ck[i]; ck[i] = tmp;
       }
     }
-    const double piv = a[k][k];
+    const double rowk = __ddiv_rn(col[k], ck[k]);
 #pragma unroll
-    for (int j = 0; j < 2 * n; ++j) a[k][j] = __ddiv_rn(a[k][j], piv);
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      if (i == k) continue;
-      const double f = a[i][k];
-#pragma unroll
-      for (int j = 0; j < 2 * n; ++j) a[i][j] = __dsub_rn(a[i][j], __dmul_rn(f, a[k][j]));
-    }
+    for (int i = 0; i < n; ++i)
+      if (i != k) col[i] = __dsub_rn(col[i], __dmul_rn(ck[i], rowk));
+    col[k] = rowk;
   }
 }
 
+// One warp per camera: lanes 0-7 invert the 4x4 extrinsic, lanes 8-13 the 3x3 intrinsic.
 __global__ void __launch_bounds__(32)
 ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr, int BN,
                            float* __restrict__ M, float* __restrict__ t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BN) return;
-  double e[4][8];
+  const int i = blockIdx.x, lane = threadIdx.x;
+  double e[4], k[3];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 4; ++r) {
+    const int c = lane & 7;
+    e[r] = (c < 4) ? (double)extr[i * 16 + r * 4 + c] : ((c - 4 == r) ? 1.0 : 0.0);
+  }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { e[r][c] = (double)extr[i * 16 + r * 4 + c]; e[r][4 + c] = (r == c) ? 1.0 : 0.0; }
-  ls_gauss_jordan<4>(e);
-  double k[3][6];
+  for (int r = 0; r < 3; ++r) {
+    const int c = (lane >= 8 && lane < 14) ? lane - 8 : 0;
+    k[r] = (c < 3) ? (double)intr[i * 9 + r * 3 + c] : ((c - 3 == r) ? 1.0 : 0.0);
+  }
+  ls_gauss_jordan_cols<4>(e, 0);
+  ls_gauss_jordan_cols<3>(k, 8);
+  // E^-1[r][c] sits in lane 4+c (e[r]); K^-1[q][c] in lane 11+c (k[q]).  Lane 11+c builds
+  // column c of M = R . K^-1 (aten's small-matrix bmm: unfused, q ascending, from +0).
+  float rot[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { k[r][c] = (double)intr[i * 9 + r * 3 + c]; k[r][3 + c] = (r == c) ? 1.0 : 0.0; }
-  ls_gauss_jordan<3>(k);
+    for (int q = 0; q < 3; ++q) rot[r][q] = (float)__shfl_sync(0xffffffffu, e[r], 4 + q);
+  if (lane >= 11 && lane < 14) {
+    const int c = lane - 11;
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    t[i * 3 + r] = (float)e[r][7];
+    for (int r = 0; r < 3; ++r) {
+      float acc = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float acc = 0.0f;  // aten's small-matrix bmm: unfused, k ascending, from +0
-#pragma unroll
-      for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn((float)e[r][4 + q], (float)k[q][3 + c]));
+      for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn(rot[r][q], (float)k[q]));
       M[i * 9 + r * 3 + c] = acc;
     }
+  }
+  if (lane == 7) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) t[i * 3 + r] = (float)e[r];
   }
 }
 
 int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s) {
-  // one camera per thread, spread thin (4 per CTA) so the serial fp64 chains run on many SMs
-  ls_camera_transform_kernel<<<(BN + 3) / 4, 4, 0, s>>>(intr, extr, BN, M, t);
+  ls_camera_transform_kernel<<<BN, 32, 0, s>>>(intr, extr, BN, M, t);
   LS_LAUNCHED();
   return LS_OK;
 }
