@@ -65,6 +65,7 @@ static int ls_check_splat_shape(const LsShape* s) {
   if (((long long)s->N * dm.HW) << dm.dbits > (1LL << 24)) return LS_ERR_UNSUPPORTED;
   if ((long long)s->N * dm.HW > (1LL << 20)) return LS_ERR_UNSUPPORTED;   // pixel id field of a sorted record
   if ((long long)s->N * dm.HW * dm.Cp >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
+  if (((long long)ls_grid(s).Vc + 1) * dm.Cp * 4 >= (1LL << 31)) return LS_ERR_UNSUPPORTED;   // 32-bit row byte offsets
   return LS_OK;
 }
 static bool ls_dtype_ok(int dtype) { return dtype == LS_F32 || dtype == LS_BF16; }

@@ -365,7 +365,8 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
           const int key = ((c[k] & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
           recs[(size_t)b * dm.Npts + sg[k] + tk[k]] = make_int2(key, wb[k]);
         }
-        if (pix_recs) stage[lane * Dp + d] = make_int2(c[k] >= 0 ? c[k] : grid.Vc, wb[k]);   // Vc = zero row
+        // byte offset of the cell's row in the cell-major gradient block (row Vc = zeros)
+        if (pix_recs) stage[lane * Dp + d] = make_int2((c[k] >= 0 ? c[k] : grid.Vc) * dm.Cp * 4, wb[k]);
       }
     }
   }

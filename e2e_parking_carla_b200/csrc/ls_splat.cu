@@ -502,7 +502,9 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
 //                                                          transposing butterfly: 15 shuffles)
 // Outputs: grad_feat NHWC-padded [pix][Cp] and grad_prob PIXEL-major [pix][D].
 // =====================================================================================
-template <typename T, int NCH>
+// kFullD: D is a multiple of 16 (no predicates on the index loads).  pix_recs.x holds the BYTE
+// offset of the cell's row inside the sample's cell-major gradient block.
+template <typename T, int NCH, bool kFullD>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, 2)
 ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
                      LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
@@ -510,8 +512,9 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const unsigned hmask = ls_half_mask();
-  // dropped points carry row index Vc: the all-zero row written by the transpose kernel
-  const float* gTb = gT + (size_t)b * (grid.Vc + 1) * dm.Cp + 4 * hl;
+  // dropped points point at row Vc: the all-zero row written by the transpose kernel
+  const char* gTb = reinterpret_cast<const char*>(gT + (size_t)b * (grid.Vc + 1) * dm.Cp + 4 * hl);
+  const unsigned zero_row = (unsigned)grid.Vc * (unsigned)dm.Cp * 4u;
   bool on[NCH];
 #pragma unroll
   for (int q = 0; q < NCH; ++q) on[q] = (q * LS_CCHUNK + 4 * hl) < dm.Cp;
@@ -527,10 +530,13 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
     }
     const int2* pr = pix_recs + pix * dm.D;
     for (int d0 = 0; d0 < dm.D; d0 += 16) {
-      const int n = min(16, dm.D - d0);
+      const int n = kFullD ? 16 : min(16, dm.D - d0);
       int2 r[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) r[u] = (u < n) ? __ldg(pr + d0 + u) : make_int2(grid.Vc, 0);  // uniform
+      for (int u = 0; u < 16; ++u) {
+        if (kFullD) r[u] = __ldg(pr + d0 + u);                                  // half-warp-uniform
+        else r[u] = (u < n) ? __ldg(pr + d0 + u) : make_int2((int)zero_row, 0);
+      }
       float dot[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) dot[u] = 0.0f;
@@ -539,8 +545,8 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
         float4 g[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on[q]) g[u] = __ldg(reinterpret_cast<const float4*>(gTb + (size_t)r[u].x * dm.Cp + q * LS_CCHUNK));
+          const char* src = gTb + (unsigned)r[u].x + (unsigned)(q * LS_CCHUNK * 4);
+          g[u] = __ldg(reinterpret_cast<const float4*>(on[q] ? src : gTb + zero_row - 16 * hl));
         }
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
@@ -597,8 +603,16 @@ static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pi
                               const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
-#define LS_GATHER(NCH) \
-  ls_bwd_gather_kernel<T, NCH><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, gprob_pm, (T*)gfeatT)
+  const bool full = dm.D % 16 == 0;
+#define LS_GATHER(NCH)                                                                                           \
+  do {                                                                                                           \
+    if (full)                                                                                                    \
+      ls_bwd_gather_kernel<T, NCH, true><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, \
+                                                                            gprob_pm, (T*)gfeatT);               \
+    else                                                                                                         \
+      ls_bwd_gather_kernel<T, NCH, false><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, \
+                                                                             gprob_pm, (T*)gfeatT);              \
+  } while (0)
   switch (nch) {
     case 1: LS_GATHER(1); break;
     case 2: LS_GATHER(2); break;

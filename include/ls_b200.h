@@ -106,8 +106,9 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
  * splat's CTAs), then every
  * kept point writes an 8-byte record {key, prob bits} to recs[B,Npts] at
  * seg_start[cell] + within;  key = cell_in_tile << 24 | (pixel << ceil(log2 D) | d).
-* pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell (cells_padded for a dropped point),
- * prob bits} per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
+* pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell * Cp * 4 (byte offset of the cell's row in
+ * the cell-major gradient; cell = cells_padded, the zero row, for a dropped point), prob bits}
+ * per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
             int dtype, const LsShape* s, int32_t* seg_start, int32_t* tile_order,
             int32_t* tile_scratch /* i32[B,tiles] or NULL: enables the parallel scan */, void* recs,

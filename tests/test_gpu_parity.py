@@ -136,7 +136,9 @@ def test_sorted_ranks_bit_exact(lib, name):
         w = recs[b, :kept[b], 1].cpu().numpy().view(np.float32)
         assert np.array_equal(w, prob.view(sh.batch, -1)[b].cpu().numpy()[p])
     # pixel-major index: {cell, prob} of every depth bin of every pixel
-    pc = pix[..., 0].view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
+    row_bytes = ls.padded_channels(sh.channels) * 4
+    assert bool((pix[..., 0] % row_bytes == 0).all())
+    pc = (pix[..., 0] // row_bytes).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
     cells_padded = ls.grid_cells(s)[1]
     assert torch.equal(pc, torch.where(cell >= 0, cell, torch.full_like(cell, cells_padded)))   # dropped -> zero row
     pw = pix[..., 1].contiguous().view(torch.float32).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2)
