@@ -38,6 +38,7 @@ from e2e_parking_carla_b200.synthetic import (LiftSplatShape, make_encoder_outpu
 
 METRIC = "lift_splat_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
+E2E_CHUNKS = int(os.environ.get("LS_E2E_CHUNKS", "8"))
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -206,17 +207,57 @@ class Stepper:
                                  self.code, C.byref(self.s), self._p(self.ws), self.ws.numel(), self._p(self.gfeat),
                                  self._p(self.glogits), stream), "ls_backward")
 
-    def step_e2e(self):
-        """Host buffers in, host buffers out: every input (including the upstream
-        gradients) is copied from pinned host memory and every output is copied back."""
-        for k, v in self.host.items():
-            self.dev[k].copy_(v, non_blocking=True)
-        self.step()
-        self.out_host["bev"].copy_(self.bev, non_blocking=True)
-        self.out_host["prob"].copy_(self.prob, non_blocking=True)
-        self.out_host["gfeat"].copy_(self.gfeat, non_blocking=True)
-        self.out_host["glogits"].copy_(self.glogits, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step_e2e(self, chunks: int = E2E_CHUNKS):
+        """Host buffers in, host buffers out: every input (including the upstream gradients)
+        is copied from pinned host memory and every output is copied back, synchronised per
+        step.  The batch is cut into `chunks` groups of samples (the path is per-sample) so
+        that the H2D copy of group k+1, the kernels of group k and the D2H copy of group k-1
+        overlap on three streams - PCIe is full duplex and is the bottleneck here."""
+        sh, ls, lib = self.shape, self.ls, self.lib
+        if not hasattr(self, "_e2e"):
+            per = (sh.batch + chunks - 1) // chunks
+            self._e2e = {"per": per, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
+                         "ev_in": [torch.cuda.Event() for _ in range(chunks)],
+                         "ev_out": [torch.cuda.Event() for _ in range(chunks)],
+                         "shapes": {}}
+        e = self._e2e
+        comp = torch.cuda.current_stream()
+        e["h2d"].wait_stream(comp)
+        n = sh.cams
+        for k, lo in enumerate(range(0, sh.batch, e["per"])):
+            hi = min(sh.batch, lo + e["per"])
+            with torch.cuda.stream(e["h2d"]):
+                for name, per_cam in (("feat", True), ("logits", True), ("gprob", True), ("intr", False),
+                                      ("extr", False), ("gbev", False)):
+                    a, b = (lo * n, hi * n) if per_cam else (lo, hi)
+                    self.dev[name][a:b].copy_(self.host[name][a:b], non_blocking=True)
+                e["ev_in"][k].record(e["h2d"])
+            comp.wait_event(e["ev_in"][k])
+            if (lo, hi) not in e["shapes"]:
+                e["shapes"][(lo, hi)] = ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid)
+            sc = e["shapes"][(lo, hi)]
+            d = self.dev
+            stream = C.c_void_p(comp.cuda_stream)
+            P = self._p
+            ls.check(lib.ls_camera_transform(P(d["intr"][lo:hi]), P(d["extr"][lo:hi]), (hi - lo) * n,
+                                             P(self.M[lo:hi]), P(self.t[lo:hi]), stream), "ls_camera_transform")
+            ls.check(lib.ls_forward(P(d["feat"][lo * n:hi * n]), P(d["logits"][lo * n:hi * n]), self.code,
+                                    P(self.M[lo:hi]), P(self.t[lo:hi]), P(self.frustum), C.byref(sc), P(self.ws),
+                                    self.ws.numel(), 1, P(self.bev[lo:hi]), C.byref(self.st),
+                                    P(self.prob[lo * n:hi * n]), stream), "ls_forward")
+            ls.check(lib.ls_backward(P(d["gbev"][lo:hi]), C.byref(self.gst), P(d["gprob"][lo * n:hi * n]),
+                                     P(self.prob[lo * n:hi * n]), self.code, C.byref(sc), P(self.ws), self.ws.numel(),
+                                     P(self.gfeat[lo * n:hi * n]), P(self.glogits[lo * n:hi * n]), stream),
+                     "ls_backward")
+            e["ev_out"][k].record(comp)
+            e["d2h"].wait_event(e["ev_out"][k])
+            with torch.cuda.stream(e["d2h"]):
+                self.out_host["bev"][lo:hi].copy_(self.bev[lo:hi], non_blocking=True)
+                self.out_host["prob"][lo * n:hi * n].copy_(self.prob[lo * n:hi * n], non_blocking=True)
+                self.out_host["gfeat"][lo * n:hi * n].copy_(self.gfeat[lo * n:hi * n], non_blocking=True)
+                self.out_host["glogits"][lo * n:hi * n].copy_(self.glogits[lo * n:hi * n], non_blocking=True)
+        comp.wait_stream(e["d2h"])
+        comp.synchronize()
 
     def e2e_bytes(self):
         h2d = sum(v.numel() * v.element_size() for v in self.host.values())
@@ -401,7 +442,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps,
                         "what": "pinned host buffers -> device -> ls_camera_transform/ls_forward/ls_backward -> "
-                                "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step"},
+                                "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step; "
+                                "%d sample groups pipelined over H2D / compute / D2H streams" % E2E_CHUNKS},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
