@@ -53,6 +53,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
+    for macro in ("LS_TX", "LS_TY", "LS_ITEM_SHIFT"):     # developer knobs: tile shape / work-item size
+        if os.environ.get(macro):
+            base += ["-D%s=%s" % (macro, os.environ[macro])]
     if os.environ.get("LS_PROFILE"):
         base += ["-DLS_PROFILE"]      # developer build: per-phase clock64 accounting in the splat
     procs = []

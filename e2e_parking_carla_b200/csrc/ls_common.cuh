@@ -12,9 +12,11 @@
 // (cell = tile*LS_TILE + lx*LS_TY + ly).  Tiles are small on purpose: a tile is one CTA of
 // the splat, and many small CTAs in different phases hide each other's latencies.
 #ifndef LS_TX
-#define LS_TX 8                      // 8 or 16 x-rows per tile
+#define LS_TX 4                      // x-rows per tile (LS_TX * LS_TY must be 128 or 256)
 #endif
-#define LS_TY 16                     // 16 y-columns = 64 B of fp32 along Y
+#ifndef LS_TY
+#define LS_TY 32                     // y-columns per tile: 32 -> whole 128-byte lines of the BEV tensor
+#endif
 #define LS_TILE (LS_TX * LS_TY)      // cells per tile (cell-in-tile fits 8 bits)
 #define LS_CCHUNK 64                 // channels per pass
 #define LS_THREADS LS_TILE           // tile kernels: one thread per cell of the tile

@@ -181,7 +181,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
   const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
   // phase C geometry of this thread (fixed): 4 consecutive y of one x-row; channel quads qg, qg+4, ...
-  const int y4 = tid & 3, xr = (tid >> 2) & (LS_TX - 1), qg = tid / (4 * LS_TX);
+  const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, qg = tid / (LS_TILE / 4);
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
   const bool inb = gx < grid.X && gy < grid.Y;
   const int clc = xr * LS_TY + 4 * y4;
@@ -318,7 +318,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
       }
     } else {
       for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
-        const int y = idx & 15, x = (idx >> 4) & (LS_TX - 1), cr = idx / LS_TILE;
+        const int y = idx % LS_TY, x = (idx / LS_TY) % LS_TX, cr = idx / LS_TILE;
         const int c = cbase + cr;
         const int ox = tx0 + x, oy = ty0 + y;
         if (c < dm.C && ox < grid.X && oy < grid.Y) {
@@ -431,7 +431,7 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   if (VEC4) {
     // thread = (4 consecutive y, x-row, channel quad): four 16-byte loads (4 channels), a 4x4
     // register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
-    const int y4 = tid & 3, xr = (tid >> 2) & (LS_TX - 1), q = tid / (4 * LS_TX);
+    const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, q = tid / (LS_TILE / 4);
     const int gx = tx0 + xr, gy = ty0 + 4 * y4;
     if (q < nquads) {
       const int clc = xr * LS_TY + 4 * y4;
@@ -453,7 +453,7 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
     }
   } else {
     for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
-      const int y = idx & 15, x = (idx >> 4) & (LS_TX - 1), cr = idx / LS_TILE;
+      const int y = idx % LS_TY, x = (idx / LS_TY) % LS_TX, cr = idx / LS_TILE;
       const int c = cbase + cr;
       const int ox = tx0 + x, oy = ty0 + y;
       float v = 0.0f;
