@@ -95,6 +95,8 @@ int ls_launch_camera_transform(const float* intr, const float* extr, int BN, flo
 // integer atomicAdd per kept point whose return value ("ticket") is the point's slot inside
 // its cell, so placement later needs no second atomic pass.
 // =====================================================================================
+#define LS_IDX_ILP 2
+
 template <bool kExport>
 __global__ void __launch_bounds__(256)
 ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const float* __restrict__ frustum,
@@ -106,44 +108,65 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   if (threadIdx.x < 9) cam[threadIdx.x] = M[(b * dm.N + n) * 9 + threadIdx.x];
   else if (threadIdx.x < 12) cam[threadIdx.x] = t[(b * dm.N + n) * 3 + threadIdx.x - 9];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dm.DHW) return;
-  const float u = __ldg(frustum + 3 * i + 0), v = __ldg(frustum + 3 * i + 1), d = __ldg(frustum + 3 * i + 2);
-  float g[3], c[3];
-  int vx[3];
-  ls_point_geom(cam, cam + 9, u, v, d, g);
-  const bool keep = ls_point_voxel(g, grid, c, vx);
-  const size_t p = (size_t)b * dm.Npts + (size_t)n * dm.DHW + i;
-  if (kExport) {
-    const int r = keep ? (vx[0] * (grid.Y * grid.Z) + vx[1] * grid.Z + vx[2]) : -1;
-    if (geom_out) { geom_out[3 * p + 0] = g[0]; geom_out[3 * p + 1] = g[1]; geom_out[3 * p + 2] = g[2]; }
-    if (vox_out) {
+  // LS_IDX_ILP points per thread (strided by the CTA width): their loads, divisions and the
+  // histogram atomics are independent, so the returning atomics overlap instead of serialising
+  const int i0 = blockIdx.x * (blockDim.x * LS_IDX_ILP) + threadIdx.x;
+  float u[LS_IDX_ILP], v[LS_IDX_ILP], d[LS_IDX_ILP];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        // Tensor.long() on x86: cvttss2si -> INT64_MIN for NaN / out of range
-        const bool ok = fabsf(c[a]) < 9.2e18f;
-        vox_out[3 * p + a] = ok ? __float2ll_rz(c[a]) : (long long)0x8000000000000000ULL;
+  for (int k = 0; k < LS_IDX_ILP; ++k) {
+    const int i = i0 + k * blockDim.x;
+    const bool in = i < dm.DHW;
+    u[k] = in ? __ldg(frustum + 3 * i + 0) : 0.0f;
+    v[k] = in ? __ldg(frustum + 3 * i + 1) : 0.0f;
+    d[k] = in ? __ldg(frustum + 3 * i + 2) : 0.0f;
+  }
+  bool keep[LS_IDX_ILP];
+  int vx[LS_IDX_ILP][3], cid[LS_IDX_ILP], tk[LS_IDX_ILP];
+  float g[LS_IDX_ILP][3], c[LS_IDX_ILP][3];
+#pragma unroll
+  for (int k = 0; k < LS_IDX_ILP; ++k) {
+    ls_point_geom(cam, cam + 9, u[k], v[k], d[k], g[k]);
+    keep[k] = ls_point_voxel(g[k], grid, c[k], vx[k]) && (i0 + k * blockDim.x < dm.DHW);
+    cid[k] = -1;
+    tk[k] = 0;
+  }
+  if (!kExport && cell) {
+#pragma unroll
+    for (int k = 0; k < LS_IDX_ILP; ++k) {
+      if (keep[k]) {
+        cid[k] = ls_cell_of_xy(vx[k][0], vx[k][1], grid.tiles_y);
+        tk[k] = atomicAdd(&counts[(size_t)b * grid.Vc + cid[k]], 1);
       }
     }
-    if (keep_out) keep_out[p] = keep ? 1 : 0;
-    if (rank64_out) rank64_out[p] = (long long)r;
-  } else {
-    if (rank) rank[p] = keep ? (vx[0] * (grid.Y * grid.Z) + vx[1] * grid.Z + vx[2]) : -1;
-    if (cell) {
-      int cid = -1, tk = 0;
-      if (keep) {
-        cid = ls_cell_of_xy(vx[0], vx[1], grid.tiles_y);
-        tk = atomicAdd(&counts[(size_t)b * grid.Vc + cid], 1);
+  }
+#pragma unroll
+  for (int k = 0; k < LS_IDX_ILP; ++k) {
+    const int i = i0 + k * blockDim.x;
+    if (i >= dm.DHW) continue;
+    const size_t p = (size_t)b * dm.Npts + (size_t)n * dm.DHW + i;
+    const int r = keep[k] ? (vx[k][0] * (grid.Y * grid.Z) + vx[k][1] * grid.Z + vx[k][2]) : -1;
+    if (kExport) {
+      if (geom_out) { geom_out[3 * p + 0] = g[k][0]; geom_out[3 * p + 1] = g[k][1]; geom_out[3 * p + 2] = g[k][2]; }
+      if (vox_out) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          // Tensor.long() on x86: cvttss2si -> INT64_MIN for NaN / out of range
+          const bool ok = fabsf(c[k][a]) < 9.2e18f;
+          vox_out[3 * p + a] = ok ? __float2ll_rz(c[k][a]) : (long long)0x8000000000000000ULL;
+        }
       }
-      cell[p] = cid;
-      within[p] = tk;
+      if (keep_out) keep_out[p] = keep[k] ? 1 : 0;
+      if (rank64_out) rank64_out[p] = (long long)r;
+    } else {
+      if (rank) rank[p] = r;
+      if (cell) { cell[p] = cid[k]; within[p] = tk[k]; }
     }
   }
 }
 
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
-  dim3 grid((dm.DHW + 255) / 256, dm.N, dm.B);
+  dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
   ls_index_kernel<false><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, rank, cell, within, counts, nullptr, nullptr,
                                               nullptr, nullptr);
   LS_LAUNCHED();
@@ -152,7 +175,7 @@ int ls_launch_index(const float* M, const float* t, const float* frustum, const 
 
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                      float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s) {
-  dim3 grid((dm.DHW + 255) / 256, dm.N, dm.B);
+  dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
   ls_index_kernel<true><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, nullptr, nullptr, nullptr, nullptr, geom, vox,
                                              keep, rank64);
   LS_LAUNCHED();
