@@ -207,6 +207,23 @@ class Stepper:
                                  self.code, C.byref(self.s), self._p(self.ws), self.ws.numel(), self._p(self.gfeat),
                                  self._p(self.glogits), stream), "ls_backward")
 
+    def capture(self):
+        """Capture one step (all its kernels, the library's side streams included) into a CUDA
+        graph; replaying it is one launch per step."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = self.lib.ls_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step()
+        self.graph_launches = int(self.lib.ls_launch_count() - l0)
+        self.graph = graph
+        return graph
+
     def step_e2e(self, chunks: int = E2E_CHUNKS):
         """Host buffers in, host buffers out: every input (including the upstream gradients)
         is copied from pinned host memory and every output is copied back, synchronised per
@@ -325,6 +342,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="samples in the bounded CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every step kernel by kernel instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -381,6 +400,14 @@ def main():
     for _ in range(args.warmup):
         st.step()
     barrier()
+    use_graph = os.environ.get("LS_BENCH_GRAPH", "1") == "1" and not args.no_graph
+    if use_graph:
+        graph = st.capture()
+        for _ in range(args.warmup):
+            graph.replay()
+        barrier()
+    config["launch"] = ("one CUDA graph replay per step (3 ABI calls captured once: %d kernels/memsets, side streams "
+                        "included)" % st.graph_launches) if use_graph else "stream launches, 3 ABI calls per step"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -389,10 +416,13 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        st.step()
+        if use_graph:
+            graph.replay()
+        else:
+            st.step()
     e1.record()
     barrier()
-    launches = int(lib.ls_launch_count() - l0)
+    launches = st.graph_launches * args.steps if use_graph else int(lib.ls_launch_count() - l0)
     ms = e0.elapsed_time(e1)
     # end to end: host buffers in/out, same number of steps
     for _ in range(2):

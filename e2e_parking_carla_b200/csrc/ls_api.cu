@@ -2,6 +2,7 @@
 // forward / backward pipelines.  No torch types, no exceptions, no allocation, no host sync.
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ls_internal.h"
@@ -13,6 +14,11 @@ void ls_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int ls_note_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d", cudaGetErrorString(e), file, line);
   return LS_ERR_CUDA;
+}
+
+bool ls_pdl_enabled() {
+  static const bool on = getenv("LS_NO_PDL") == nullptr;
+  return on;
 }
 
 // ---- side streams ---------------------------------------------------------------------

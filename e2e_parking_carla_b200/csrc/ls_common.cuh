@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "ls_b200.h"
 
@@ -164,3 +165,44 @@ int ls_note_cuda_error(cudaError_t e, const char* file, int line);
     if (e__ != cudaSuccess) return ls_note_cuda_error(e__, __FILE__, __LINE__); \
   } while (0)
 #define LS_LAUNCHED() do { ls_note_launch(); LS_CUDA(cudaGetLastError()); } while (0)
+
+// ---- programmatic dependent launch ------------------------------------------------------
+// Every kernel of the pipeline is launched with the programmatic-stream-serialization
+// attribute: it may be scheduled while the tail of its predecessor in the stream is still
+// running, does its private prologue (index math, shared-memory zeroing) and blocks in
+// ls_pdl_wait() until the predecessor has completed and its writes are visible.  EVERY kernel
+// calls ls_pdl_wait() before touching global memory, which keeps the ordering transitive
+// along the chain.  ls_pdl_trigger() lets the successor start being scheduled as soon as all
+// CTAs of this grid are resident.  Set LS_NO_PDL=1 to launch with plain stream ordering.
+__device__ __forceinline__ void ls_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef LS_PDL_TRIGGER
+#define LS_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void ls_pdl_trigger() {
+  if (LS_PDL_TRIGGER) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool ls_pdl_enabled();   // ls_api.cu
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ls_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ls_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel names with template commas go in parentheses: LS_LAUNCH((k<T, 4>), grid, block, smem, s, args...)
+#define LS_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                      \
+    cudaError_t e__ = ls_launch(kernel, grid, block, smem, stream, __VA_ARGS__);            \
+    if (e__ != cudaSuccess) return ls_note_cuda_error(e__, __FILE__, __LINE__);             \
+    ls_note_launch();                                                                       \
+  } while (0)

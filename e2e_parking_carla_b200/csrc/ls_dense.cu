@@ -11,6 +11,8 @@
 template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ prob) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   __shared__ float red[8][33];
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
@@ -54,6 +56,8 @@ ls_softmax_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ p
 template <typename T>
 __global__ void __launch_bounds__(256)
 ls_softmax_serial_kernel(const T* __restrict__ logits, int D, int HW, T* __restrict__ prob) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int img = blockIdx.y;
   const int rc = blockIdx.x * blockDim.x + threadIdx.x;
   if (rc >= HW) return;
@@ -68,9 +72,9 @@ ls_softmax_serial_kernel(const T* __restrict__ logits, int D, int HW, T* __restr
 }
 
 template <typename T>
-static void ls_softmax_dispatch(const T* logits, const LsDims& dm, T* prob, dim3 grid, cudaStream_t s) {
+static int ls_softmax_dispatch(const T* logits, const LsDims& dm, T* prob, dim3 grid, cudaStream_t s) {
   const int k = (dm.D + 7) / 8;
-#define LS_SM(KK) ls_softmax_kernel<T, KK><<<grid, 256, 0, s>>>(logits, dm.D, dm.HW, prob)
+#define LS_SM(KK) LS_LAUNCH((ls_softmax_kernel<T, KK>), grid, dim3(256), 0, s, logits, dm.D, dm.HW, prob)
   if (k <= 2) LS_SM(2);
   else if (k <= 4) LS_SM(4);
   else if (k <= 6) LS_SM(6);
@@ -78,25 +82,22 @@ static void ls_softmax_dispatch(const T* logits, const LsDims& dm, T* prob, dim3
   else if (k <= 12) LS_SM(12);
   else LS_SM(16);
 #undef LS_SM
+  return LS_OK;
 }
 
 int ls_launch_softmax(const void* logits, int dtype, const LsDims& dm, void* prob, cudaStream_t s) {
   const int images = dm.B * dm.N;
   if (dm.D <= 8 * LS_SM_MAXK) {
     dim3 grid((dm.HW + 31) / 32, images);
-    if (dtype == LS_F32)
-      ls_softmax_dispatch<float>((const float*)logits, dm, (float*)prob, grid, s);
-    else
-      ls_softmax_dispatch<__nv_bfloat16>((const __nv_bfloat16*)logits, dm, (__nv_bfloat16*)prob, grid, s);
-  } else {
-    dim3 grid((dm.HW + 255) / 256, images);
-    if (dtype == LS_F32)
-      ls_softmax_serial_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, dm.D, dm.HW, (float*)prob);
-    else
-      ls_softmax_serial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, dm.D, dm.HW,
-                                                                   (__nv_bfloat16*)prob);
+    if (dtype == LS_F32) return ls_softmax_dispatch<float>((const float*)logits, dm, (float*)prob, grid, s);
+    return ls_softmax_dispatch<__nv_bfloat16>((const __nv_bfloat16*)logits, dm, (__nv_bfloat16*)prob, grid, s);
   }
-  LS_LAUNCHED();
+  dim3 grid((dm.HW + 255) / 256, images);
+  if (dtype == LS_F32)
+    LS_LAUNCH(ls_softmax_serial_kernel<float>, grid, dim3(256), 0, s, (const float*)logits, dm.D, dm.HW, (float*)prob);
+  else
+    LS_LAUNCH(ls_softmax_serial_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)logits, dm.D,
+              dm.HW, (__nv_bfloat16*)prob);
   return LS_OK;
 }
 
@@ -109,6 +110,8 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_softmax_bwd_kernel(const T* __restrict__ prob, const float* __restrict__ gprob_pm, const T* __restrict__ gext,
                       int D, int HW, T* __restrict__ glogits) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   extern __shared__ float sm[];
   const int Dp = D | 1;
   float* stage = sm;                   // [32][Dp]
@@ -157,6 +160,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ls_softmax_bwd_serial_kernel(const T* __restrict__ prob, const float* __restrict__ gprob_pm, const T* __restrict__ gext,
                              int D, int HW, T* __restrict__ glogits) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int img = blockIdx.y;
   const int rc = blockIdx.x * blockDim.x + threadIdx.x;
   if (rc >= HW) return;
@@ -176,10 +181,11 @@ ls_softmax_bwd_serial_kernel(const T* __restrict__ prob, const float* __restrict
 }
 
 template <typename T>
-static void ls_softmax_bwd_dispatch(const T* prob, const float* gprob_pm, const T* gext, const LsDims& dm, T* glogits,
+static int ls_softmax_bwd_dispatch(const T* prob, const float* gprob_pm, const T* gext, const LsDims& dm, T* glogits,
                                     dim3 grid, size_t smem, cudaStream_t s) {
   const int k = (dm.D + 7) / 8;
-#define LS_SB(KK) ls_softmax_bwd_kernel<T, KK><<<grid, 256, smem, s>>>(prob, gprob_pm, gext, dm.D, dm.HW, glogits)
+#define LS_SB(KK) \
+  LS_LAUNCH((ls_softmax_bwd_kernel<T, KK>), grid, dim3(256), smem, s, prob, gprob_pm, gext, dm.D, dm.HW, glogits)
   if (k <= 2) LS_SB(2);
   else if (k <= 4) LS_SB(4);
   else if (k <= 6) LS_SB(6);
@@ -187,6 +193,7 @@ static void ls_softmax_bwd_dispatch(const T* prob, const float* gprob_pm, const 
   else if (k <= 12) LS_SB(12);
   else LS_SB(16);
 #undef LS_SB
+  return LS_OK;
 }
 
 int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* gext, int dtype, const LsDims& dm,
@@ -195,21 +202,18 @@ int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* g
   if (dm.D <= 8 * LS_SM_MAXK && smem <= 48 * 1024) {
     dim3 grid((dm.HW + 31) / 32, dm.B * dm.N);
     if (dtype == LS_F32)
-      ls_softmax_bwd_dispatch<float>((const float*)prob, gprob_pm, (const float*)gext, dm, (float*)glogits, grid, smem, s);
-    else
-      ls_softmax_bwd_dispatch<__nv_bfloat16>((const __nv_bfloat16*)prob, gprob_pm, (const __nv_bfloat16*)gext, dm,
-                                             (__nv_bfloat16*)glogits, grid, smem, s);
-  } else {
-    dim3 grid((dm.HW + 255) / 256, dm.B * dm.N);
-    if (dtype == LS_F32)
-      ls_softmax_bwd_serial_kernel<float><<<grid, 256, 0, s>>>((const float*)prob, gprob_pm, (const float*)gext, dm.D,
-                                                               dm.HW, (float*)glogits);
-    else
-      ls_softmax_bwd_serial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)prob, gprob_pm,
-                                                                       (const __nv_bfloat16*)gext, dm.D, dm.HW,
-                                                                       (__nv_bfloat16*)glogits);
+      return ls_softmax_bwd_dispatch<float>((const float*)prob, gprob_pm, (const float*)gext, dm, (float*)glogits, grid,
+                                            smem, s);
+    return ls_softmax_bwd_dispatch<__nv_bfloat16>((const __nv_bfloat16*)prob, gprob_pm, (const __nv_bfloat16*)gext, dm,
+                                                  (__nv_bfloat16*)glogits, grid, smem, s);
   }
-  LS_LAUNCHED();
+  dim3 grid((dm.HW + 255) / 256, dm.B * dm.N);
+  if (dtype == LS_F32)
+    LS_LAUNCH(ls_softmax_bwd_serial_kernel<float>, grid, dim3(256), 0, s, (const float*)prob, gprob_pm,
+              (const float*)gext, dm.D, dm.HW, (float*)glogits);
+  else
+    LS_LAUNCH(ls_softmax_bwd_serial_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)prob, gprob_pm,
+              (const __nv_bfloat16*)gext, dm.D, dm.HW, (__nv_bfloat16*)glogits);
   return LS_OK;
 }
 
@@ -220,6 +224,8 @@ int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* g
 template <typename T>
 __global__ void __launch_bounds__(256)
 ls_to_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restrict__ dst) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   __shared__ float tile[64][65];
   const int img = blockIdx.z, hw0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const T* in = src + (size_t)img * C * HW;
@@ -247,6 +253,8 @@ ls_to_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256)
 ls_from_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restrict__ dst) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   __shared__ float tile[64][65];
   const int img = blockIdx.z, hw0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const T* in = src + (size_t)img * HW * Cp;
@@ -272,20 +280,19 @@ ls_from_nhwc_kernel(const T* __restrict__ src, int C, int Cp, int HW, T* __restr
 int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s) {
   dim3 grid((HW + 63) / 64, (Cp + 63) / 64, images);
   if (dtype == LS_F32)
-    ls_to_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)src, C, Cp, HW, (float*)dst);
+    LS_LAUNCH(ls_to_nhwc_kernel<float>, grid, dim3(256), 0, s, (const float*)src, C, Cp, HW, (float*)dst);
   else
-    ls_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, C, Cp, HW, (__nv_bfloat16*)dst);
-  LS_LAUNCHED();
+    LS_LAUNCH(ls_to_nhwc_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)src, C, Cp, HW,
+              (__nv_bfloat16*)dst);
   return LS_OK;
 }
 
 int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s) {
   dim3 grid((HW + 63) / 64, (Cp + 63) / 64, images);
   if (dtype == LS_F32)
-    ls_from_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)src, C, Cp, HW, (float*)dst);
+    LS_LAUNCH(ls_from_nhwc_kernel<float>, grid, dim3(256), 0, s, (const float*)src, C, Cp, HW, (float*)dst);
   else
-    ls_from_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, C, Cp, HW,
-                                                            (__nv_bfloat16*)dst);
-  LS_LAUNCHED();
+    LS_LAUNCH(ls_from_nhwc_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, (const __nv_bfloat16*)src, C, Cp, HW,
+              (__nv_bfloat16*)dst);
   return LS_OK;
 }

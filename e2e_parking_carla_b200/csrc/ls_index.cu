@@ -45,6 +45,8 @@ __device__ __forceinline__ void ls_gauss_jordan_cols(double (&col)[n], int base)
 __global__ void __launch_bounds__(32)
 ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr, int BN,
                            float* __restrict__ M, float* __restrict__ t) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int i = blockIdx.x, lane = threadIdx.x;
   double e[4], k[3];
 #pragma unroll
@@ -83,8 +85,7 @@ ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restri
 }
 
 int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s) {
-  ls_camera_transform_kernel<<<BN, 32, 0, s>>>(intr, extr, BN, M, t);
-  LS_LAUNCHED();
+  LS_LAUNCH(ls_camera_transform_kernel, dim3(BN), dim3(32), 0, s, intr, extr, BN, M, t);
   return LS_OK;
 }
 
@@ -95,7 +96,9 @@ int ls_launch_camera_transform(const float* intr, const float* extr, int BN, flo
 // integer atomicAdd per kept point whose return value ("ticket") is the point's slot inside
 // its cell, so placement later needs no second atomic pass.
 // =====================================================================================
+#ifndef LS_IDX_ILP
 #define LS_IDX_ILP 2
+#endif
 
 template <bool kExport>
 __global__ void __launch_bounds__(256)
@@ -103,11 +106,14 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
                 LsDims dm, LsGrid grid, int* __restrict__ rank, int* __restrict__ cell, int* __restrict__ within,
                 int* __restrict__ counts, float* __restrict__ geom_out, long long* __restrict__ vox_out,
                 unsigned char* __restrict__ keep_out, long long* __restrict__ rank64_out) {
-  __shared__ float cam[12];
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int b = blockIdx.z, n = blockIdx.y;
-  if (threadIdx.x < 9) cam[threadIdx.x] = M[(b * dm.N + n) * 9 + threadIdx.x];
-  else if (threadIdx.x < 12) cam[threadIdx.x] = t[(b * dm.N + n) * 3 + threadIdx.x - 9];
-  __syncthreads();
+  float cam[12];   // warp-uniform loads: every thread keeps the camera's 3x3 + translation in registers
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cam[k] = __ldg(M + (b * dm.N + n) * 9 + k);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cam[9 + k] = __ldg(t + (b * dm.N + n) * 3 + k);
   // LS_IDX_ILP points per thread (strided by the CTA width): their loads, divisions and the
   // histogram atomics are independent, so the returning atomics overlap instead of serialising
   const int i0 = blockIdx.x * (blockDim.x * LS_IDX_ILP) + threadIdx.x;
@@ -167,9 +173,8 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
   dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
-  ls_index_kernel<false><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, rank, cell, within, counts, nullptr, nullptr,
-                                              nullptr, nullptr);
-  LS_LAUNCHED();
+  LS_LAUNCH(ls_index_kernel<false>, grid, dim3(256), 0, s, M, t, frustum, dm, g, rank, cell, within, counts,
+            (float*)nullptr, (long long*)nullptr, (unsigned char*)nullptr, (long long*)nullptr);
   return LS_OK;
 }
 
@@ -212,6 +217,8 @@ __device__ __forceinline__ int ls_warp_incl_scan(int v, int lane) {
 
 __global__ void __launch_bounds__(1024)
 ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_start, int* __restrict__ tile_order) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   __shared__ int tile_base[1024];
   __shared__ int warp_tot[32];
   __shared__ int chunk_total;
@@ -282,6 +289,8 @@ ls_scan_kernel(const int* __restrict__ counts, LsGrid g, int* __restrict__ seg_s
 // place in the heaviest-first order, and the in-tile scan.  No cross-CTA dependency.
 __global__ void __launch_bounds__(256)
 ls_tile_totals_kernel(const int* __restrict__ counts, int ntiles_all, int* __restrict__ tile_tot) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (t >= ntiles_all) return;
   int4 a, c;
@@ -295,6 +304,8 @@ ls_tile_totals_kernel(const int* __restrict__ counts, int ntiles_all, int* __res
 __global__ void __launch_bounds__(256)
 ls_tile_scan_kernel(const int* __restrict__ counts, const int* __restrict__ tile_tot, LsGrid g,
                     int* __restrict__ seg_start, int* __restrict__ tile_order) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= g.tiles) return;
@@ -330,14 +341,12 @@ int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* se
                    int* tile_tot, cudaStream_t s) {
   if (g.tiles <= 2048 && tile_tot) {
     const int all = g.tiles * dm.B;
-    ls_tile_totals_kernel<<<(all + 7) / 8, 256, 0, s>>>(counts, all, tile_tot);
-    LS_LAUNCHED();
-    ls_tile_scan_kernel<<<dim3((g.tiles + 7) / 8, dm.B), 256, 0, s>>>(counts, tile_tot, g, seg_start, tile_order);
-    LS_LAUNCHED();
+    LS_LAUNCH(ls_tile_totals_kernel, dim3((all + 7) / 8), dim3(256), 0, s, counts, all, tile_tot);
+    LS_LAUNCH(ls_tile_scan_kernel, dim3((g.tiles + 7) / 8, dm.B), dim3(256), 0, s, counts, (const int*)tile_tot, g,
+              seg_start, tile_order);
     return LS_OK;
   }
-  ls_scan_kernel<<<dm.B, 1024, 0, s>>>(counts, g, seg_start, tile_order);
-  LS_LAUNCHED();
+  LS_LAUNCH(ls_scan_kernel, dim3(dm.B), dim3(1024), 0, s, counts, g, seg_start, tile_order);
   return LS_OK;
 }
 
@@ -356,6 +365,8 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, const T* __restrict__ prob, LsDims dm,
                 LsGrid grid, const int* __restrict__ seg_start, int2* __restrict__ recs, int2* __restrict__ pix_recs) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   extern __shared__ int2 stage[];                 // [32][Dp], Dp odd
   const int Dp = dm.D | 1;
   const int b = blockIdx.z, n = blockIdx.y, rc0 = blockIdx.x * 32;
@@ -405,7 +416,8 @@ template <typename T>
 static int ls_place_dispatch(const int* cell, const int* within, const T* prob, const LsDims& dm, const LsGrid& g,
                              const int* seg_start, int2* recs, int2* pix_recs, dim3 grid, size_t smem, cudaStream_t s) {
   const int k = (dm.D + 7) / 8;
-#define LS_PL(KK) ls_place_kernel<T, KK><<<grid, 256, smem, s>>>(cell, within, prob, dm, g, seg_start, recs, pix_recs)
+#define LS_PL(KK) \
+  LS_LAUNCH((ls_place_kernel<T, KK>), grid, dim3(256), smem, s, cell, within, prob, dm, g, seg_start, recs, pix_recs)
   if (k <= 2) LS_PL(2);
   else if (k <= 4) LS_PL(4);
   else if (k <= 6) LS_PL(6);
@@ -429,9 +441,7 @@ int ls_launch_place(const int* cell, const int* within, const void* prob, int dt
   else
     rc = ls_place_dispatch<__nv_bfloat16>(cell, within, (const __nv_bfloat16*)prob, dm, g, seg_start, recs, pix_recs,
                                           grid, smem, s);
-  if (rc) return rc;
-  LS_LAUNCHED();
-  return LS_OK;
+  return rc;
 }
 
 // (row-major rank, point count) of every cell of sample b, from the CSR (test export)

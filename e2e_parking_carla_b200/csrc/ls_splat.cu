@@ -23,13 +23,11 @@ __host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
   return t;
 }
 
-// sorted record: x = pixel << 12 | last_of_cell << 11 | cell_in_tile,  y = prob bits
+// canonical record: x = pixel << 12 | last_of_cell << 11 | valid << 10 | cell_in_tile,  y = prob bits
 #define LS_REC_LAST 0x800
-#ifndef LS_ITEM_SHIFT
-#define LS_ITEM_SHIFT 4
-#endif
-#define LS_ITEM (1 << LS_ITEM_SHIFT)   // target records per work item of phase B
-#define LS_QWIN 4    // records a quarter-warp keeps in flight (work items are padded to this)
+#define LS_REC_VALID 0x400
+#define LS_QWIN 4    // records a quarter-warp keeps in flight
+#define LS_QWARPS (LS_THREADS / 8)
 
 #ifdef LS_PROFILE
 __device__ unsigned long long ls_dbg_phase[8];
@@ -51,35 +49,60 @@ __device__ int ls_dbg_cta[8192][8];   // per CTA: records, then cycles of each p
 
 __device__ __forceinline__ unsigned ls_quarter_mask() { return 0xFFu << (threadIdx.x & 24); }
 
-// Padded scratch layout of the re-ordered records: tile t of a sample starts at
-// s0 + (s0 >> (LS_ITEM_SHIFT-2)) + 4*t  (s0 = first record of the tile in the CSR); every work
-// item is padded to a multiple of LS_QWIN=4 records: at most 3*(n/LS_ITEM + 1) <=
-// (n >> (LS_ITEM_SHIFT-2)) + 3 extra records per tile, so the regions never overlap.
-#define LS_PAD_SHIFT (LS_ITEM_SHIFT - 2)
-__host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts, int tiles) {
-  return (size_t)Npts + ((size_t)Npts >> LS_PAD_SHIFT) + 4 * (size_t)tiles + 8;
+// Canonical records of a sample live in the CSR layout of `recs` (slot seg_start[cell] + rank);
+// the slack lets a stream prefetch one window past the end of the sample.
+#define LS_SORTED_SLACK 8
+__host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return (size_t)Npts + LS_SORTED_SLACK; }
+
+// =====================================================================================
+// K3a: canonical order.  The placement wrote every cell's records in ticket (atomic arrival)
+// order; here each record finds its rank among the records of its cell (keys are unique:
+// pixel, depth bin) and moves to slot seg_start[cell] + rank of a second buffer, so the
+// splat's summation order - and with it every bit of the BEV tensor - is independent of
+// the atomics.  Flat: one thread per record, one CTA per tile (heaviest first), the compare
+// loop runs over L1-resident keys.  Replaces the (unstable) argsort of model/bev_model.py:96.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
+                LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  __shared__ int seg[LS_TILE + 1];
+  const int b = blockIdx.x % dm.B;
+  const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
+  const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  for (int i = threadIdx.x; i <= LS_TILE; i += blockDim.x) seg[i] = segg[i];
+  __syncthreads();
+  const int s0 = seg[0], s1 = seg[LS_TILE];
+  const int2* rin = recs + (size_t)b * dm.Npts;
+  int2* out = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
+  for (int i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+    const int2 r = rin[i];
+    const int cl = (unsigned)r.x >> 24;
+    const int a = seg[cl], e = seg[cl + 1];
+    int pos = a;
+#pragma unroll 4
+    for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
+    const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
+    out[pos] = make_int2((pix << 12) | cl | LS_REC_VALID | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
+  }
 }
 
 // =====================================================================================
-// K3: forward splat.  One CTA per (sample, 16x16-voxel tile), heaviest tiles first:
-//  0  work items: the tile's record run is cut at cell boundaries into items of about
-//     LS_ITEM records, each padded to a multiple of LS_QWIN (dummy records weigh 0).
-//  A  canonicalise: one thread per point record of the tile; its position inside its cell =
-//     number of records of that cell with a smaller key (keys are unique), which makes the
-//     summation order independent of the atomics that placed the records.  The re-ordered
-//     records {pixel<<12 | last_of_cell<<11 | cell_in_tile, prob} go to the padded scratch.
-//  B  reduce: work items are dealt round-robin to the 32 quarter-warps.  A lane owns 8 channels
-//     (two 16-byte pieces of the 256-byte feature row); LS_QWIN rows are in flight while the
-//     next records are prefetched; prob*feat accumulates in registers and is dropped into the
-//     shared-memory tile [cell][channel] (swizzled, conflict-free) on a last-of-cell record.
+// K3b: forward splat.  One CTA per (sample, LS_TX x LS_TY voxel tile), heaviest tiles first:
+//  B  reduce: the tile's run of canonical records is cut at cell boundaries into LS_QWARPS
+//     nearly equal pieces, one per quarter-warp.  A lane owns 8 channels (two 16-byte pieces of
+//     the 256-byte feature row); LS_QWIN rows are in flight while the next records are
+//     prefetched; prob*feat accumulates in registers and is dropped into the shared-memory
+//     tile [cell][channel] (swizzled, conflict-free) on a last-of-cell record.
 //  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
 //     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
 // =====================================================================================
 template <typename T, bool VEC4, int kCC>
 __global__ void __launch_bounds__(LS_THREADS, 768 / LS_THREADS)
-ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, const int* __restrict__ seg_start,
-                    const int* __restrict__ tile_order, int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
+ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
+                    const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
                     float* __restrict__ bev, LsBevStrides st) {
   extern __shared__ float smem[];
   const LsTileGeom tgr = ls_tile_geom(dm.Cp);
@@ -89,96 +112,25 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   const int ccmax = kCC ? kCC : tgr.cc;
   float* tile = smem;                                            // [LS_TILE][stride]
   int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1] CSR offsets of the tile
-  int* heads = seg + LS_TILE + 1;                                // [LS_TILE + 1] first cell of each work item
-  int* pstart = heads + LS_TILE + 1;                             // [LS_TILE + 1] padded start of each work item
-  int* cell_item = pstart + LS_TILE + 1;                         // [LS_TILE]     work item of each cell
-  int* ctl = cell_item + LS_TILE;                                // [0] items, [1] next item, [2..17] warp sums
 
   // heaviest tiles first, all samples interleaved: blockIdx.x = order_index * B + b
   const int b = blockIdx.x % dm.B;
+  const int tid = threadIdx.x;
+  LS_TICK_INIT();
+  ls_pdl_trigger();
+  // private prologue of a programmatic dependent launch: zero the accumulator tile, then wait
+  // for the producers of seg_start / tile_order / the canonical records
+  for (int i = tid; i < LS_TILE * stride / 4; i += LS_THREADS)
+    reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  ls_pdl_wait();
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
-  LS_TICK_INIT();
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
-  __syncthreads();
-  LS_TICK(0);
-#ifdef LS_PROFILE
-  if (threadIdx.x == 0 && blockIdx.x < 8192) ls_dbg_cta[blockIdx.x][0] = seg[LS_TILE] - seg[0];
-#endif
-  const int s0 = seg[0], s1 = seg[LS_TILE];
-  const bool tile_empty = (s0 == s1);
-  const int2* rin = recs + (size_t)b * dm.Npts;
-  int2* rsp = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts, grid.tiles) + (s0 + (s0 >> LS_PAD_SHIFT) + 4 * tile_id);
-
-  if (!tile_empty) {
-    // ---- work items: runs of whole cells of about LS_ITEM records ----------------------
-    // cell `tid` opens an item when its first record falls in a new LS_ITEM-sized bucket
-    const int id = (seg[tid] - s0) / LS_ITEM;
-    const bool head = (tid == 0) || (id != (seg[tid - 1] - s0) / LS_ITEM);
-    const unsigned bal = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) ctl[2 + warp] = __popc(bal);
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += ctl[2 + w];
-    const int my_item = before + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
-    cell_item[tid] = my_item;
-    if (head) heads[my_item] = tid;
-    int nitems = 0;
-    for (int w = 0; w < LS_THREADS / 32; ++w) nitems += ctl[2 + w];
-    if (tid == 0) { heads[nitems] = LS_TILE; ctl[0] = nitems; }
-    __syncthreads();
-    // padded item starts: exclusive scan of the item lengths rounded up to LS_QWIN
-    int plen = 0;
-    if (tid < nitems) plen = (seg[heads[tid + 1]] - seg[heads[tid]] + LS_QWIN - 1) & ~(LS_QWIN - 1);
-    int incl = plen;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) ctl[10 + warp] = incl;
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += ctl[10 + w];
-    if (tid < nitems) pstart[tid] = wbase + incl - plen;
-    if (tid == LS_THREADS - 1) pstart[nitems] = wbase + incl;  // padded total (plen = 0 beyond the last item)
-    __syncthreads();
-    LS_TICK(1);
-    // ---- phase A: canonical order inside each cell, scattered into the padded layout ----
-    // The tile's records are staged in the (not yet used) accumulator tile so that the
-    // rank-by-counting loop reads shared memory; records beyond its capacity (never at the
-    // shipped grid sizes) are ranked straight from global memory.
-    int2* stage = reinterpret_cast<int2*>(tile);
-    const int cap = LS_TILE * stride / 2;
-    const int nst = min(s1 - s0, cap);
-    for (int i = tid; i < nst; i += LS_THREADS) stage[i] = rin[s0 + i];
-    __syncthreads();
-    for (int i = s0 + tid; i < s1; i += LS_THREADS) {
-      const int2 r = (i - s0 < nst) ? stage[i - s0] : rin[i];
-      const int cl = (unsigned)r.x >> 24;
-      const int a = seg[cl], e = seg[cl + 1];
-      int pos = a;
-      if (e - s0 <= nst) {
-        for (int j = a - s0; j < e - s0; ++j) pos += (stage[j].x < r.x) ? 1 : 0;
-      } else {
-        for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
-      }
-      const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
-      const int it = cell_item[cl];
-      rsp[pstart[it] + pos - seg[heads[it]]] =
-          make_int2((pix << 12) | cl | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
-    }
-    if (tid < nitems) {   // dummy records: pixel 0, weight 0, never flush
-      const int len = seg[heads[tid + 1]] - seg[heads[tid]];
-      for (int j = len; j < plen; ++j) rsp[pstart[tid] + j] = make_int2(0, 0);
-    }
-    __syncthreads();      // staging area is about to be zeroed and re-used as the accumulator tile
-  }
 
   const int ql = tid & 7;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
+  const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
   const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
   // phase C geometry of this thread (fixed): 4 consecutive y of one x-row; channel quads qg, qg+4, ...
   const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, qg = tid / (LS_TILE / 4);
@@ -189,46 +141,55 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
   for (int cbase = 0; cbase < Cp; cbase += LS_CCHUNK) {
     const int cc = kCC ? kCC : min(ccmax, Cp - cbase);
     const int nquads = cc >> 2;
-    if (!tile_empty) {
-      // zero the tile: cells nobody hits are never touched by phase B
+    // zero the tile (cells nobody hits are never touched by phase B); the first pass did it
+    // in the prologue
+    if (cbase > 0) {
       for (int i = tid; i < LS_TILE * stride / 4; i += LS_THREADS)
         reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();   // also orders phase A's scratch records before phase B's reads
-    LS_TICK(2);
-    // ---- phase B: a quarter-warp per work item; lane = channels [4ql,4ql+4) and [32+4ql,..) ----
+    __syncthreads();
+    LS_TICK(0);
+    const int s0 = seg[0], s1 = seg[LS_TILE];
+    const bool tile_empty = (s0 == s1);
+#ifdef LS_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < 8192) ls_dbg_cta[blockIdx.x][0] = s1 - s0;
+#endif
+    // ---- phase B: lane = channels [4ql,4ql+4) and [32+4ql,..) of its quarter-warp's records ----
     if (!tile_empty) {
+      // this quarter-warp's cells [c0, c1): boundary q = first cell that starts at or after
+      // record s0 + q*n/LS_QWARPS (binary search in the tile's offsets)
+      const int qw = tid >> 3, n = s1 - s0;
+      int c0, c1;
+      {
+        const int t0 = s0 + (int)(((long long)qw * n) / LS_QWARPS);
+        const int t1 = s0 + (int)(((long long)(qw + 1) * n) / LS_QWARPS);
+        int lo0 = 0, hi0 = LS_TILE, lo1 = 0, hi1 = LS_TILE;
+#pragma unroll
+        for (int step = 0; step < 8; ++step) {          // LS_TILE <= 256
+          const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+          if (lo0 < hi0) { if (seg[m0] < t0) lo0 = m0 + 1; else hi0 = m0; }
+          if (lo1 < hi1) { if (seg[m1] < t1) lo1 = m1 + 1; else hi1 = m1; }
+        }
+        c0 = lo0;
+        c1 = (qw == LS_QWARPS - 1) ? LS_TILE : lo1;
+      }
+      int idx = seg[c0];
+      const int end = seg[c1];
       const bool on0 = 4 * ql < cc, on1 = 32 + 4 * ql < cc;
       // lanes beyond the channel count read valid bytes (lane 0's) and never store
       const char* f0 = reinterpret_cast<const char*>(fbase + cbase + (on0 ? 4 * ql : 0));
       const unsigned f1off = (unsigned)((on1 ? 32 : 0) * sizeof(T));       // second 16-byte piece of the row
       const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);    // 32-bit shared-window address
       const unsigned row_sbytes = (unsigned)stride * 4u, ql16 = (unsigned)ql << 4, swz_mask = (unsigned)(nqp - 1) << 4;
-      const int nitems = ctl[0];
-      // Static round-robin of work items over the CTA's 32 quarter-warps.  A stream's items
-      // form one flat sequence of LS_QWIN-record windows: accumulators are flushed by the
-      // last-of-cell flags (every item ends on one), so nothing special happens between items
-      // and the next window's records are always prefetched one window ahead.
-      int it = tid >> 3;
-      const int2* p = nullptr;
-      int wleft = 0;
-      for (; it < nitems; it += LS_THREADS / 8) {
-        wleft = (pstart[it + 1] - pstart[it]) / LS_QWIN;
-        if (wleft > 0) { p = rsp + pstart[it]; break; }
-      }
-      if (wleft > 0) {
+      if (idx < end) {
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int2* p = rs + idx;
         int2 r[LS_QWIN];
 #pragma unroll
-        for (int u = 0; u < LS_QWIN; ++u) r[u] = p[u];          // quarter-warp-uniform 8-byte loads
-#ifdef LS_PROFILE
-        long long tb0 = clock64();
-        if (threadIdx.x == 0 && blockIdx.x < 8192) {
-          if (r[0].x + r[1].x + r[2].x + r[3].x == 0x7f123456) tb0 = 0;   // wait for the records
-          ls_dbg_cta[blockIdx.x][6] = (int)(clock64() - tick__);
+        for (int u = 0; u < LS_QWIN; ++u) {                     // quarter-warp-uniform 8-byte loads
+          r[u] = p[u];
+          if (idx + u >= end) r[u] = make_int2(0, 0);           // beyond the piece: pixel 0, not valid
         }
-        bool first_win__ = true;
-#endif
         for (;;) {
           float4 fa[LS_QWIN], fb[LS_QWIN];
 #pragma unroll
@@ -238,34 +199,22 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int2* __restrict__ recs, 
             fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));
             fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));
           }
-          // locate and fetch the next window while these feature rows are in flight
-          bool more = true;
-          if (--wleft > 0) {
-            p += LS_QWIN;
-          } else {
-            more = false;
-            for (it += LS_THREADS / 8; it < nitems; it += LS_THREADS / 8) {
-              wleft = (pstart[it + 1] - pstart[it]) / LS_QWIN;
-              if (wleft > 0) { p = rsp + pstart[it]; more = true; break; }
-            }
-          }
+          // fetch the next window while these feature rows are in flight
+          idx += LS_QWIN;
+          p += LS_QWIN;
+          const bool more = idx < end;
           int2 rn[LS_QWIN];
 #pragma unroll
-          for (int u = 0; u < LS_QWIN; ++u) rn[u] = more ? p[u] : make_int2(0, 0);
-#ifdef LS_PROFILE
-          if (threadIdx.x == 0 && blockIdx.x < 8192 && first_win__) {
-            if (fa[0].x + fb[3].w == 1.2345e33f) tb0 = 0;                  // wait for the feature rows
-            ls_dbg_cta[blockIdx.x][7] = (int)(clock64() - tick__);
-            first_win__ = false;
-          }
-#endif
+          for (int u = 0; u < LS_QWIN; ++u) rn[u] = (idx + u < end) ? p[u] : make_int2(0, 0);
 #pragma unroll
           for (int u = 0; u < LS_QWIN; ++u) {
-            const float wt = __int_as_float(r[u].y);
-            acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);
-            acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);
-            acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);
-            acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);
+            if (r[u].x & LS_REC_VALID) {
+              const float wt = __int_as_float(r[u].y);
+              acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);
+              acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);
+              acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);
+              acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);
+            }
             if (r[u].x & LS_REC_LAST) {
               const unsigned cl = (unsigned)r[u].x & 255u;
               // row of the cell + this lane's swizzled quads (q and q+8 differ by one address bit)
@@ -350,11 +299,11 @@ int ls_debug_fetch_phase_cycles(unsigned long long* out8) {
 #endif
 }
 
-size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g) { return ls_sorted_capacity(dm.Npts, g.tiles); }
+size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g) { (void)g; return ls_sorted_capacity(dm.Npts); }
 
 static size_t ls_tile_smem_bytes(const LsDims& dm) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  return (size_t)LS_TILE * tg.stride * sizeof(float) + (4 * (LS_TILE + 1) + 32) * sizeof(int);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 4) * sizeof(int);
 }
 static size_t ls_tile_smem_max() {
   LsDims d;
@@ -379,17 +328,19 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   }
   const size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
+  LS_LAUNCH(ls_canon_kernel, grid, dim3(256), 0, s, recs, seg_start, tile_order, dm, g, recs_sorted);
   const bool v4 = ls_bev_vec4(bev, st, g);
+  const dim3 block(LS_THREADS);
+  const int2* rs = recs_sorted;
   if (v4 && dm.Cp == 64 && dm.C == 64)
-    ls_splat_fwd_kernel<T, true, 64><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
-                                                                   dm, g, bev, st);
+    LS_LAUNCH((ls_splat_fwd_kernel<T, true, 64>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
+              bev, st);
   else if (v4)
-    ls_splat_fwd_kernel<T, true, 0><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
-                                                                  dm, g, bev, st);
+    LS_LAUNCH((ls_splat_fwd_kernel<T, true, 0>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
+              bev, st);
   else
-    ls_splat_fwd_kernel<T, false, 0><<<grid, LS_THREADS, smem, s>>>((const T*)featT, recs, seg_start, tile_order, recs_sorted,
-                                                                   dm, g, bev, st);
-  LS_LAUNCHED();
+    LS_LAUNCH((ls_splat_fwd_kernel<T, false, 0>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
+              bev, st);
   return LS_OK;
 }
 
@@ -411,6 +362,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(LS_THREADS)
 ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const int* __restrict__ seg_start,
                         LsDims dm, LsGrid grid, float* __restrict__ gT) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   extern __shared__ float smem[];
   const LsTileGeom tg = ls_tile_geom(min(dm.Cp, LS_TCHUNK));
   float* tile = smem;
@@ -484,10 +437,9 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
   const size_t smem = (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 1) * sizeof(int);
   dim3 grid(g.tiles, dm.B, (dm.Cp + LS_TCHUNK - 1) / LS_TCHUNK);
   if (ls_bev_vec4(gbev, st, g))
-    ls_bwd_transpose_kernel<true><<<grid, LS_THREADS, smem, s>>>(gbev, st, seg_start, dm, g, gT);
+    LS_LAUNCH(ls_bwd_transpose_kernel<true>, grid, dim3(LS_THREADS), smem, s, gbev, st, seg_start, dm, g, gT);
   else
-    ls_bwd_transpose_kernel<false><<<grid, LS_THREADS, smem, s>>>(gbev, st, seg_start, dm, g, gT);
-  LS_LAUNCHED();
+    LS_LAUNCH(ls_bwd_transpose_kernel<false>, grid, dim3(LS_THREADS), smem, s, gbev, st, seg_start, dm, g, gT);
   return LS_OK;
 }
 
@@ -508,6 +460,8 @@ template <typename T, int NCH, bool kFullD>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, 2)
 ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
                      LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
   const int col = blockIdx.x, bn = blockIdx.y;
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
@@ -604,14 +558,14 @@ static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pi
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
   const bool full = dm.D % 16 == 0;
-#define LS_GATHER(NCH)                                                                                           \
-  do {                                                                                                           \
-    if (full)                                                                                                    \
-      ls_bwd_gather_kernel<T, NCH, true><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, \
-                                                                            gprob_pm, (T*)gfeatT);               \
-    else                                                                                                         \
-      ls_bwd_gather_kernel<T, NCH, false><<<grid, LS_GATHER_THREADS, 0, s>>>(gT, (const T*)featT, pix_recs, dm, g, \
-                                                                             gprob_pm, (T*)gfeatT);              \
+#define LS_GATHER(NCH)                                                                                        \
+  do {                                                                                                        \
+    if (full)                                                                                                 \
+      LS_LAUNCH((ls_bwd_gather_kernel<T, NCH, true>), grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, \
+                pix_recs, dm, g, gprob_pm, (T*)gfeatT);                                                       \
+    else                                                                                                      \
+      LS_LAUNCH((ls_bwd_gather_kernel<T, NCH, false>), grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, \
+                pix_recs, dm, g, gprob_pm, (T*)gfeatT);                                                       \
   } while (0)
   switch (nch) {
     case 1: LS_GATHER(1); break;
@@ -621,7 +575,6 @@ static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pi
     default: return LS_ERR_UNSUPPORTED;
   }
 #undef LS_GATHER
-  LS_LAUNCHED();
   return LS_OK;
 }
 

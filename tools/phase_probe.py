@@ -12,8 +12,8 @@ for _ in range(5): st.step()
 torch.cuda.synchronize()
 rc = st.lib.ls_debug_phase_cycles(out)
 v = [x / 5 for x in out]
-ctas = 169 * 16
-names = ["seg load", "items setup", "phaseA+zero", "phaseB", "phaseC", "", "", ""]
+ctas = 350 * 16
+names = ["seg+zero", "", "", "phaseB", "phaseC", "", "", ""]
 print("rc", rc)
 for n, x in zip(names, v):
     if n: print("%-12s avg cycles per CTA %9.0f" % (n, x / ctas))
