@@ -356,7 +356,9 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 // K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
 // =====================================================================================
-#define LS_TCHUNK 16   // channels per CTA of the gradient transposer (small CTAs, many in flight)
+#ifndef LS_TCHUNK
+#define LS_TCHUNK 32   // channels per CTA of the gradient transposer (16, 32 or 64): 8 x 16 B in flight per thread
+#endif
 
 template <bool VEC4>
 __global__ void __launch_bounds__(LS_THREADS)
@@ -372,6 +374,29 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   const int cbase = blockIdx.z * LS_TCHUNK;
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  const int nquads = min(tg.cc, dm.Cp - cbase) >> 2;
+  // thread = (4 consecutive y, x-row, channel quad): four 16-byte loads (4 channels) per pass.
+  // The gradient loads do not depend on the tile's offsets, so they are issued first and
+  // both round trips overlap.
+  const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, q0 = tid / (LS_TILE / 4);
+  const int gx = tx0 + xr, gy = ty0 + 4 * y4;
+  constexpr int kPasses = LS_TCHUNK / 16;
+  float4 c[kPasses][4];
+  if (VEC4) {
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int q = q0 + 4 * ps;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < nquads && gx < grid.X && gy < grid.Y) {
+        const int ch = cbase + 4 * q;
+        const float* g = gbev + (size_t)b * st.b + (size_t)ch * st.c + (size_t)gx * st.x + gy;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ch + k < dm.C) c[ps][k] = __ldg(reinterpret_cast<const float4*>(g + (size_t)k * st.c));
+      }
+    }
+  }
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
   if (tile_id == 0 && blockIdx.z == 0) {   // row Vc of every sample = zeros: where dropped points gather from
     float* zrow = gT + ((size_t)b * (grid.Vc + 1) + grid.Vc) * dm.Cp;
@@ -380,49 +405,41 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   __syncthreads();
   if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
   float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp + cbase;
-  const int nquads = min(tg.cc, dm.Cp - cbase) >> 2;
   if (VEC4) {
-    // thread = (4 consecutive y, x-row, channel quad): four 16-byte loads (4 channels), a 4x4
-    // register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
-    const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, q = tid / (LS_TILE / 4);
-    const int gx = tx0 + xr, gy = ty0 + 4 * y4;
-    if (q < nquads) {
-      const int clc = xr * LS_TY + 4 * y4;
-      const int swz = (clc >> 3) & (tg.nqp - 1);
-      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
-      if (gx < grid.X && gy < grid.Y) {
-        const int c = cbase + 4 * q;
-        const float* g = gbev + (size_t)b * st.b + (size_t)c * st.c + (size_t)gx * st.x + gy;
-        if (c + 0 < dm.C) c0 = __ldg(reinterpret_cast<const float4*>(g));
-        if (c + 1 < dm.C) c1 = __ldg(reinterpret_cast<const float4*>(g + st.c));
-        if (c + 2 < dm.C) c2 = __ldg(reinterpret_cast<const float4*>(g + 2 * st.c));
-        if (c + 3 < dm.C) c3 = __ldg(reinterpret_cast<const float4*>(g + 3 * st.c));
+    // 4x4 register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
+    const int clc = xr * LS_TY + 4 * y4;
+    const int swz = (clc >> 3) & (tg.nqp - 1);
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int q = q0 + 4 * ps;
+      if (q < nquads) {
+        float* d = tile + clc * tg.stride + 4 * (q ^ swz);
+        *reinterpret_cast<float4*>(d) = make_float4(c[ps][0].x, c[ps][1].x, c[ps][2].x, c[ps][3].x);
+        *reinterpret_cast<float4*>(d + tg.stride) = make_float4(c[ps][0].y, c[ps][1].y, c[ps][2].y, c[ps][3].y);
+        *reinterpret_cast<float4*>(d + 2 * tg.stride) = make_float4(c[ps][0].z, c[ps][1].z, c[ps][2].z, c[ps][3].z);
+        *reinterpret_cast<float4*>(d + 3 * tg.stride) = make_float4(c[ps][0].w, c[ps][1].w, c[ps][2].w, c[ps][3].w);
       }
-      float* d = tile + clc * tg.stride + 4 * (q ^ swz);
-      *reinterpret_cast<float4*>(d) = make_float4(c0.x, c1.x, c2.x, c3.x);
-      *reinterpret_cast<float4*>(d + tg.stride) = make_float4(c0.y, c1.y, c2.y, c3.y);
-      *reinterpret_cast<float4*>(d + 2 * tg.stride) = make_float4(c0.z, c1.z, c2.z, c3.z);
-      *reinterpret_cast<float4*>(d + 3 * tg.stride) = make_float4(c0.w, c1.w, c2.w, c3.w);
     }
   } else {
     for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
       const int y = idx % LS_TY, x = (idx / LS_TY) % LS_TX, cr = idx / LS_TILE;
-      const int c = cbase + cr;
+      const int ch = cbase + cr;
       const int ox = tx0 + x, oy = ty0 + y;
       float v = 0.0f;
-      if (c < dm.C && ox < grid.X && oy < grid.Y)
-        v = gbev[(size_t)b * st.b + (size_t)c * st.c + (size_t)ox * st.x + oy];
+      if (ch < dm.C && ox < grid.X && oy < grid.Y)
+        v = gbev[(size_t)b * st.b + (size_t)ch * st.c + (size_t)ox * st.x + oy];
       const int cl = x * LS_TY + y;
       tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
     }
   }
   __syncthreads();
-  // rows of non-empty cells: thread = (quad, cell), 16 B per lane, 64 B per cell
+  // rows of non-empty cells: thread = (quad, cell), 16 B per lane, LS_TCHUNK*4 B per cell
   {
-    const int q = tid & 3;
+    constexpr int kQ = LS_TCHUNK / 4;
+    const int q = tid % kQ;
     if (q < nquads) {
-#pragma unroll
-      for (int cl = tid >> 2; cl < LS_TILE; cl += LS_THREADS / 4) {
+#pragma unroll 4
+      for (int cl = tid / kQ; cl < LS_TILE; cl += LS_THREADS / kQ) {
         if (seg[cl + 1] != seg[cl])
           *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + 4 * q) =
               *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
