@@ -38,7 +38,24 @@ from e2e_parking_carla_b200.synthetic import (LiftSplatShape, make_encoder_outpu
 
 METRIC = "lift_splat_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
-E2E_CHUNKS = int(os.environ.get("LS_E2E_CHUNKS", "8"))
+E2E_CHUNKS = int(os.environ.get("LS_E2E_CHUNKS", "0"))   # 0: small first and last group (see _e2e_sizes)
+
+
+def _e2e_sizes(batch: int, chunks: int):
+    """Sample groups of the host-to-host pipeline.  Every group costs ~10 DMA set-ups, and only
+    the first group's upload and the last group's download are exposed, so the default is a
+    small group at each end and one big group between them (measured best on PCIe gen5:
+    2 + 12 + 2 for 16 samples).  LS_E2E_GROUPS=a,b,c or chunks > 0 (equal groups) override."""
+    sizes = [int(v) for v in os.environ.get("LS_E2E_GROUPS", "").split(",") if v]
+    if sum(sizes) == batch and all(v > 0 for v in sizes):
+        return sizes
+    if chunks > 0:
+        per = (batch + chunks - 1) // chunks
+        return [min(per, batch - lo) for lo in range(0, batch, per)]
+    if batch < 4:
+        return [batch]
+    edge = max(1, batch // 8)
+    return [edge, batch - 2 * edge, edge]
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -227,54 +244,90 @@ class Stepper:
     def step_e2e(self, chunks: int = E2E_CHUNKS):
         """Host buffers in, host buffers out: every input (including the upstream gradients)
         is copied from pinned host memory and every output is copied back, synchronised per
-        step.  The batch is cut into `chunks` groups of samples (the path is per-sample) so
-        that the H2D copy of group k+1, the kernels of group k and the D2H copy of group k-1
-        overlap on three streams - PCIe is full duplex and is the bottleneck here."""
+        step.  PCIe is the bottleneck (2 x 206 MB per step against 0.35 ms of kernels), so the
+        step is scheduled around the link: the batch is cut into `chunks` groups of samples (the
+        path is per-sample, each group has its own workspace); the H2D stream sends the forward
+        inputs of every group first and the upstream gradients after them, the forward of a
+        group starts as soon as its inputs have landed, and the D2H stream returns BEV features
+        while the gradients are still arriving - both directions of the link stay busy."""
+        e2e_graph = getattr(self, "_e2e_graph", None)
+        if e2e_graph is not None and e2e_graph[0] == chunks:
+            e2e_graph[1].replay()
+            torch.cuda.current_stream().synchronize()
+            return
+        self._e2e_enqueue(chunks)
+        torch.cuda.current_stream().synchronize()
+
+    def capture_e2e(self, chunks: int = E2E_CHUNKS):
+        """Capture the whole host-to-host step (copies on the two copy streams included) into
+        one CUDA graph; the pinned host buffers are the graph's fixed inputs and outputs."""
+        self.step_e2e(chunks)                      # allocates the per-group state outside capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._e2e_enqueue(chunks)
+        self._e2e_graph = (chunks, graph)
+        return graph
+
+    def _e2e_enqueue(self, chunks: int):
         sh, ls, lib = self.shape, self.ls, self.lib
-        if not hasattr(self, "_e2e"):
-            per = (sh.batch + chunks - 1) // chunks
-            self._e2e = {"per": per, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
-                         "ev_in": [torch.cuda.Event() for _ in range(chunks)],
-                         "ev_out": [torch.cuda.Event() for _ in range(chunks)],
-                         "shapes": {}}
-        e = self._e2e
-        comp = torch.cuda.current_stream()
-        e["h2d"].wait_stream(comp)
         n = sh.cams
-        for k, lo in enumerate(range(0, sh.batch, e["per"])):
-            hi = min(sh.batch, lo + e["per"])
-            with torch.cuda.stream(e["h2d"]):
-                for name, per_cam in (("feat", True), ("logits", True), ("gprob", True), ("intr", False),
-                                      ("extr", False), ("gbev", False)):
+        if not hasattr(self, "_e2e") or self._e2e["chunks"] != chunks:
+            sizes = _e2e_sizes(sh.batch, chunks)
+            starts = [sum(sizes[:i]) for i in range(len(sizes))]
+            groups = [(lo, lo + sz) for lo, sz in zip(starts, sizes)]
+            shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid)
+                      for lo, hi in groups]
+            self._e2e = {"chunks": chunks, "groups": groups, "shapes": shapes, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
+                         "ws": [torch.empty(ls.workspace_bytes(sc, self.code, True), dtype=torch.uint8,
+                                            device=self.device) for sc in shapes],
+                         "ev": [[torch.cuda.Event() for _ in groups] for _ in range(4)]}
+        e = self._e2e
+        ev_fin, ev_bin, ev_fout, ev_bout = e["ev"]
+        comp = torch.cuda.current_stream()
+        stream = C.c_void_p(comp.cuda_stream)
+        d, P = self.dev, self._p
+        e["h2d"].wait_stream(comp)
+        e["d2h"].wait_stream(comp)
+        with torch.cuda.stream(e["h2d"]):
+            for k, (lo, hi) in enumerate(e["groups"]):
+                for name, per_cam in (("feat", True), ("logits", True), ("intr", False), ("extr", False)):
                     a, b = (lo * n, hi * n) if per_cam else (lo, hi)
-                    self.dev[name][a:b].copy_(self.host[name][a:b], non_blocking=True)
-                e["ev_in"][k].record(e["h2d"])
-            comp.wait_event(e["ev_in"][k])
-            if (lo, hi) not in e["shapes"]:
-                e["shapes"][(lo, hi)] = ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid)
-            sc = e["shapes"][(lo, hi)]
-            d = self.dev
-            stream = C.c_void_p(comp.cuda_stream)
-            P = self._p
+                    d[name][a:b].copy_(self.host[name][a:b], non_blocking=True)
+                ev_fin[k].record(e["h2d"])
+            for k, (lo, hi) in enumerate(e["groups"]):
+                d["gbev"][lo:hi].copy_(self.host["gbev"][lo:hi], non_blocking=True)
+                d["gprob"][lo * n:hi * n].copy_(self.host["gprob"][lo * n:hi * n], non_blocking=True)
+                ev_bin[k].record(e["h2d"])
+        for k, (lo, hi) in enumerate(e["groups"]):
+            sc, ws = e["shapes"][k], e["ws"][k]
+            comp.wait_event(ev_fin[k])
             ls.check(lib.ls_camera_transform(P(d["intr"][lo:hi]), P(d["extr"][lo:hi]), (hi - lo) * n,
                                              P(self.M[lo:hi]), P(self.t[lo:hi]), stream), "ls_camera_transform")
             ls.check(lib.ls_forward(P(d["feat"][lo * n:hi * n]), P(d["logits"][lo * n:hi * n]), self.code,
-                                    P(self.M[lo:hi]), P(self.t[lo:hi]), P(self.frustum), C.byref(sc), P(self.ws),
-                                    self.ws.numel(), 1, P(self.bev[lo:hi]), C.byref(self.st),
+                                    P(self.M[lo:hi]), P(self.t[lo:hi]), P(self.frustum), C.byref(sc), P(ws),
+                                    ws.numel(), 1, P(self.bev[lo:hi]), C.byref(self.st),
                                     P(self.prob[lo * n:hi * n]), stream), "ls_forward")
-            ls.check(lib.ls_backward(P(d["gbev"][lo:hi]), C.byref(self.gst), P(d["gprob"][lo * n:hi * n]),
-                                     P(self.prob[lo * n:hi * n]), self.code, C.byref(sc), P(self.ws), self.ws.numel(),
-                                     P(self.gfeat[lo * n:hi * n]), P(self.glogits[lo * n:hi * n]), stream),
-                     "ls_backward")
-            e["ev_out"][k].record(comp)
-            e["d2h"].wait_event(e["ev_out"][k])
-            with torch.cuda.stream(e["d2h"]):
+            ev_fout[k].record(comp)
+        with torch.cuda.stream(e["d2h"]):
+            for k, (lo, hi) in enumerate(e["groups"]):
+                e["d2h"].wait_event(ev_fout[k])
                 self.out_host["bev"][lo:hi].copy_(self.bev[lo:hi], non_blocking=True)
                 self.out_host["prob"][lo * n:hi * n].copy_(self.prob[lo * n:hi * n], non_blocking=True)
+        for k, (lo, hi) in enumerate(e["groups"]):
+            sc, ws = e["shapes"][k], e["ws"][k]
+            comp.wait_event(ev_bin[k])
+            ls.check(lib.ls_backward(P(d["gbev"][lo:hi]), C.byref(self.gst), P(d["gprob"][lo * n:hi * n]),
+                                     P(self.prob[lo * n:hi * n]), self.code, C.byref(sc), P(ws), ws.numel(),
+                                     P(self.gfeat[lo * n:hi * n]), P(self.glogits[lo * n:hi * n]), stream),
+                     "ls_backward")
+            ev_bout[k].record(comp)
+        with torch.cuda.stream(e["d2h"]):
+            for k, (lo, hi) in enumerate(e["groups"]):
+                e["d2h"].wait_event(ev_bout[k])
                 self.out_host["gfeat"][lo * n:hi * n].copy_(self.gfeat[lo * n:hi * n], non_blocking=True)
                 self.out_host["glogits"][lo * n:hi * n].copy_(self.glogits[lo * n:hi * n], non_blocking=True)
         comp.wait_stream(e["d2h"])
-        comp.synchronize()
+        comp.wait_stream(e["h2d"])
 
     def e2e_bytes(self):
         h2d = sum(v.numel() * v.element_size() for v in self.host.values())
@@ -427,6 +480,12 @@ def main():
     # end to end: host buffers in/out, same number of steps
     for _ in range(2):
         st.step_e2e()
+    if use_graph:
+        try:
+            st.capture_e2e()
+        except Exception as exc:        # keep the stream-launched pipeline if the capture is refused
+            sys.stderr.write("e2e graph capture failed, using stream launches: %r\n" % (exc,))
+        st.step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(3, min(args.steps, 10))
@@ -473,7 +532,9 @@ def main():
                         "ms_per_step": ms_e2e / e2e_steps,
                         "what": "pinned host buffers -> device -> ls_camera_transform/ls_forward/ls_backward -> "
                                 "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step; "
-                                "%d sample groups pipelined over H2D / compute / D2H streams" % E2E_CHUNKS},
+                                "sample groups %s; forward inputs sent first, BEV returned while the upstream "
+                                "gradients arrive (H2D / compute / D2H streams, one CUDA graph)"
+                                % "+".join(str(v) for v in _e2e_sizes(shape.batch, E2E_CHUNKS))},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

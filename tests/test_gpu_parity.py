@@ -9,6 +9,8 @@ Bars (BASELINE.json north_star): voxel indices / keep mask / sorted ranks BIT-EX
 BEV features and gradients <= 1e-5 relative (fp32) or <= 2e-2 (bf16) against the
 reference run in float64.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -443,3 +445,38 @@ def test_bev_model_drop_in(lib):
     assert relerr(bev_t, bev) < 1e-2
     geom = model.get_geometry(intr.to(DEV), extr.to(DEV))
     assert tuple(geom.shape) == (2, 4, 48, 32, 32, 3)
+
+
+def test_bench_paths_agree(lib):
+    """The three ways bench.py drives the library - kernel-by-kernel launches, the captured
+    CUDA graph, and the host-buffer pipeline (per-group workspaces, forward of every group
+    before the backwards) - produce bit-identical outputs."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    st = bench.Stepper(LiftSplatShape(batch=5, channels=16), torch.float32, DEV)
+    outs = ("bev", "prob", "gfeat", "glogits")
+    st.step()
+    torch.cuda.synchronize()
+    ref = {k: getattr(st, k).clone() for k in outs}
+    assert ref["bev"].abs().sum() > 0 and ref["gfeat"].abs().sum() > 0
+    graph = st.capture()
+    for k in outs:
+        getattr(st, k).zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for k in outs:
+        assert torch.equal(getattr(st, k), ref[k]), k
+    assert st.graph_launches >= 10
+    for k in outs:
+        getattr(st, k).zero_()
+    st.step_e2e(chunks=3)       # ragged groups: 2 + 2 + 1 samples
+    for k in outs:
+        assert torch.equal(st.out_host[k], ref[k].cpu()), k
+    st.capture_e2e(chunks=3)    # the same pipeline as one graph, copies included
+    for k in outs:
+        st.out_host[k].zero_()
+    st.step_e2e(chunks=3)
+    for k in outs:
+        assert torch.equal(st.out_host[k], ref[k].cpu()), k
