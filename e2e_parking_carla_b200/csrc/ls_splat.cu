@@ -26,7 +26,12 @@ __host__ __device__ __forceinline__ LsTileGeom ls_tile_geom(int Cp) {
 // canonical record: x = pixel << 12 | last_of_cell << 11 | valid << 10 | cell_in_tile,  y = prob bits
 #define LS_REC_LAST 0x800
 #define LS_REC_VALID 0x400
+#ifndef LS_QWIN
 #define LS_QWIN 4    // records a quarter-warp keeps in flight
+#endif
+#ifndef LS_SPLAT_MINB
+#define LS_SPLAT_MINB 5   // register budget of the splat: 5 CTAs/SM worth (measured best: 4 and 6 are ~6 us slower)
+#endif
 #define LS_QWARPS (LS_THREADS / 8)
 
 #ifdef LS_PROFILE
@@ -100,7 +105,7 @@ ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
 // =====================================================================================
 template <typename T, bool VEC4, int kCC>
-__global__ void __launch_bounds__(LS_THREADS, 768 / LS_THREADS)
+__global__ void __launch_bounds__(LS_THREADS, LS_SPLAT_MINB)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
                     const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
                     float* __restrict__ bev, LsBevStrides st) {
@@ -131,7 +136,8 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
   const int ql = tid & 7;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
   const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
-  const unsigned row_bytes = (unsigned)(Cp * sizeof(T));
+  unsigned row_bytes = (unsigned)(Cp * sizeof(T));
+  asm volatile("" : "+r"(row_bytes));   // opaque: pixel * row_bytes + base stays one wide multiply-add
   // phase C geometry of this thread (fixed): 4 consecutive y of one x-row; channel quads qg, qg+4, ...
   const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, qg = tid / (LS_TILE / 4);
   const int gx = tx0 + xr, gy = ty0 + 4 * y4;
@@ -179,61 +185,64 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
       // lanes beyond the channel count read valid bytes (lane 0's) and never store
       const char* f0 = reinterpret_cast<const char*>(fbase + cbase + (on0 ? 4 * ql : 0));
       const unsigned f1off = (unsigned)((on1 ? 32 : 0) * sizeof(T));       // second 16-byte piece of the row
-      const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);    // 32-bit shared-window address
+      unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);          // 32-bit shared-window address
+      asm volatile("" : "+r"(tile_s));                                     // computed once, not per flush
       const unsigned row_sbytes = (unsigned)stride * 4u, ql16 = (unsigned)ql << 4, swz_mask = (unsigned)(nqp - 1) << 4;
       if (idx < end) {
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
         const int2* p = rs + idx;
-        int2 r[LS_QWIN];
+        int2 r[LS_QWIN], rn[LS_QWIN];
 #pragma unroll
         for (int u = 0; u < LS_QWIN; ++u) {                     // quarter-warp-uniform 8-byte loads
           r[u] = p[u];
           if (idx + u >= end) r[u] = make_int2(0, 0);           // beyond the piece: pixel 0, not valid
         }
+        // One window: gather the rows of `cur`, fetch the next window's records into `nxt`
+        // while they are in flight, then accumulate.  Two windows per trip with the record
+        // buffers swapped, so no registers are copied between trips.
+#define LS_SPLAT_WINDOW(cur, nxt)                                                                    \
+  {                                                                                                  \
+    float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
+      /* base + pixel * row_bytes as one 32x32+64 multiply-add */                                    \
+      const char* row = f0 + (unsigned long long)((unsigned)cur[u].x >> 12) * row_bytes;             \
+      fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));                                          \
+      fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));                                  \
+    }                                                                                                \
+    idx += LS_QWIN;                                                                                  \
+    p += LS_QWIN;                                                                                    \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) nxt[u] = (idx + u < end) ? p[u] : make_int2(0, 0); \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
+      if (cur[u].x & LS_REC_VALID) {                                                                 \
+        const float wt = __int_as_float(cur[u].y);                                                   \
+        acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);                      \
+        acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);                      \
+        acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);                      \
+        acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);                      \
+      }                                                                                              \
+      if (cur[u].x & LS_REC_LAST) {                                                                  \
+        const unsigned cl = (unsigned)cur[u].x & 255u;                                               \
+        /* row of the cell + this lane's swizzled quads (q and q+8 differ by one address bit) */     \
+        const unsigned rowb = tile_s + cl * row_sbytes, x0 = ql16 ^ ((cl << 1) & swz_mask);          \
+        const unsigned a0 = rowb + x0, a1 = rowb + (x0 ^ 0x80u);                                     \
+        if (on0)                                                                                     \
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(acc0.x), "f"(acc0.y), \
+                       "f"(acc0.z), "f"(acc0.w) : "memory");                                         \
+        if (on1)                                                                                     \
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(acc1.x), "f"(acc1.y), \
+                       "f"(acc1.z), "f"(acc1.w) : "memory");                                         \
+        acc0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
+        acc1 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
+      }                                                                                              \
+    }                                                                                                \
+  }
         for (;;) {
-          float4 fa[LS_QWIN], fb[LS_QWIN];
-#pragma unroll
-          for (int u = 0; u < LS_QWIN; ++u) {
-            // base + pixel * row_bytes as one 32x32+64 multiply-add
-            const char* row = f0 + (unsigned long long)((unsigned)r[u].x >> 12) * row_bytes;
-            fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));
-            fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));
-          }
-          // fetch the next window while these feature rows are in flight
-          idx += LS_QWIN;
-          p += LS_QWIN;
-          const bool more = idx < end;
-          int2 rn[LS_QWIN];
-#pragma unroll
-          for (int u = 0; u < LS_QWIN; ++u) rn[u] = (idx + u < end) ? p[u] : make_int2(0, 0);
-#pragma unroll
-          for (int u = 0; u < LS_QWIN; ++u) {
-            if (r[u].x & LS_REC_VALID) {
-              const float wt = __int_as_float(r[u].y);
-              acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);
-              acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);
-              acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);
-              acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);
-            }
-            if (r[u].x & LS_REC_LAST) {
-              const unsigned cl = (unsigned)r[u].x & 255u;
-              // row of the cell + this lane's swizzled quads (q and q+8 differ by one address bit)
-              const unsigned rowb = tile_s + cl * row_sbytes, x0 = ql16 ^ ((cl << 1) & swz_mask);
-              const unsigned a0 = rowb + x0, a1 = rowb + (x0 ^ 0x80u);
-              if (on0)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(acc0.x), "f"(acc0.y),
-                             "f"(acc0.z), "f"(acc0.w) : "memory");
-              if (on1)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(acc1.x), "f"(acc1.y),
-                             "f"(acc1.z), "f"(acc1.w) : "memory");
-              acc0 = make_float4(0.f, 0.f, 0.f, 0.f);
-              acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (!more) break;
-#pragma unroll
-          for (int u = 0; u < LS_QWIN; ++u) r[u] = rn[u];
+          LS_SPLAT_WINDOW(r, rn);
+          if (idx >= end) break;
+          LS_SPLAT_WINDOW(rn, r);
+          if (idx >= end) break;
         }
+#undef LS_SPLAT_WINDOW
       }
     }
     __syncthreads();
