@@ -66,8 +66,8 @@ int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32
 /* Channel count of the internal NHWC staging rows: C rounded up to a multiple of 4. */
 int32_t ls_padded_channels(int32_t C);
 
-/* Per-sample capacity (in 8-byte records) of ls_splat_fwd's recs_scratch: the re-ordered
- * records are stored with every work item padded to a multiple of 4 records. */
+/* Per-sample capacity (in 8-byte records) of ls_splat_fwd's recs_scratch: the records of
+ * every cell re-ordered by key, in the CSR slots of `recs`, plus a few records of read slack. */
 size_t ls_sorted_records(const LsShape* s);
 
 /* a4 first half - model/bev_model.py:46-47,53:  E^-1 = inverse(extrinsics),

@@ -8,16 +8,18 @@ d = json.load(open("profiles/%s_kernels.json" % tag))
 b = json.load(open("profiles/%s_bench.json" % tag))
 k, L = d["kernels"], d["launch_us"]
 find = lambda p: next(x for x in k if p in x)
-fwd, tr, ga = k[find("splat_fwd")], k[find("bwd_transpose")], k[find("bwd_gather")]
+fwd, tr, ga, ca = k[find("splat_fwd")], k[find("bwd_transpose")], k[find("bwd_gather")], k[find("canon")]
 traffic = {"source": "profiles/%s_kernels.json (ncu --set full --clock-control none over `python bench.py --steps 3 "
-                     "--warmup 3 --no-cpu-baseline`, first launch of each kernel; DRAM read+write bytes per launch)" % tag,
-           "cfg2/fp32": {"splat_fwd": int((fwd["dram_read_MB"] + fwd["dram_write_MB"]) * 1e6),
+                     "--warmup 3 --no-cpu-baseline --no-graph`, first launch of each kernel; DRAM read+write bytes per launch)" % tag,
+           "cfg2/fp32": {"splat_fwd": int((fwd["dram_read_MB"] + fwd["dram_write_MB"] + ca["dram_read_MB"] +
+                                           ca["dram_write_MB"]) * 1e6),
                          "splat_bwd(transpose+gather)": int((tr["dram_read_MB"] + tr["dram_write_MB"] +
                                                              ga["dram_read_MB"] + ga["dram_write_MB"]) * 1e6)}}
 json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 tot = sum(v for kk, v in L.items() if kk.startswith("ls_"))
 out = ["# Round %s profile summary (B200, sm_100a)" % tag[1:], "",
-       "Command profiled: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline` (BASELINE.json configs[1]: fwd+bwd, "
+       "Command profiled: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph` (kernel-by-kernel launches of "
+       "the same step the bench replays as a CUDA graph; BASELINE.json configs[1]: fwd+bwd, "
        "B=16, 4 cams, D=48, C=64, 200x200, fp32).", "",
        "* `%s_launches.csv` - every launch with `gpu__time_duration.sum` (`ncu --metrics gpu__time_duration.sum "
        "--clock-control none`); cold-cache, serialised: compare SHARES, not absolutes.  The first 6 launches of each "
@@ -46,20 +48,33 @@ for kk, v in sorted(L.items(), key=lambda kv: -kv[1]):
 out += ["", "Sum of `ls_*` kernels per step (ncu, serialised, cold caches): %.1f us; un-profiled step: %.1f us (softmax and "
         "layout staging overlap the index/sort chain on side streams)." % (tot, b["ms_per_step"] * 1e3), "",
         "## Reading", "",
-        "* Every kernel is latency/occupancy-bound, none is bandwidth-bound: DRAM utilisation is 1-50 %, L2->SM return "
-        "traffic <= 5.5 TB/s.",
-        "* Ceiling of the access pattern, measured with `tools/gather_bench.cu` on the same GPU: random 256-byte row "
-        "gathers from an L2-resident table with `LDG.128` reach 16-18 TB/s at >= 16 warps/SM.  The same gather with "
-        "`cp.async.bulk` (TMA, one 256 B copy per row, `tools/bulk_bench.cu`) tops out at 8.3 TB/s and 16-byte `cp.async` "
-        "copies are issue-bound (an asynchronous variant of the gather was 1.8x slower) - which is why the splat and the "
-        "gradient gather use plain 128-bit loads with 4-16 rows in flight per lane group rather than TMA.",
-        "* `ls_splat_fwd_kernel`: per-CTA phase accounting (`LS_PROFILE=1` build + `tools/phase_probe.py`): the reduce phase "
-        "is ~50 % of CTA time and runs at the gather ceiling while active (~1800 cycles per 4-record window per "
-        "quarter-warp), canonical-order phase ~30 %, setup + write-out ~20 %; 6 CTAs/SM (35 KB smem, 78 regs).  Splitting "
-        "the canonical-order phase into its own kernel, 16-channel-per-lane streams, larger L1 carve-outs and 16-byte "
-        "`cp.async` staging were all measured slower.",
-        "* `ls_bwd_gather_kernel`: 128 regs (16 gradient rows x 16 B in flight per lane) -> 16 warps/SM; ~0.2 rows/cycle/SM, "
-        "the rate the micro-benchmark gives at that occupancy.",
-        "* `ls_bwd_transpose_kernel`: pure streaming (166 MB read, 103 MB written), 16-channel CTAs; 3.9-4.1 TB/s."]
+        "* In-situ timeline (CUPTI, `tools/timeline.py graph`, file `%s_timeline.txt`): with the step replayed as one CUDA "
+        "graph the GPU is idle ~2 us per step - launch gaps are gone (they were ~45 us per step with stream launches, "
+        "~15 us with programmatic dependent launches); what is left is kernel time." % tag,
+        "* No kernel is DRAM-bound: DRAM utilisation is 1-50 %.  The two gathers (`ls_splat_fwd_kernel`, "
+        "`ls_bwd_gather_kernel`) each move one 256-byte row per kept point from L2 to an SM (2.48 M rows = 636 MB per "
+        "direction) and sustain 6-8 TB/s of L2->SM traffic; `tools/gather_bench.cu` reaches 16-18 TB/s for the bare access "
+        "pattern at >= 16 warps/SM, the guide's LTS cap is ~12 TB/s.  `cp.async.bulk` (one 256 B copy per row, "
+        "`tools/bulk_bench.cu`) tops out at 8.3 TB/s and 16-byte `cp.async` is issue-bound, which is why both gathers use "
+        "plain 128-bit loads with 4-16 rows in flight per lane group rather than TMA.",
+        "* `ls_splat_fwd_kernel` (after the canonical ordering moved into `ls_canon_kernel`): the reduce phase is ~80 % of "
+        "CTA time (`LS_PROFILE=1` build + `tools/phase_probe.py`), seg+zero ~13 %, write-out ~8 %.  Instruction trimming "
+        "(ping-pong record windows, opaque constants: -20 % instructions in the loop) did not move the time; the register "
+        "budget did (5 CTAs/SM worth: -6 us), tile shapes 8x16 / 16x8 were 20-30 us slower, 8-record windows at 4-5 "
+        "CTAs/SM slower.  L1 hit rate is 14 % because six 35 KB tiles leave ~16 KB of L1 per SM; a shared-memory slab of "
+        "the tile's distinct pixel rows would cut L2 fetches ~2.5x but the heaviest tiles see 800-1000 distinct pixels "
+        "(does not fit) - not built.",
+        "* `ls_canon_kernel` is issue-bound (72 % issue-active, 15.7 M warp instructions: sum over cells of k^2 key "
+        "compares) and needs full occupancy: run as a one-wave persistent producer overlapped with the splat through "
+        "per-tile ready flags it was 3-4x slower and the pipeline lost 45-80 us - reverted.",
+        "* `ls_bwd_transpose_kernel`: streaming (166 MB read, 103 MB written); 32-channel CTAs with the gradient loads "
+        "issued before the tile offsets arrive: 72 -> 63 us in situ (4.3 TB/s).  L2 eviction-policy hints "
+        "(`createpolicy` + `ld/st.L2::cache_hint`) cost +20 us (the per-thread `createpolicy` alone) and evict-last rows "
+        "slowed the forward gather - reverted.",
+        "* `ls_bwd_gather_kernel`: 128 regs (16 gradient rows x 16 B in flight per lane) -> 16 warps/SM, 318 warp "
+        "instructions per 32 records, L1 hit 42 % (a CTA is one feature-map column, its rays share cells).",
+        "* `ls_index_kernel`: ~150 instructions per point (three IEEE divisions with their slow-path checks, unfused "
+        "multiply/add chains that reproduce torch's rounding), 51 % issue-active; `ls_place_kernel`: latency-bound chain "
+        "(three coalesced streams -> seg_start gather -> scattered 8-byte stores)."]
 open("profiles/%s_summary.md" % tag, "w").write("\n".join(out) + "\n")
 print("\n".join(out[9:26]))
