@@ -10,13 +10,15 @@
 
 // ---- BEV tiling ---------------------------------------------------------------------
 // The grid is cut into LS_TX x LS_TY voxel tiles; cells are numbered tile-major
-// (cell = tile*LS_TILE + lx*LS_TY + ly).  Tiles are small on purpose: a tile is one CTA of
-// the splat, and many small CTAs in different phases hide each other's latencies.
+// (cell = tile*LS_TILE + lx*LS_TY + ly).  A tile is one CTA of the splat and of the gradient
+// transposer.  Tiles are small on purpose (many CTAs in different phases hide each other's
+// latencies) and long along y: a tile row is a contiguous run of the [B,C,X,Y] tensors, and
+// 512-byte runs (1 x 128) measured 3 % faster per step than 128-byte runs (4 x 32).
 #ifndef LS_TX
-#define LS_TX 4                      // x-rows per tile (LS_TX * LS_TY must be 128 or 256)
+#define LS_TX 1                      // x-rows per tile (LS_TX * LS_TY must be 128 or 256)
 #endif
 #ifndef LS_TY
-#define LS_TY 32                     // y-columns per tile: 32 -> whole 128-byte lines of the BEV tensor
+#define LS_TY 128                    // y-columns per tile
 #endif
 #define LS_TILE (LS_TX * LS_TY)      // cells per tile (cell-in-tile fits 8 bits)
 #define LS_CCHUNK 64                 // channels per pass
