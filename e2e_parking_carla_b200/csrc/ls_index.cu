@@ -361,8 +361,11 @@ int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* se
 // CTA = (sample, camera, 32 consecutive pixels) x all depth bins; loads are coalesced over
 // pixels, the pixel-major rows are transposed through shared memory.
 // =====================================================================================
+#ifndef LS_PLACE_GROUPS
+#define LS_PLACE_GROUPS 16    // depth groups (warps) per CTA; a thread handles ceil(D / groups) bins of one pixel
+#endif
 template <typename T, int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * LS_PLACE_GROUPS)
 ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, const T* __restrict__ prob, LsDims dm,
                 LsGrid grid, const int* __restrict__ seg_start, int2* __restrict__ recs, int2* __restrict__ pix_recs) {
   ls_pdl_trigger();
@@ -380,7 +383,7 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
     int c[K], tk[K], wb[K], sg[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const int d = dg + 8 * k;
+      const int d = dg + LS_PLACE_GROUPS * k;
       c[k] = -1; tk[k] = 0; wb[k] = 0;
       if (d < dm.D) {
         const size_t idx = (size_t)b * dm.Npts + (size_t)(n * dm.D + d) * dm.HW + rc;
@@ -393,7 +396,7 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
     for (int k = 0; k < K; ++k) sg[k] = (c[k] >= 0) ? __ldg(seg + c[k]) : 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const int d = dg + 8 * k;
+      const int d = dg + LS_PLACE_GROUPS * k;
       if (d < dm.D) {
         if (c[k] >= 0) {
           const int key = ((c[k] & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
@@ -408,17 +411,19 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
   __syncthreads();
   const int valid = min(32, dm.HW - rc0);
   int2* dst = pix_recs + ((size_t)(b * dm.N + n) * dm.HW + rc0) * dm.D;
-  for (int r = dg; r < valid; r += 8)
+  for (int r = dg; r < valid; r += LS_PLACE_GROUPS)
     for (int d = lane; d < dm.D; d += 32) dst[(size_t)r * dm.D + d] = stage[r * Dp + d];
 }
 
 template <typename T>
 static int ls_place_dispatch(const int* cell, const int* within, const T* prob, const LsDims& dm, const LsGrid& g,
                              const int* seg_start, int2* recs, int2* pix_recs, dim3 grid, size_t smem, cudaStream_t s) {
-  const int k = (dm.D + 7) / 8;
+  const int k = (dm.D + LS_PLACE_GROUPS - 1) / LS_PLACE_GROUPS;
 #define LS_PL(KK) \
-  LS_LAUNCH((ls_place_kernel<T, KK>), grid, dim3(256), smem, s, cell, within, prob, dm, g, seg_start, recs, pix_recs)
-  if (k <= 2) LS_PL(2);
+  LS_LAUNCH((ls_place_kernel<T, KK>), grid, dim3(32 * LS_PLACE_GROUPS), smem, s, cell, within, prob, dm, g, seg_start, recs, pix_recs)
+  if (k <= 1) LS_PL(1);
+  else if (k <= 2) LS_PL(2);
+  else if (k <= 3) LS_PL(3);
   else if (k <= 4) LS_PL(4);
   else if (k <= 6) LS_PL(6);
   else if (k <= 8) LS_PL(8);

@@ -60,15 +60,16 @@ out += ["", "Sum of `ls_*` kernels per step (ncu, serialised, cold caches): %.1f
         "* `ls_splat_fwd_kernel` (after the canonical ordering moved into `ls_canon_kernel`): the reduce phase is ~80 % of "
         "CTA time (`LS_PROFILE=1` build + `tools/phase_probe.py`), seg+zero ~13 %, write-out ~8 %.  Instruction trimming "
         "(ping-pong record windows, opaque constants: -20 % instructions in the loop) did not move the time; the register "
-        "budget did (5 CTAs/SM worth: -6 us), tile shapes 8x16 / 16x8 were 20-30 us slower, 8-record windows at 4-5 "
-        "CTAs/SM slower.  L1 hit rate is 14 % because six 35 KB tiles leave ~16 KB of L1 per SM; a shared-memory slab of "
+        "budget did (5 CTAs/SM worth: -6 us) and so did the tile shape (4x32 -> 1x128 cells, i.e. 512-byte runs of the "
+        "BEV tensors: -11 us per step over splat and transposer; 8x16 / 16x8 were 20-30 us slower, 256-cell tiles "
+        "60-70 us slower); 8-record windows at 4-5 CTAs/SM slower.  L1 hit rate is 14 % because six 35 KB tiles leave ~16 KB of L1 per SM; a shared-memory slab of "
         "the tile's distinct pixel rows would cut L2 fetches ~2.5x but the heaviest tiles see 800-1000 distinct pixels "
         "(does not fit) - not built.",
         "* `ls_canon_kernel` is issue-bound (72 % issue-active, 15.7 M warp instructions: sum over cells of k^2 key "
         "compares) and needs full occupancy: run as a one-wave persistent producer overlapped with the splat through "
         "per-tile ready flags it was 3-4x slower and the pipeline lost 45-80 us - reverted.",
         "* `ls_bwd_transpose_kernel`: streaming (166 MB read, 103 MB written); 32-channel CTAs with the gradient loads "
-        "issued before the tile offsets arrive: 72 -> 63 us in situ (4.3 TB/s).  L2 eviction-policy hints "
+        "issued before the tile offsets arrive, 512-byte runs: 72 -> 54 us in situ (5.0 TB/s of DRAM traffic, 78 % of peak).  L2 eviction-policy hints "
         "(`createpolicy` + `ld/st.L2::cache_hint`) cost +20 us (the per-thread `createpolicy` alone) and evict-last rows "
         "slowed the forward gather - reverted.",
         "* `ls_bwd_gather_kernel`: 128 regs (16 gradient rows x 16 B in flight per lane) -> 16 warps/SM, 318 warp "
