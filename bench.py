@@ -235,7 +235,7 @@ class Stepper:
         torch.cuda.synchronize()
         l0 = self.lib.ls_launch_count()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self.step()
         self.graph_launches = int(self.lib.ls_launch_count() - l0)
         self.graph = graph
@@ -263,7 +263,7 @@ class Stepper:
         one CUDA graph; the pinned host buffers are the graph's fixed inputs and outputs."""
         self.step_e2e(chunks)                      # allocates the per-group state outside capture
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self._e2e_enqueue(chunks)
         self._e2e_graph = (chunks, graph)
         return graph

@@ -23,7 +23,12 @@
 #define LS_TILE (LS_TX * LS_TY)      // cells per tile (cell-in-tile fits 8 bits)
 #define LS_CCHUNK 64                 // channels per pass
 #define LS_THREADS LS_TILE           // tile kernels: one thread per cell of the tile
+#ifndef LS_GATHER_THREADS
 #define LS_GATHER_THREADS 256
+#endif
+#ifndef LS_GATHER_MINB
+#define LS_GATHER_MINB 2
+#endif
 #define LS_HALFWARPS (LS_GATHER_THREADS / 16)
 #define LS_SEG_PAD 4                 // seg_start row stride = Vc + LS_SEG_PAD (16 B aligned rows)
 

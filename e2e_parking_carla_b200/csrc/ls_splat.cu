@@ -483,7 +483,7 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
 // kFullD: D is a multiple of 16 (no predicates on the index loads).  pix_recs.x holds the BYTE
 // offset of the cell's row inside the sample's cell-major gradient block.
 template <typename T, int NCH, bool kFullD>
-__global__ void __launch_bounds__(LS_GATHER_THREADS, 2)
+__global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GATHER_MINB)
 ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
                      LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
   ls_pdl_trigger();
