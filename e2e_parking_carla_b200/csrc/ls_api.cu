@@ -296,8 +296,7 @@ int ls_forward(const void* feat, const void* logits, int dtype, const float* M, 
     LS_CUDA(cudaEventRecord(a->j2, a->s2));
   }
   // caller's stream: index -> scan, then (after softmax) placement, then (after staging) the splat
-  LS_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)dm.B * g.Vc * sizeof(int), stream));
-  ls_note_launch();
+  if ((rc = ls_launch_zero_counts(w.counts, dm, g, stream))) return rc;
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
   if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, w.tile_tot, stream))) return rc;
   if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j1, 0));

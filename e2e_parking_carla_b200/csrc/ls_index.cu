@@ -170,6 +170,22 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   }
 }
 
+// zero the per-cell histogram (B * Vc ints, a multiple of 128): one 16-byte store per thread and trip
+__global__ void __launch_bounds__(256)
+ls_zero_counts_kernel(int4* __restrict__ p, int n16) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int4 z = make_int4(0, 0, 0, 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) p[i] = z;
+}
+
+int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaStream_t s) {
+  const int n16 = (int)(((size_t)dm.B * g.Vc) / 4);      // Vc is a multiple of LS_TILE
+  const int blocks = (n16 + 1023) / 1024;
+  LS_LAUNCH(ls_zero_counts_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, s, reinterpret_cast<int4*>(counts), n16);
+  return LS_OK;
+}
+
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
   dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);

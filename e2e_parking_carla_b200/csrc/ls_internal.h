@@ -4,6 +4,7 @@
 
 // ls_index.cu
 int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s);
+int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaStream_t s);
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s);
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,

@@ -67,7 +67,8 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 // the atomics.  Flat: one thread per record, one CTA per tile (heaviest first), the compare
 // loop runs over L1-resident keys.  Replaces the (unstable) argsort of model/bev_model.py:96.
 // =====================================================================================
-__global__ void __launch_bounds__(256)
+#define LS_CANON_THREADS 256
+__global__ void __launch_bounds__(LS_CANON_THREADS)
 ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
                 LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
   ls_pdl_trigger();
@@ -76,12 +77,12 @@ ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start
   const int b = blockIdx.x % dm.B;
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
-  for (int i = threadIdx.x; i <= LS_TILE; i += blockDim.x) seg[i] = segg[i];
+  for (int i = threadIdx.x; i <= LS_TILE; i += LS_CANON_THREADS) seg[i] = segg[i];
   __syncthreads();
   const int s0 = seg[0], s1 = seg[LS_TILE];
   const int2* rin = recs + (size_t)b * dm.Npts;
   int2* out = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
-  for (int i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+  for (int i = s0 + threadIdx.x; i < s1; i += LS_CANON_THREADS) {
     const int2 r = rin[i];
     const int cl = (unsigned)r.x >> 24;
     const int a = seg[cl], e = seg[cl + 1];
@@ -337,7 +338,7 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   }
   const size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
-  LS_LAUNCH(ls_canon_kernel, grid, dim3(256), 0, s, recs, seg_start, tile_order, dm, g, recs_sorted);
+  LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, recs, seg_start, tile_order, dm, g, recs_sorted);
   const bool v4 = ls_bev_vec4(bev, st, g);
   const dim3 block(LS_THREADS);
   const int2* rs = recs_sorted;
