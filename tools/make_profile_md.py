@@ -56,7 +56,12 @@ out += ["", "Sum of `ls_*` kernels per step (ncu, serialised, cold caches): %.1f
         "direction) and sustain 6-8 TB/s of L2->SM traffic; `tools/gather_bench.cu` reaches 16-18 TB/s for the bare access "
         "pattern at >= 16 warps/SM, the guide's LTS cap is ~12 TB/s.  `cp.async.bulk` (one 256 B copy per row, "
         "`tools/bulk_bench.cu`) tops out at 8.3 TB/s and 16-byte `cp.async` is issue-bound, which is why both gathers use "
-        "plain 128-bit loads with 4-16 rows in flight per lane group rather than TMA.",
+        "plain 128-bit loads with 4-16 rows in flight per lane group rather than TMA.  The two paths are not additive "
+        "either (`tools/mix_bench.cu`: 17.0 TB/s LDG-only at 20 warps/SM, 15.1 / 12.5 / 6.8 TB/s with 4 / 8 / 16 extra bulk "
+        "rows per window).  The gap between the bare pattern (17 TB/s at the splat's nominal occupancy) and the kernels "
+        "(6-8 TB/s) is structure: a tile CTA gathers during ~80 % of its life, its 16 quarter-warp pieces are 78 % "
+        "balanced (cells cannot be split without giving up the fixed summation order), and the last window of a piece "
+        "is partial.",
         "* `ls_splat_fwd_kernel` (after the canonical ordering moved into `ls_canon_kernel`): the reduce phase is ~80 % of "
         "CTA time (`LS_PROFILE=1` build + `tools/phase_probe.py`), seg+zero ~13 %, write-out ~8 %.  Instruction trimming "
         "(ping-pong record windows, opaque constants: -20 % instructions in the loop) did not move the time; the register "
