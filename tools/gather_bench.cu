@@ -32,18 +32,20 @@ __global__ void gather(const float4* __restrict__ table, const int* __restrict__
 }
 
 template <int WIN, bool NOALLOC>
-void run(const float4* table, const int* idx, float4* out, int blocks, int threads, int total_recs, const char* tag) {
+void run(const float4* table, const int* idx, float4* out, int blocks, int threads, int total_recs, const char* tag,
+         size_t smem = 0) {
+  cudaFuncSetAttribute(gather<WIN, NOALLOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int streams = blocks * threads / 8;
   const int nps = (total_recs / streams) / WIN * WIN;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int w = 0; w < 2; ++w) gather<WIN, NOALLOC><<<blocks, threads>>>(table, idx, nps, out);
+  for (int w = 0; w < 2; ++w) gather<WIN, NOALLOC><<<blocks, threads, smem>>>(table, idx, nps, out);
   cudaEventRecord(e0);
-  for (int w = 0; w < 5; ++w) gather<WIN, NOALLOC><<<blocks, threads>>>(table, idx, nps, out);
+  for (int w = 0; w < 5; ++w) gather<WIN, NOALLOC><<<blocks, threads, smem>>>(table, idx, nps, out);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
   const double bytes = (double)streams * nps * 256;
-  printf("%-28s blocks %5d x %3d thr (%.1f warps/SM) win %d: %7.1f us  %6.2f TB/s\n", tag, blocks, threads,
-         blocks * threads / 32.0 / 148, WIN, ms * 1e3, bytes / ms / 1e9);
+  printf("%-28s blocks %5d x %3d thr (%.1f warps/SM) win %d smem %3zu KB/CTA: %7.1f us  %6.2f TB/s\n", tag, blocks, threads,
+         blocks * threads / 32.0 / 148, WIN, smem / 1024, ms * 1e3, bytes / ms / 1e9);
 }
 
 int main() {
@@ -60,6 +62,12 @@ int main() {
     run<4, false>(table, idx, out, blocks, threads, total, "ldg win4");
     run<8, false>(table, idx, out, blocks, threads, total, "ldg win8");
     run<4, true>(table, idx, out, blocks, threads, total, "no_allocate win4");
+  }
+  // the splat's residency: 5 CTAs of 128 threads per SM, with and without its 35 KB of shared memory per CTA
+  // (the shared-memory carve-out shrinks L1, which also holds the lines of the loads in flight)
+  for (size_t kb : {0, 16, 35, 44}) {
+    run<4, false>(table, idx, out, 148 * 5, 128, total, "ldg win4, 5 CTAs/SM", kb * 1024);
+    run<4, true>(table, idx, out, 148 * 5, 128, total, "no_allocate win4, 5 CTAs/SM", kb * 1024);
   }
   return 0;
 }
