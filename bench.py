@@ -459,7 +459,7 @@ def main():
         for _ in range(args.warmup):
             graph.replay()
         barrier()
-    config["launch"] = ("one CUDA graph replay per step (3 ABI calls captured once: %d kernels/memsets, side streams "
+    config["launch"] = ("one CUDA graph replay per step (3 ABI calls captured once: %d kernels, side streams "
                         "included)" % st.graph_launches) if use_graph else "stream launches, 3 ABI calls per step"
     sampler = ClockSampler(local)
     if rank == 0:

@@ -59,8 +59,9 @@ const char* ls_version(void);
 const char* ls_strerror(int status);
 const char* ls_last_cuda_error(void);
 
-/* Internal BEV tiling: the grid is cut in 16 x 16-voxel tiles; cells are numbered
- * tile-major.  cells_padded = tiles * 256 (>= X*Y); seg_stride = row stride of seg_start. */
+/* Internal BEV tiling: the grid is cut into tiles of 128 consecutive cells of one x-row
+ * (a build-time choice); cells are numbered tile-major.  cells_padded = tiles * cells per
+ * tile (>= X*Y); seg_stride = row stride of seg_start. */
 int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32_t* seg_stride);
 
 /* Channel count of the internal NHWC staging rows: C rounded up to a multiple of 4. */
@@ -185,7 +186,7 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
  * call; LS_ERR_UNSUPPORTED unless the library was built with -DLS_PROFILE. */
 int ls_debug_phase_cycles(uint64_t* out8);
 
-/* Number of kernel launches (and memsets) issued by this library since load; bench.py
+/* Number of kernel launches (and copies) issued by this library since load; bench.py
  * reads it around the timed region to report gpu_launches. */
 int64_t ls_launch_count(void);
 
