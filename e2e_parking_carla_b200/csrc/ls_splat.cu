@@ -366,6 +366,9 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 // K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
 // =====================================================================================
+#ifndef LS_GATHER_REVERSE
+#define LS_GATHER_REVERSE 1
+#endif
 #ifndef LS_TCHUNK
 #define LS_TCHUNK 32   // channels per CTA of the gradient transposer (16, 32 or 64): 8 x 16 B in flight per thread
 #endif
@@ -489,7 +492,9 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
                      LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
   ls_pdl_trigger();
   ls_pdl_wait();
-  const int col = blockIdx.x, bn = blockIdx.y;
+  // images in reverse order: the transposer wrote the last samples' rows last, they are the
+  // ones still in L2 when this kernel starts
+  const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const unsigned hmask = ls_half_mask();
