@@ -480,3 +480,27 @@ def test_bench_paths_agree(lib):
     st.step_e2e(chunks=3)
     for k in outs:
         assert torch.equal(st.out_host[k], ref[k].cpu()), k
+
+
+def test_plain_stream_order_matches(lib):
+    """LS_NO_PDL=1 (no programmatic dependent launches) and LS_NO_SIDE_STREAMS=1 (everything on
+    the caller's stream) are read once per process, so they are exercised in a child process:
+    the step must give the same bits as the default configuration."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch, hashlib; sys.path.insert(0, %r); import bench\n"
+        "from e2e_parking_carla_b200.synthetic import LiftSplatShape\n"
+        "st = bench.Stepper(LiftSplatShape(batch=3, channels=16), torch.float32, torch.device('cuda:0'))\n"
+        "st.step(); torch.cuda.synchronize()\n"
+        "h = hashlib.sha256()\n"
+        "for k in ('bev', 'prob', 'gfeat', 'glogits'): h.update(getattr(st, k).cpu().numpy().tobytes())\n"
+        "print('DIGEST', h.hexdigest())\n" % root)
+    digests = []
+    for extra in ({}, {"LS_NO_PDL": "1", "LS_NO_SIDE_STREAMS": "1"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
