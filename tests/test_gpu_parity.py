@@ -338,7 +338,7 @@ def test_nan_extrinsics_drop_points(lib):
 
 
 def test_odd_sizes(lib):
-    """Grid that is not a multiple of the 8x32 tile, non-square feature map, D not a
+    """Grid that is not a multiple of the tile (and whose rows are not 16-byte multiples), non-square feature map, D not a
     multiple of anything, C=6."""
     from oracle import lift_splat_oracle as lo
     shape = LiftSplatShape(batch=2, cams=3, channels=6, bev_x_bound=[-7.0, 6.0, 0.2], bev_y_bound=[-5.0, 9.0, 0.2],
@@ -504,3 +504,30 @@ def test_plain_stream_order_matches(lib):
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
     assert digests[0] == digests[1]
+
+
+def test_many_tiles_single_cta_scan(lib):
+    """A long, narrow grid with more than 2048 tiles takes the single-CTA scan (identity tile
+    order) instead of the two-kernel parallel scan; everything downstream must not care."""
+    from oracle import lift_splat_oracle as lo
+    shape = LiftSplatShape(batch=1, cams=2, channels=8, bev_x_bound=[-105.0, 105.0, 0.1], bev_y_bound=[-4.0, 4.0, 0.1],
+                           d_bound=[0.5, 60.5, 2.5], final_dim=[128, 128], bev_down_sample=8)
+    ls = _ls()
+    tiles = ls.grid_cells(_ls_shape(shape))[0]
+    assert tiles > 2048
+    intr, extr = make_rig(1, 2, jitter=True, seed=23)
+    feat, logits = make_encoder_outputs(shape, seed=12)
+    gb, gp = make_upstream_grads(shape, seed=12)
+    res, start, dim = grid_of(shape)
+    gb = gb[:, :, :int(dim[0]), :int(dim[1])].contiguous()
+    M, t = lo.camera_transform(intr.numpy(), extr.numpy())
+    _, _, rank = lo.voxel_index(lo.geometry(M, t, frustum_of(shape)), start, res, dim)
+    assert (rank >= 0).sum() > 1000
+    bev_o, prob_o = lo.splat_forward(feat.numpy(), logits.numpy(), rank, dim, shape.cams)
+    gf_o, gl_o = lo.splat_backward(feat.numpy(), logits.numpy(), rank, dim, shape.cams, gb.numpy(), gp.numpy())
+    r = ls.index(_dev(M), _dev(t), _dev(frustum_of(shape)), _ls_shape(shape)).cpu().numpy()
+    assert np.array_equal(r, rank.astype(np.int32))
+    out = _run(shape, feat, logits, M, t, gb, gp)
+    assert relerr(out["bev"], bev_o) <= FP32_TOL
+    assert relerr(out["grad_feat"], gf_o) <= FP32_TOL
+    assert relerr(out["grad_logits"], gl_o) <= FP32_TOL
