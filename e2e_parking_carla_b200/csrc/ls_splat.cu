@@ -96,11 +96,13 @@ ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start
 
 // =====================================================================================
 // K3b: forward splat.  One CTA per (sample, LS_TX x LS_TY voxel tile), heaviest tiles first:
-//  B  reduce: the tile's run of canonical records is cut at cell boundaries into LS_QWARPS
-//     nearly equal pieces, one per quarter-warp.  A lane owns 8 channels (two 16-byte pieces of
-//     the 256-byte feature row); LS_QWIN rows are in flight while the next records are
-//     prefetched; prob*feat accumulates in registers and is dropped into the shared-memory
-//     tile [cell][channel] (swizzled, conflict-free) on a last-of-cell record.
+//  B  reduce: the tile's run of canonical records is cut into LS_QWARPS pieces of equal record
+//     count, one per quarter-warp.  A lane owns 8 channels (two 16-byte pieces of the 256-byte
+//     feature row); LS_QWIN rows are in flight while the next records are prefetched; prob*feat
+//     accumulates in registers and is dropped into the shared-memory tile [cell][channel]
+//     (swizzled, conflict-free) on a last-of-cell record.  A cell cut by a piece boundary is
+//     stored by the piece holding its last record; the open sums of the pieces before it are
+//     added after the barrier in piece order (fixed association).
 //  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
 //     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
@@ -118,6 +120,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
   const int ccmax = kCC ? kCC : tgr.cc;
   float* tile = smem;                                            // [LS_TILE][stride]
   int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1] CSR offsets of the tile
+  int* part_cell = seg + LS_TILE + 1;                            // [LS_QWARPS] cell of each piece's open partial sum (-1: none)
 
   // heaviest tiles first, all samples interleaved: blockIdx.x = order_index * B + b
   const int b = blockIdx.x % dm.B;
@@ -163,25 +166,15 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
 #endif
     // ---- phase B: lane = channels [4ql,4ql+4) and [32+4ql,..) of its quarter-warp's records ----
     if (!tile_empty) {
-      // this quarter-warp's cells [c0, c1): boundary q = first cell that starts at or after
-      // record s0 + q*n/LS_QWARPS (binary search in the tile's offsets)
+      // Equal pieces: quarter-warp q reduces records [s0 + q*n/16, s0 + (q+1)*n/16) of the tile's
+      // canonical run, cut wherever that falls.  A cell that straddles a cut is finished by the
+      // piece that holds its last record (plain store); the pieces before it keep their partial
+      // sums in registers and add them after the barrier, in piece order - a fixed association,
+      // so the result is still independent of the atomics and of the schedule.
       const int qw = tid >> 3, n = s1 - s0;
-      int c0, c1;
-      {
-        const int t0 = s0 + (int)(((long long)qw * n) / LS_QWARPS);
-        const int t1 = s0 + (int)(((long long)(qw + 1) * n) / LS_QWARPS);
-        int lo0 = 0, hi0 = LS_TILE, lo1 = 0, hi1 = LS_TILE;
-#pragma unroll
-        for (int step = 0; step < 8; ++step) {          // LS_TILE <= 256
-          const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
-          if (lo0 < hi0) { if (seg[m0] < t0) lo0 = m0 + 1; else hi0 = m0; }
-          if (lo1 < hi1) { if (seg[m1] < t1) lo1 = m1 + 1; else hi1 = m1; }
-        }
-        c0 = lo0;
-        c1 = (qw == LS_QWARPS - 1) ? LS_TILE : lo1;
-      }
-      int idx = seg[c0];
-      const int end = seg[c1];
+      int idx = s0 + (int)(((long long)qw * n) / LS_QWARPS);
+      const int end = s0 + (int)(((long long)(qw + 1) * n) / LS_QWARPS);
+      const int idx_first = idx;
       const bool on0 = 4 * ql < cc, on1 = 32 + 4 * ql < cc;
       // lanes beyond the channel count read valid bytes (lane 0's) and never store
       const char* f0 = reinterpret_cast<const char*>(fbase + cbase + (on0 ? 4 * ql : 0));
@@ -189,8 +182,11 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
       unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);          // 32-bit shared-window address
       asm volatile("" : "+r"(tile_s));                                     // computed once, not per flush
       const unsigned row_sbytes = (unsigned)stride * 4u, ql16 = (unsigned)ql << 4, swz_mask = (unsigned)(nqp - 1) << 4;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int pc = -1;                                           // cell of this piece's open partial sum
       if (idx < end) {
-        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int xl = __ldg(&rs[end - 1].x);
+        if (!(xl & LS_REC_LAST)) pc = xl & 255;
         const int2* p = rs + idx;
         int2 r[LS_QWIN], rn[LS_QWIN];
 #pragma unroll
@@ -245,8 +241,48 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
         }
 #undef LS_SPLAT_WINDOW
       }
+      (void)idx_first;
+      if (ql == 0) part_cell[qw] = pc;
+      __syncthreads();
+      // open partial sums: round r adds the partial of every piece that has exactly r open
+      // pieces of the same cell directly before it (a cell longer than two pieces), so no two
+      // quarter-warps touch the same row in one round
+      int depth = 0, maxd = -1;
+      {
+        int run = 0, prev = -1;
+#pragma unroll
+        for (int j = 0; j < LS_QWARPS; ++j) {
+          const int c = part_cell[j];
+          if (c >= 0) {                 // pieces without an open sum (empty, or ending on a cell's last record) are transparent
+            run = (c == prev) ? run + 1 : 0;
+            maxd = max(maxd, run);
+            prev = c;
+          }
+          if (j == qw) depth = run;
+        }
+      }
+      for (int rd = 0; rd <= maxd; ++rd) {
+        if (pc >= 0 && depth == rd) {
+          const unsigned cl = (unsigned)pc;
+          const unsigned rowb = tile_s + cl * row_sbytes, x0 = ql16 ^ ((cl << 1) & swz_mask);
+          const unsigned a0 = rowb + x0, a1 = rowb + (x0 ^ 0x80u);
+          float4 t0, t1;
+          if (on0) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0.x), "=f"(t0.y), "=f"(t0.z), "=f"(t0.w) : "r"(a0) : "memory");
+            t0.x += acc0.x; t0.y += acc0.y; t0.z += acc0.z; t0.w += acc0.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(t0.x), "f"(t0.y), "f"(t0.z), "f"(t0.w) : "memory");
+          }
+          if (on1) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t1.x), "=f"(t1.y), "=f"(t1.z), "=f"(t1.w) : "r"(a1) : "memory");
+            t1.x += acc1.x; t1.y += acc1.y; t1.z += acc1.z; t1.w += acc1.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(t1.x), "f"(t1.y), "f"(t1.z), "f"(t1.w) : "memory");
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      __syncthreads();
     }
-    __syncthreads();
     LS_TICK(3);
     // ---- phase C --------------------------------------------------------------------
     if (VEC4) {
@@ -313,7 +349,7 @@ size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g) { (void)g; 
 
 static size_t ls_tile_smem_bytes(const LsDims& dm) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 4) * sizeof(int);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 4 + LS_QWARPS) * sizeof(int);
 }
 static size_t ls_tile_smem_max() {
   LsDims d;
