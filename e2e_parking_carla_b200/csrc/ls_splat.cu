@@ -119,8 +119,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
   const int nqp = kCC ? kCC / 4 : tgr.nqp;
   const int ccmax = kCC ? kCC : tgr.cc;
   float* tile = smem;                                            // [LS_TILE][stride]
-  int* seg = reinterpret_cast<int*>(smem + LS_TILE * stride);    // [LS_TILE + 1] CSR offsets of the tile
-  int* part_cell = seg + LS_TILE + 1;                            // [LS_QWARPS] cell of each piece's open partial sum (-1: none)
+  int* part_cell = reinterpret_cast<int*>(smem + LS_TILE * stride);   // [LS_QWARPS] cell of each piece's open partial sum (-1: none)
 
   // heaviest tiles first, all samples interleaved: blockIdx.x = order_index * B + b
   const int b = blockIdx.x % dm.B;
@@ -135,7 +134,8 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
   const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
-  for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
+  // only the ends of the tile's record run are needed (uniform loads, one line each)
+  const int s0 = __ldg(segg), s1 = __ldg(segg + LS_TILE);
 
   const int ql = tid & 7;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * Cp;
@@ -159,7 +159,6 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
     }
     __syncthreads();
     LS_TICK(0);
-    const int s0 = seg[0], s1 = seg[LS_TILE];
     const bool tile_empty = (s0 == s1);
 #ifdef LS_PROFILE
     if (threadIdx.x == 0 && blockIdx.x < 8192) ls_dbg_cta[blockIdx.x][0] = s1 - s0;
@@ -349,7 +348,7 @@ size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g) { (void)g; 
 
 static size_t ls_tile_smem_bytes(const LsDims& dm) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp);
-  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 4 + LS_QWARPS) * sizeof(int);
+  return (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
 }
 static size_t ls_tile_smem_max() {
   LsDims d;
