@@ -401,6 +401,15 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 // K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
 // =====================================================================================
+#ifndef LS_GOCC_ROWS
+#define LS_GOCC_ROWS 8    // rows gathered at a time by a half-warp of the register-lean gather
+#endif
+#ifndef LS_GOCC_MINB
+#define LS_GOCC_MINB 3    // its CTAs per SM
+#endif
+#ifndef LS_GATHER_OCC
+#define LS_GATHER_OCC 1   // register-lean gradient gather (24 warps/SM) for Cp <= 64, D % 16 == 0
+#endif
 #ifndef LS_GATHER_REVERSE
 #define LS_GATHER_REVERSE 1
 #endif
@@ -619,12 +628,105 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
   }
 }
 
+// Higher-occupancy variant for the common shape (Cp <= 64, D a multiple of 16).  The random
+// 256-byte row gather from the 100 MB cell-major gradient scales with the number of resident
+// warps, not with the rows in flight per warp (tools/gather_bench.cu 400000: 7.8 / 11.0 / 13.7
+// TB/s at 16 / 24 / 32 warps per SM), so this version trades registers for warps: the sixteen
+// records of a depth window are loaded one per lane (a single coalesced 128-byte load per
+// half-warp, prefetched a window ahead, broadcast with 16-wide shuffles) and the rows are
+// gathered eight at a time - under 86 registers, three CTAs (24 warps) per SM.
+template <typename T>
+__global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GOCC_MINB)
+ls_bwd_gather_occ_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
+                         LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  // images in reverse order: the transposer wrote the last samples' rows last, they are the
+  // ones still in L2 when this kernel starts
+  const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int b = bn / dm.N;
+  const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const unsigned hmask = ls_half_mask();
+  const bool on = 4 * hl < dm.Cp;
+  // lanes beyond the channel count read valid bytes (lane 0's) and never store
+  const char* gTb = reinterpret_cast<const char*>(gT + (size_t)b * (grid.Vc + 1) * dm.Cp + (on ? 4 * hl : 0));
+  const int wpp = dm.D >> 4;                                                  // windows per pixel
+  for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
+    const size_t pix = (size_t)bn * dm.HW + (size_t)row * dm.fw + col;
+    const float4 f = on ? ls_load4<T>(featT + pix * dm.Cp + 4 * hl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gf = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int2* pr = pix_recs + pix * dm.D + hl;
+    int2 rec = __ldg(pr);
+    for (int w = 0; w < wpp; ++w) {
+      int2 recn = rec;
+      if (w + 1 < wpp) recn = __ldg(pr + 16 * (w + 1));
+      float dot[16];
+#pragma unroll
+      for (int h = 0; h < 16 / LS_GOCC_ROWS; ++h) {
+        float4 g[LS_GOCC_ROWS];
+#pragma unroll
+        for (int u = 0; u < LS_GOCC_ROWS; ++u) {
+          const unsigned off = (unsigned)__shfl_sync(hmask, rec.x, LS_GOCC_ROWS * h + u, 16);
+          g[u] = __ldg(reinterpret_cast<const float4*>(gTb + off));
+        }
+#pragma unroll
+        for (int u = 0; u < LS_GOCC_ROWS; ++u) {
+          const float wgt = __int_as_float(__shfl_sync(hmask, rec.y, LS_GOCC_ROWS * h + u, 16));
+          float dv = f.x * g[u].x;
+          dv = fmaf(f.y, g[u].y, dv);
+          dv = fmaf(f.z, g[u].z, dv);
+          dv = fmaf(f.w, g[u].w, dv);
+          dot[LS_GOCC_ROWS * h + u] = dv;
+          gf.x = fmaf(wgt, g[u].x, gf.x); gf.y = fmaf(wgt, g[u].y, gf.y);
+          gf.z = fmaf(wgt, g[u].z, gf.z); gf.w = fmaf(wgt, g[u].w, gf.w);
+        }
+      }
+      // transposing butterfly: lane hl ends up with sum over the 16 lanes of dot[hl]
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool hi = hl & 8;
+        const float send = hi ? dot[u] : dot[u + 8];
+        const float keep = hi ? dot[u + 8] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool hi = hl & 4;
+        const float send = hi ? dot[u] : dot[u + 4];
+        const float keep = hi ? dot[u + 4] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool hi = hl & 2;
+        const float send = hi ? dot[u] : dot[u + 2];
+        const float keep = hi ? dot[u + 2] : dot[u];
+        dot[u] = keep + __shfl_xor_sync(hmask, send, 2, 16);
+      }
+      {
+        const bool hi = hl & 1;
+        const float send = hi ? dot[0] : dot[1];
+        const float keep = hi ? dot[1] : dot[0];
+        dot[0] = keep + __shfl_xor_sync(hmask, send, 1, 16);
+      }
+      gprob_pm[pix * dm.D + 16 * w + hl] = dot[0];
+      rec = recn;
+    }
+    if (on) ls_store4<T>(gfeatT + pix * dm.Cp + 4 * hl, gf);
+  }
+}
+
 template <typename T>
 static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pix_recs, const LsDims& dm,
                               const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
   const bool full = dm.D % 16 == 0;
+  if (LS_GATHER_OCC && full && nch == 1) {
+    LS_LAUNCH(ls_bwd_gather_occ_kernel<T>, grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, pix_recs, dm, g,
+              gprob_pm, (T*)gfeatT);
+    return LS_OK;
+  }
 #define LS_GATHER(NCH)                                                                                        \
   do {                                                                                                        \
     if (full)                                                                                                 \

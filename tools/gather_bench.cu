@@ -48,8 +48,10 @@ void run(const float4* table, const int* idx, float4* out, int blocks, int threa
          blocks * threads / 32.0 / 148, WIN, smem / 1024, ms * 1e3, bytes / ms / 1e9);
 }
 
-int main() {
-  const int rows = 65536, total = 2500000 * 2;
+int main(int argc, char** argv) {
+  // rows of the table: 65536 (16.8 MB, L2-resident: the splat's feature table) by default;
+  // 400000 (102 MB) is the size of the backward's cell-major gradient
+  const int rows = argc > 1 ? atoi(argv[1]) : 65536, total = 2500000 * 2;
   float4* table; int* idx; float4* out;
   cudaMalloc(&table, (size_t)rows * 256); cudaMemset(table, 0, (size_t)rows * 256);
   std::vector<int> h(total);
