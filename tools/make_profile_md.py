@@ -52,7 +52,7 @@ out += ["", "Sum of `ls_*` kernels per step (ncu, serialised, cold caches): %.1f
         "graph the GPU is idle ~2 us per step - launch gaps are gone (they were ~45 us per step with stream launches, "
         "~15 us with programmatic dependent launches); what is left is kernel time." % tag,
         "* No kernel is DRAM-bound: DRAM utilisation is 1-50 %.  The two gathers (`ls_splat_fwd_kernel`, "
-        "`ls_bwd_gather_kernel`) each move one 256-byte row per kept point from L2 to an SM (2.48 M rows = 636 MB per "
+        "`ls_bwd_gather_occ_kernel`) each move one 256-byte row per kept point from L2 to an SM (2.48 M rows = 636 MB per "
         "direction) and sustain 6-8 TB/s of L2->SM traffic; `tools/gather_bench.cu` reaches 16-18 TB/s for the bare access "
         "pattern at >= 16 warps/SM, the guide's LTS cap is ~12 TB/s.  `cp.async.bulk` (one 256 B copy per row, "
         "`tools/bulk_bench.cu`) tops out at 8.3 TB/s and 16-byte `cp.async` is issue-bound, which is why both gathers use "
@@ -77,8 +77,12 @@ out += ["", "Sum of `ls_*` kernels per step (ncu, serialised, cold caches): %.1f
         "issued before the tile offsets arrive, 512-byte runs: 72 -> 54 us in situ (5.0 TB/s of DRAM traffic, 78 % of peak).  L2 eviction-policy hints "
         "(`createpolicy` + `ld/st.L2::cache_hint`) cost +20 us (the per-thread `createpolicy` alone) and evict-last rows "
         "slowed the forward gather - reverted.",
-        "* `ls_bwd_gather_kernel`: 128 regs (16 gradient rows x 16 B in flight per lane) -> 16 warps/SM, 318 warp "
-        "instructions per 32 records, L1 hit 42 % (a CTA is one feature-map column, its rays share cells).",
+        "* `ls_bwd_gather_occ_kernel`: the random 256-byte row gather from the 100 MB cell-major gradient scales with "
+        "resident warps, not with rows in flight per warp (`tools/gather_bench.cu 400000`: 7.8 / 11.0 / 13.7 TB/s at 16 / 24 "
+        "/ 32 warps per SM).  The first version (128 regs, 16 rows in flight per half-warp, 16 warps/SM) took 80 us; the "
+        "register-lean one (records one per lane + shuffles, eight rows at a time, 80 regs, 24 warps/SM) takes 65 us; at 32 "
+        "warps/SM (64 regs) it spills and is 2.5 us slower again.  L1 hit 42 % (a CTA is one feature-map column, its rays "
+        "share cells).",
         "* `ls_index_kernel`: ~150 instructions per point (three IEEE divisions with their slow-path checks, unfused "
         "multiply/add chains that reproduce torch's rounding), 51 % issue-active; `ls_place_kernel`: latency-bound chain "
         "(three coalesced streams -> seg_start gather -> scattered 8-byte stores)."]
