@@ -174,7 +174,7 @@ class Stepper:
     """Pre-allocated device buffers + direct C-ABI calls (what LiftSplatFunction does,
     minus the autograd bookkeeping) so the timed region is the library, not Python."""
 
-    def __init__(self, shape: LiftSplatShape, dtype, device, seed=0):
+    def __init__(self, shape: LiftSplatShape, dtype, device, seed=0, bev_format="channels_last", feat_format="nchw"):
         from e2e_parking_carla_b200 import _lib, lift_splat as ls
         from e2e_parking_carla_b200.bev_model import BevModel
         from e2e_parking_carla_b200.synthetic import make_cfg
@@ -188,6 +188,13 @@ class Stepper:
         intr, extr = make_rig(shape.batch, shape.cams, jitter=True, seed=1 + seed)
         feat, logits = make_encoder_outputs(shape, seed=seed)
         gb, gp = make_upstream_grads(shape, seed=seed)
+        # memory formats of the BEV tensors (output + upstream gradient) and of the feature maps
+        self.bev_format, self.feat_format = bev_format, feat_format
+        bfmt = torch.channels_last if bev_format == "channels_last" else torch.contiguous_format
+        ffmt = torch.channels_last if feat_format == "channels_last" else torch.contiguous_format
+        self.layout = ls.LS_FEAT_NHWC if feat_format == "channels_last" else ls.LS_FEAT_NCHW
+        feat = feat.contiguous(memory_format=ffmt)
+        gb = gb.contiguous(memory_format=bfmt)
         self.host = {"feat": feat.to(dtype).pin_memory(), "logits": logits.to(dtype).pin_memory(),
                      "intr": intr.pin_memory(), "extr": extr.pin_memory(), "gbev": gb.pin_memory(),
                      "gprob": gp.to(dtype).pin_memory()}
@@ -195,17 +202,18 @@ class Stepper:
         B, Cc, X, Y = shape.batch, shape.channels, self.grid.dim[0], self.grid.dim[1]
         self.M = torch.empty(B, shape.cams, 3, 3, device=device)
         self.t = torch.empty(B, shape.cams, 3, device=device)
-        self.bev = torch.empty(B, Cc, X, Y, device=device)
+        self.bev = torch.empty((B, Cc, X, Y), device=device, memory_format=bfmt)
         self.prob = torch.empty_like(self.dev["logits"])
-        self.gfeat = torch.empty_like(self.dev["feat"])
+        self.gfeat = torch.empty_like(self.dev["feat"])          # same memory format as feat
         self.glogits = torch.empty_like(self.dev["logits"])
-        self.ws = torch.empty(ls.workspace_bytes(self.s, self.code, True), dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(ls.scratch_bytes(self.s, self.code, True), dtype=torch.uint8, device=device)
+        self.saved = torch.empty(ls.saved_bytes(self.s, self.code, self.layout), dtype=torch.uint8, device=device)
         self.st = ls._bev_strides(self.bev)
         self.gst = ls._bev_strides(self.dev["gbev"])
-        self.out_host = {"bev": torch.empty(self.bev.shape, dtype=self.bev.dtype).pin_memory(),
-                         "prob": torch.empty(self.prob.shape, dtype=self.prob.dtype).pin_memory(),
-                         "gfeat": torch.empty(self.gfeat.shape, dtype=self.gfeat.dtype).pin_memory(),
-                         "glogits": torch.empty(self.glogits.shape, dtype=self.glogits.dtype).pin_memory()}
+        self.out_host = {"bev": torch.empty_like(self.bev, device="cpu").pin_memory(),
+                         "prob": torch.empty_like(self.prob, device="cpu").pin_memory(),
+                         "gfeat": torch.empty_like(self.gfeat, device="cpu").pin_memory(),
+                         "glogits": torch.empty_like(self.glogits, device="cpu").pin_memory()}
 
     def _p(self, t):
         return C.c_void_p(t.data_ptr())
@@ -216,12 +224,13 @@ class Stepper:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         ls.check(lib.ls_camera_transform(self._p(d["intr"]), self._p(d["extr"]), self.shape.batch * self.shape.cams,
                                          self._p(self.M), self._p(self.t), stream), "ls_camera_transform")
-        ls.check(lib.ls_forward(self._p(d["feat"]), self._p(d["logits"]), self.code, self._p(self.M),
-                                self._p(self.t), self._p(self.frustum), C.byref(self.s), self._p(self.ws),
-                                self.ws.numel(), 1, self._p(self.bev), C.byref(self.st), self._p(self.prob), stream),
-                 "ls_forward")
+        ls.check(lib.ls_forward(self._p(d["feat"]), self.layout, self._p(d["logits"]), self.code, self._p(self.M),
+                                self._p(self.t), self._p(self.frustum), C.byref(self.s), self._p(self.scratch),
+                                self.scratch.numel(), self._p(self.saved), self.saved.numel(), self._p(self.bev),
+                                C.byref(self.st), self._p(self.prob), stream), "ls_forward")
         ls.check(lib.ls_backward(self._p(d["gbev"]), C.byref(self.gst), self._p(d["gprob"]), self._p(self.prob),
-                                 self.code, C.byref(self.s), self._p(self.ws), self.ws.numel(), self._p(self.gfeat),
+                                 self._p(d["feat"]), self.layout, self.code, C.byref(self.s), self._p(self.scratch),
+                                 self.scratch.numel(), self._p(self.saved), self.saved.numel(), self._p(self.gfeat),
                                  self._p(self.glogits), stream), "ls_backward")
 
     def capture(self):
@@ -278,8 +287,10 @@ class Stepper:
             shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid)
                       for lo, hi in groups]
             self._e2e = {"chunks": chunks, "groups": groups, "shapes": shapes, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
-                         "ws": [torch.empty(ls.workspace_bytes(sc, self.code, True), dtype=torch.uint8,
-                                            device=self.device) for sc in shapes],
+                         "scratch": [torch.empty(ls.scratch_bytes(sc, self.code, True), dtype=torch.uint8,
+                                                 device=self.device) for sc in shapes],
+                         "saved": [torch.empty(ls.saved_bytes(sc, self.code, self.layout), dtype=torch.uint8,
+                                               device=self.device) for sc in shapes],
                          "ev": [[torch.cuda.Event() for _ in groups] for _ in range(4)]}
         e = self._e2e
         ev_fin, ev_bin, ev_fout, ev_bout = e["ev"]
@@ -299,13 +310,13 @@ class Stepper:
                 d["gprob"][lo * n:hi * n].copy_(self.host["gprob"][lo * n:hi * n], non_blocking=True)
                 ev_bin[k].record(e["h2d"])
         for k, (lo, hi) in enumerate(e["groups"]):
-            sc, ws = e["shapes"][k], e["ws"][k]
+            sc, scr, sav = e["shapes"][k], e["scratch"][k], e["saved"][k]
             comp.wait_event(ev_fin[k])
             ls.check(lib.ls_camera_transform(P(d["intr"][lo:hi]), P(d["extr"][lo:hi]), (hi - lo) * n,
                                              P(self.M[lo:hi]), P(self.t[lo:hi]), stream), "ls_camera_transform")
-            ls.check(lib.ls_forward(P(d["feat"][lo * n:hi * n]), P(d["logits"][lo * n:hi * n]), self.code,
-                                    P(self.M[lo:hi]), P(self.t[lo:hi]), P(self.frustum), C.byref(sc), P(ws),
-                                    ws.numel(), 1, P(self.bev[lo:hi]), C.byref(self.st),
+            ls.check(lib.ls_forward(P(d["feat"][lo * n:hi * n]), self.layout, P(d["logits"][lo * n:hi * n]),
+                                    self.code, P(self.M[lo:hi]), P(self.t[lo:hi]), P(self.frustum), C.byref(sc),
+                                    P(scr), scr.numel(), P(sav), sav.numel(), P(self.bev[lo:hi]), C.byref(self.st),
                                     P(self.prob[lo * n:hi * n]), stream), "ls_forward")
             ev_fout[k].record(comp)
         with torch.cuda.stream(e["d2h"]):
@@ -314,10 +325,11 @@ class Stepper:
                 self.out_host["bev"][lo:hi].copy_(self.bev[lo:hi], non_blocking=True)
                 self.out_host["prob"][lo * n:hi * n].copy_(self.prob[lo * n:hi * n], non_blocking=True)
         for k, (lo, hi) in enumerate(e["groups"]):
-            sc, ws = e["shapes"][k], e["ws"][k]
+            sc, scr, sav = e["shapes"][k], e["scratch"][k], e["saved"][k]
             comp.wait_event(ev_bin[k])
             ls.check(lib.ls_backward(P(d["gbev"][lo:hi]), C.byref(self.gst), P(d["gprob"][lo * n:hi * n]),
-                                     P(self.prob[lo * n:hi * n]), self.code, C.byref(sc), P(ws), ws.numel(),
+                                     P(self.prob[lo * n:hi * n]), P(d["feat"][lo * n:hi * n]), self.layout, self.code,
+                                     C.byref(sc), P(scr), scr.numel(), P(sav), sav.numel(),
                                      P(self.gfeat[lo * n:hi * n]), P(self.glogits[lo * n:hi * n]), stream),
                      "ls_backward")
             ev_bout[k].record(comp)
@@ -353,9 +365,12 @@ class Stepper:
         recs2 = torch.empty(sh.batch, int(lib.ls_sorted_records(C.byref(s))), 2, dtype=torch.int32, device=dev)
         pix = torch.empty(sh.batch * sh.cams * sh.fh * sh.fw, sh.depth_bins, 2, dtype=torch.int32, device=dev)
         featT = torch.empty(sh.batch * sh.cams, sh.fh, sh.fw, cp, dtype=self.dtype, device=dev)
-        gT = torch.empty(sh.batch, cells + 1, cp, device=dev)
+        gT = torch.empty(sh.batch, self.grid.dim[0] * self.grid.dim[1] + 1, cp, device=dev)
         gprob = torch.empty(sh.batch * npts, device=dev)
         gfeatT = torch.empty_like(featT)
+        nhwc_feat = self.feat_format == "channels_last"
+        if nhwc_feat:            # consumed / produced in place: no staging copies
+            featT, gfeatT = d["feat"], self.gfeat
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         bn, hw = sh.batch * sh.cams, sh.fh * sh.fw
         P = self._p
@@ -370,6 +385,8 @@ class Stepper:
             ("nhwc_to_nchw", lambda: lib.ls_nhwc_to_nchw(P(gfeatT), self.code, bn, sh.channels, hw, P(self.gfeat), stream)),
             ("softmax_bwd", lambda: lib.ls_softmax_bwd(P(self.prob), P(gprob), P(d["gprob"]), self.code, C.byref(s), P(self.glogits), stream)),
         ]
+        if nhwc_feat:
+            stages = [st for st in stages if st[0] not in ("nchw_to_nhwc", "nhwc_to_nchw")]
         acc = {n: 0.0 for n, _ in stages}
         for it in range(steps + 2):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
@@ -393,6 +410,10 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "stress"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--bev-format", default="channels_last", choices=["channels_last", "nchw"],
+                    help="memory format of the BEV output and of the gradient arriving on it")
+    ap.add_argument("--feat-format", default="nchw", choices=["channels_last", "nchw"],
+                    help="memory format of the encoder's feature maps (and of their gradient)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="samples in the bounded CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
@@ -443,7 +464,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from e2e_parking_carla_b200 import _lib
     lib = _lib.load()
-    st = Stepper(shape, dtype, device, seed=rank)
+    st = Stepper(shape, dtype, device, seed=rank, bev_format=args.bev_format, feat_format=args.feat_format)
+    config["bev_format"], config["feat_format"] = args.bev_format, args.feat_format
 
     def barrier():
         if dist is not None:

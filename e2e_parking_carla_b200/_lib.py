@@ -13,6 +13,7 @@ from .build import LIB_PATH
 
 LS_OK = 0
 LS_F32, LS_BF16 = 0, 1
+LS_FEAT_NCHW, LS_FEAT_NHWC = 0, 1
 
 
 class LsShape(C.Structure):
@@ -22,7 +23,7 @@ class LsShape(C.Structure):
 
 
 class LsBevStrides(C.Structure):
-    _fields_ = [("b", C.c_int64), ("c", C.c_int64), ("x", C.c_int64)]
+    _fields_ = [("b", C.c_int64), ("c", C.c_int64), ("x", C.c_int64), ("y", C.c_int64)]
 
 
 _P = C.c_void_p
@@ -51,9 +52,12 @@ PROTOTYPES = {
     "ls_splat_fwd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _SH, _P, _ST, _P]),
     "ls_splat_bwd": (C.c_int, [_P, _ST, _P, C.c_int, _P, _P, _SH, _P, _P, _P, _P]),
     "ls_softmax_bwd": (C.c_int, [_P, _P, _P, C.c_int, _SH, _P, _P]),
-    "ls_workspace_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
-    "ls_forward": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _SH, _P, C.c_size_t, C.c_int, _P, _ST, _P, _P]),
-    "ls_backward": (C.c_int, [_P, _ST, _P, _P, C.c_int, _SH, _P, C.c_size_t, _P, _P, _P]),
+    "ls_scratch_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
+    "ls_saved_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
+    "ls_forward": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _SH, _P, C.c_size_t, _P, C.c_size_t, _P, _ST, _P,
+                             _P]),
+    "ls_backward": (C.c_int, [_P, _ST, _P, _P, _P, C.c_int, C.c_int, _SH, _P, C.c_size_t, _P, C.c_size_t, _P, _P,
+                              _P]),
 }
 
 

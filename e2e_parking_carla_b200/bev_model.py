@@ -49,14 +49,24 @@ class BevModel(nn.Module):
     geometry : ``"native"`` (default) computes E^-1, K^-1 in ``ls_camera_transform``
         (no host sync, graph-capturable); ``"torch"`` calls ``torch.inverse`` exactly as
         model/bev_model.py:46,53 does, for bit-parity with the reference on the same device.
+    bev_memory_format : memory format of the returned ``bev_feature`` ([B,C,X,Y] fp32 with the
+        reference's values either way).  ``torch.channels_last`` (default) is the splat's native
+        layout: a cell's channels are one 256-byte row, tiles leave as bulk (TMA) stores, and
+        when the consumer keeps the format (``add_target_bev`` below, ``F.interpolate``,
+        ``conv1`` do) the gradient comes back channels_last and is gathered in place.
+        ``torch.contiguous_format`` reproduces the reference's strides (model/bev_model.py:76,105).
     """
 
-    def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native"):
+    def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native",
+                 bev_memory_format=torch.channels_last):
         super().__init__()
         self.cfg = cfg
         if geometry not in ("native", "torch"):
             raise ValueError("geometry must be 'native' or 'torch'")
+        if bev_memory_format not in (torch.channels_last, torch.contiguous_format):
+            raise ValueError("bev_memory_format must be torch.channels_last or torch.contiguous_format")
         self.geometry_mode = geometry
+        self.bev_memory_format = bev_memory_format
         if not getattr(cfg, "use_depth_distribution", 1):
             # the reference crashes in this mode too (depth is None at bev_model.py:64)
             raise ValueError("use_depth_distribution=0 is not supported (nor by the reference)")
@@ -144,7 +154,8 @@ class BevModel(nn.Module):
         b, n, c, h, w = images.shape
         feat, depth_logits = self.cam_encoder(images.view(b * n, c, h, w))
         M, t = self.camera_transform(intrinsics, extrinsics)
-        bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid)
+        bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid,
+                                                self.bev_memory_format)
         return bev_feature, pred_depth
 
     def forward(self, images, intrinsics, extrinsics):

@@ -26,12 +26,17 @@ bool ls_pdl_enabled() {
 // library-owned non-blocking streams and join them back into the caller's stream with events:
 // still one asynchronous unit of work on `stream` for the caller (and capturable in a CUDA
 // graph as a fork/join), but the small kernels overlap instead of queueing behind each other.
+// The streams and events are per device and shared by every caller, so the whole enqueue
+// sequence of a pipeline call runs under the device's mutex (a wait captures the state of
+// its event at the time of the call, so later calls re-recording it do no harm), and LsFork's
+// destructor joins whatever was forked on EVERY exit path - an error return never leaves a
+// side stream running on buffers the caller is about to free, nor a capture unjoined.
 #include <mutex>
-#include <stdlib.h>
 struct LsAsync {
   cudaStream_t s1 = nullptr, s2 = nullptr;
   cudaEvent_t fork = nullptr, j1 = nullptr, j2 = nullptr;
   bool ready = false;
+  std::mutex mu;     // held while a pipeline call enqueues
 };
 static LsAsync g_async[64];
 static std::mutex g_async_mu;
@@ -53,6 +58,43 @@ static LsAsync* ls_async() {
   return &a;
 }
 
+// Scope of one pipeline call's use of the side streams.
+struct LsFork {
+  LsAsync* a;
+  cudaStream_t main;
+  bool open1 = false, open2 = false;
+  explicit LsFork(cudaStream_t stream) : a(ls_async()), main(stream) {
+    if (a) a->mu.lock();
+  }
+  // side stream k (1 or 2) ordered after everything enqueued on the caller's stream so far;
+  // the caller's stream itself when side streams are off or the fork fails
+  cudaStream_t side(int k) {
+    if (!a) return main;
+    bool& open = (k == 1) ? open1 : open2;
+    cudaStream_t st = (k == 1) ? a->s1 : a->s2;
+    if (cudaEventRecord(a->fork, main) != cudaSuccess || cudaStreamWaitEvent(st, a->fork, 0) != cudaSuccess) return main;
+    open = true;
+    return st;
+  }
+  // the caller's stream waits for side stream k
+  int join(int k) {
+    if (!a) return LS_OK;
+    bool& open = (k == 1) ? open1 : open2;
+    if (!open) return LS_OK;
+    open = false;
+    cudaEvent_t ev = (k == 1) ? a->j1 : a->j2;
+    LS_CUDA(cudaEventRecord(ev, (k == 1) ? a->s1 : a->s2));
+    LS_CUDA(cudaStreamWaitEvent(main, ev, 0));
+    return LS_OK;
+  }
+  ~LsFork() {
+    if (!a) return;
+    (void)join(1);
+    (void)join(2);
+    a->mu.unlock();
+  }
+};
+
 static int ls_check_shape(const LsShape* s) {
   if (!s) return LS_ERR_BAD_ARG;
   if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fh <= 0 || s->fw <= 0 || s->C <= 0) return LS_ERR_BAD_ARG;
@@ -66,7 +108,11 @@ static int ls_check_splat_shape(const LsShape* s) {
   if (rc) return rc;
   if (s->Z != 1) return LS_ERR_UNSUPPORTED;   // reference: squeeze(0) needs Z == 1 (bev_model.py:104)
   if (s->C > 4 * LS_CCHUNK) return LS_ERR_UNSUPPORTED;
+  // placement: at most 32 depth bins per thread of 16 depth groups, and its pixel-major staging
+  // tile (32 pixels x (D|1) records) has to fit the default 48 KB of shared memory
+  if (s->D > ls_max_depth_bins()) return LS_ERR_UNSUPPORTED;
   LsDims dm = ls_dims(s);
+  if (ls_grid(s).tiles >= (1 << 21)) return LS_ERR_UNSUPPORTED;        // exact magic division tile / tiles_y
   // sort key: 8 bits cell-in-tile | (pixel << dbits | d) must fit 24 bits
   if (((long long)s->N * dm.HW) << dm.dbits > (1LL << 24)) return LS_ERR_UNSUPPORTED;
   if ((long long)s->N * dm.HW > (1LL << 20)) return LS_ERR_UNSUPPORTED;   // pixel id field of a sorted record
@@ -74,45 +120,66 @@ static int ls_check_splat_shape(const LsShape* s) {
   if (((long long)ls_grid(s).Vc + 1) * dm.Cp * 4 >= (1LL << 31)) return LS_ERR_UNSUPPORTED;   // 32-bit row byte offsets
   return LS_OK;
 }
+static bool ls_layout_ok(int layout, const LsShape* s) {
+  return layout == LS_FEAT_NCHW || (layout == LS_FEAT_NHWC && s->C % 4 == 0);
+}
 static bool ls_dtype_ok(int dtype) { return dtype == LS_F32 || dtype == LS_BF16; }
 
 // ---- workspace carving -------------------------------------------------------------
+// scratch: transient buffers of one call.  saved: what ls_backward needs from ls_forward.
 struct LsWs {
-  int *cell, *within, *counts, *seg_start, *tile_order, *tile_tot;
-  int2 *recs, *recs_sorted, *pix_recs;
-  void* featT;
+  // scratch (forward)
+  int *cell, *within, *counts, *tile_order, *tile_tot;
+  int2 *recs, *recs_sorted;
+  // scratch (backward)
   float *gT, *gprob_pm;
   void* gfeatT;
-  size_t bytes;
+  // saved
+  void* featT;
+  int* seg_start;
+  int2* pix_recs;
+  size_t scratch_bytes, saved_bytes;
 };
 static inline size_t ls_align(size_t v) { return (v + 255) & ~(size_t)255; }
-static LsWs ls_carve(const LsShape* s, int dtype, int with_backward, void* base) {
+// phase: 0 forward scratch, 1 backward scratch.  saved may be NULL (forward without backward
+// state): seg_start then lives in the scratch blob.
+static LsWs ls_carve(const LsShape* s, int dtype, int feat_layout, int phase, void* scratch, void* saved, bool with_saved) {
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
   const size_t es = dtype == LS_BF16 ? 2 : 4;
   const size_t pts = (size_t)dm.B * dm.Npts;
   const size_t feat = (size_t)dm.B * dm.N * dm.HW * dm.Cp * es;
-  char* p = (char*)base;
-  size_t off = 0;
   LsWs w;
   memset(&w, 0, sizeof(w));
+  char* p = (char*)scratch;
+  size_t off = 0;
   auto take = [&](size_t n) { void* r = p ? (void*)(p + off) : nullptr; off += ls_align(n); return r; };
-  w.featT = take(feat);                       // kept for backward
-  w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);   // kept for backward
-  w.tile_order = (int*)take((size_t)dm.B * g.tiles * 4);
-  w.tile_tot = (int*)take((size_t)dm.B * g.tiles * 4);
-  w.counts = (int*)take((size_t)dm.B * g.Vc * 4);
-  w.cell = (int*)take(pts * 4);
-  w.within = (int*)take(pts * 4);
-  w.recs = (int2*)take(pts * 8);
-  w.recs_sorted = (int2*)take((size_t)dm.B * ls_sorted_records_capacity(dm, g) * 8);
-  if (with_backward) {
-    w.pix_recs = (int2*)take(pts * 8);        // kept for backward
-    w.gT = (float*)take((size_t)dm.B * (g.Vc + 1) * dm.Cp * 4);
+  if (phase == 0) {
+    w.tile_order = (int*)take((size_t)dm.B * g.tiles * 4);
+    w.tile_tot = (int*)take((size_t)dm.B * g.tiles * 4);
+    w.counts = (int*)take((size_t)dm.B * g.Vc * 4);
+    w.cell = (int*)take(pts * 4);
+    w.within = (int*)take(pts * 4);
+    w.recs = (int2*)take(pts * 8);
+    w.recs_sorted = (int2*)take((size_t)dm.B * ls_sorted_records_capacity(dm, g) * 8);
+    if (!with_saved) {
+      w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);
+      if (feat_layout == LS_FEAT_NCHW) w.featT = take(feat);
+    }
+  } else {
     w.gprob_pm = (float*)take(pts * 4);
-    w.gfeatT = take(feat);
+    if (feat_layout == LS_FEAT_NCHW) w.gfeatT = take(feat);
+    w.gT = (float*)take((size_t)dm.B * (g.XY + 1) * dm.Cp * 4);     // only read for NCHW gradients
   }
-  w.bytes = off;
+  w.scratch_bytes = off;
+  p = (char*)saved;
+  off = 0;
+  if (with_saved) {
+    w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);
+    w.pix_recs = (int2*)take(pts * 8);
+    if (feat_layout == LS_FEAT_NCHW) w.featT = take(feat);
+  }
+  w.saved_bytes = off;
   return w;
 }
 
@@ -252,89 +319,106 @@ int ls_splat_bwd(const float* grad_bev, const LsBevStrides* gst, const void* fea
                  void* grad_feat_nhwc, ls_stream_t stream) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
-  if (!grad_bev || !gst || !feat_nhwc || !pix_recs || !seg_start || !gT_ws || !grad_prob_pm || !grad_feat_nhwc ||
-      !ls_dtype_ok(dtype))
+  if (!grad_bev || !gst || !feat_nhwc || !pix_recs || !grad_prob_pm || !grad_feat_nhwc || !ls_dtype_ok(dtype))
     return LS_ERR_BAD_ARG;
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
-  if ((rc = ls_launch_bwd_transpose(grad_bev, *gst, seg_start, dm, g, gT_ws, (cudaStream_t)stream))) return rc;
-  return ls_launch_bwd_gather(gT_ws, feat_nhwc, dtype, (const int2*)pix_recs, dm, g, grad_prob_pm, grad_feat_nhwc,
-                              (cudaStream_t)stream);
+  const int mode = ls_classify_grad_in(grad_bev, *gst, dm, g);
+  if (mode == LS_GRAD_BAD) return LS_ERR_UNSUPPORTED;
+  if (mode == LS_GRAD_STAGED) {
+    if (!gT_ws || !seg_start) return LS_ERR_BAD_ARG;
+    if ((rc = ls_launch_bwd_transpose(grad_bev, *gst, seg_start, dm, g, gT_ws, (cudaStream_t)stream))) return rc;
+    return ls_launch_bwd_gather(gT_ws, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, feat_nhwc, dtype,
+                                (const int2*)pix_recs, dm, g, grad_prob_pm, grad_feat_nhwc, (cudaStream_t)stream);
+  }
+  return ls_launch_bwd_gather(grad_bev, gst->b, gst->y, mode, feat_nhwc, dtype, (const int2*)pix_recs, dm, g,
+                              grad_prob_pm, grad_feat_nhwc, (cudaStream_t)stream);
 }
 
-size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward) {
+size_t ls_scratch_bytes(const LsShape* s, int dtype, int with_backward) {
   if (ls_check_splat_shape(s) || !ls_dtype_ok(dtype)) return 0;
-  return ls_carve(s, dtype, with_backward, nullptr).bytes;
+  // sized for the layout that needs most (NCHW features and gradients), so one blob serves any call
+  size_t n = ls_carve(s, dtype, LS_FEAT_NCHW, 0, nullptr, nullptr, false).scratch_bytes;
+  if (with_backward) {
+    const size_t b = ls_carve(s, dtype, LS_FEAT_NCHW, 1, nullptr, nullptr, true).scratch_bytes;
+    n = b > n ? b : n;
+  }
+  return n;
 }
 
-int ls_forward(const void* feat, const void* logits, int dtype, const float* M, const float* t, const float* frustum,
-               const LsShape* s, void* ws, size_t ws_bytes, int with_backward, float* bev,
-               const LsBevStrides* bev_strides, void* prob, ls_stream_t stream_) {
+size_t ls_saved_bytes(const LsShape* s, int dtype, int feat_layout) {
+  if (ls_check_splat_shape(s) || !ls_dtype_ok(dtype) || !ls_layout_ok(feat_layout, s)) return 0;
+  return ls_carve(s, dtype, feat_layout, 0, nullptr, nullptr, true).saved_bytes;
+}
+
+int ls_forward(const void* feat, int feat_layout, const void* logits, int dtype, const float* M, const float* t,
+               const float* frustum, const LsShape* s, void* scratch, size_t scratch_bytes, void* saved,
+               size_t saved_bytes, float* bev, const LsBevStrides* bev_strides, void* prob, ls_stream_t stream_) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
-  if (!feat || !logits || !M || !t || !frustum || !ws || !bev || !bev_strides || !prob || !ls_dtype_ok(dtype))
+  if (!feat || !logits || !M || !t || !frustum || !scratch || !bev || !bev_strides || !prob || !ls_dtype_ok(dtype))
     return LS_ERR_BAD_ARG;
-  if (ws_bytes < ls_carve(s, dtype, with_backward, nullptr).bytes) return LS_ERR_WORKSPACE;
+  if (!ls_layout_ok(feat_layout, s)) return LS_ERR_UNSUPPORTED;
+  const bool with_saved = saved != nullptr;
+  LsWs w = ls_carve(s, dtype, feat_layout, 0, scratch, saved, with_saved);
+  if (scratch_bytes < w.scratch_bytes || saved_bytes < w.saved_bytes) return LS_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  LsWs w = ls_carve(s, dtype, with_backward, ws);
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
-  LsAsync* a = ls_async();
-  cudaStream_t s_soft = stream, s_feat = stream;
-  if (a) {
-    LS_CUDA(cudaEventRecord(a->fork, stream));
-    LS_CUDA(cudaStreamWaitEvent(a->s1, a->fork, 0));
-    LS_CUDA(cudaStreamWaitEvent(a->s2, a->fork, 0));
-    s_soft = a->s1;
-    s_feat = a->s2;
-  }
-  // side stream 1: depth softmax; side stream 2: NHWC staging of the features
-  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, s_soft))) return rc;
-  if ((rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, s_feat))) return rc;
-  if (a) {
-    LS_CUDA(cudaEventRecord(a->j1, a->s1));
-    LS_CUDA(cudaEventRecord(a->j2, a->s2));
-  }
+  if (ls_classify_bev_out(bev, *bev_strides, dm, g) == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
+  const void* featT = feat_layout == LS_FEAT_NHWC ? feat : w.featT;
+  LsFork fk(stream);
+  // side stream 1: depth softmax; side stream 2: NHWC staging of NCHW features
+  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, fk.side(1)))) return rc;
+  if (feat_layout == LS_FEAT_NCHW &&
+      (rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, fk.side(2))))
+    return rc;
   // caller's stream: index -> scan, then (after softmax) placement, then (after staging) the splat
   if ((rc = ls_launch_zero_counts(w.counts, dm, g, stream))) return rc;
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
   if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, w.tile_tot, stream))) return rc;
-  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j1, 0));
-  if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs,
-                            with_backward ? w.pix_recs : nullptr, stream)))
-    return rc;
-  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j2, 0));
-  return ls_launch_splat_fwd(w.featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, dm, g, bev,
+  if ((rc = fk.join(1))) return rc;
+  if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs, w.pix_recs, stream))) return rc;
+  if ((rc = fk.join(2))) return rc;
+  return ls_launch_splat_fwd(featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, dm, g, bev,
                              *bev_strides, stream);
 }
 
 int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext, const void* prob,
-                int dtype, const LsShape* s, void* ws, size_t ws_bytes, void* grad_feat, void* grad_logits,
-                ls_stream_t stream_) {
+                const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch, size_t scratch_bytes,
+                const void* saved, size_t saved_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream_) {
   int rc = ls_check_splat_shape(s);
   if (rc) return rc;
-  if (!grad_bev || !grad_strides || !prob || !ws || !grad_feat || !grad_logits || !ls_dtype_ok(dtype))
+  if (!grad_bev || !grad_strides || !prob || !scratch || !saved || !grad_feat || !grad_logits || !ls_dtype_ok(dtype))
     return LS_ERR_BAD_ARG;
-  if (ws_bytes < ls_carve(s, dtype, 1, nullptr).bytes) return LS_ERR_WORKSPACE;
+  if (!ls_layout_ok(feat_layout, s)) return LS_ERR_UNSUPPORTED;
+  if (feat_layout == LS_FEAT_NHWC && !feat) return LS_ERR_BAD_ARG;
+  LsWs wf = ls_carve(s, dtype, feat_layout, 0, nullptr, const_cast<void*>(saved), true);
+  LsWs w = ls_carve(s, dtype, feat_layout, 1, scratch, nullptr, false);
+  if (scratch_bytes < w.scratch_bytes || saved_bytes < wf.saved_bytes) return LS_ERR_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
-  LsWs w = ls_carve(s, dtype, 1, ws);
   LsDims dm = ls_dims(s);
   LsGrid g = ls_grid(s);
-  if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, w.seg_start, dm, g, w.gT, stream))) return rc;
-  if ((rc = ls_launch_bwd_gather(w.gT, w.featT, dtype, w.pix_recs, dm, g, w.gprob_pm, w.gfeatT, stream))) return rc;
-  // the two layout fix-ups are independent: grad_feat on a side stream, grad_logits on the caller's
-  LsAsync* a = ls_async();
-  cudaStream_t s_feat = stream;
-  if (a) {
-    LS_CUDA(cudaEventRecord(a->fork, stream));
-    LS_CUDA(cudaStreamWaitEvent(a->s1, a->fork, 0));
-    s_feat = a->s1;
+  const int mode = ls_classify_grad_in(grad_bev, *grad_strides, dm, g);
+  if (mode == LS_GRAD_BAD) return LS_ERR_UNSUPPORTED;
+  const void* featT = feat_layout == LS_FEAT_NHWC ? feat : wf.featT;
+  void* gfeatT = feat_layout == LS_FEAT_NHWC ? grad_feat : w.gfeatT;
+  if (mode == LS_GRAD_STAGED) {
+    if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, wf.seg_start, dm, g, w.gT, stream))) return rc;
+    rc = ls_launch_bwd_gather(w.gT, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, featT, dtype, wf.pix_recs, dm, g,
+                              w.gprob_pm, gfeatT, stream);
+  } else {
+    rc = ls_launch_bwd_gather(grad_bev, grad_strides->b, grad_strides->y, mode, featT, dtype, wf.pix_recs, dm, g,
+                              w.gprob_pm, gfeatT, stream);
   }
-  if ((rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, s_feat))) return rc;
-  if (a) LS_CUDA(cudaEventRecord(a->j1, a->s1));
+  if (rc) return rc;
+  // the two layout fix-ups are independent: grad_feat on a side stream, grad_logits on the caller's
+  LsFork fk(stream);
+  if (feat_layout == LS_FEAT_NCHW &&
+      (rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, fk.side(1))))
+    return rc;
   if ((rc = ls_launch_softmax_bwd(prob, w.gprob_pm, grad_prob_ext, dtype, dm, grad_logits, stream))) return rc;
-  if (a) LS_CUDA(cudaStreamWaitEvent(stream, a->j1, 0));
-  return LS_OK;
+  return fk.join(1);
 }
 
 }  // extern "C"

@@ -35,9 +35,11 @@
 // Everything a kernel needs to know about the BEV grid, derived once on the host.
 struct LsGrid {
   int X, Y, Z;
+  int XY;          // X * Y: cells of one sample in the reference's row-major rank order
   int tiles_x, tiles_y, tiles;
   int Vc;          // padded cell count = tiles * LS_TILE
   int seg_stride;  // Vc + LS_SEG_PAD
+  unsigned long long ty_magic;   // ceil(2^42 / tiles_y): tile / tiles_y == (tile * ty_magic) >> 42 for tile < 2^21
   float off[3];    // bev_start_pos - bev_res / 2   (float32 ops, model/bev_model.py:85)
   float res[3];
   float fdim[3];   // (float)dim, exact (dim < 2^24)
@@ -72,6 +74,8 @@ static inline LsGrid ls_grid(const LsShape* s) {
   g.tiles = g.tiles_x * g.tiles_y;
   g.Vc = g.tiles * LS_TILE;
   g.seg_stride = g.Vc + LS_SEG_PAD;
+  g.XY = s->X * s->Y;
+  g.ty_magic = ((1ULL << 42) + (unsigned long long)g.tiles_y - 1) / (unsigned long long)g.tiles_y;
   for (int i = 0; i < 3; ++i) {
     // x86-64 float arithmetic is IEEE single (SSE), same bits as torch's float32 ops.
     volatile float half = s->res[i] / 2.0f;
@@ -95,6 +99,31 @@ __host__ __device__ __forceinline__ int ls_rank_of_cell(int cell, const LsGrid& 
   const int gy = (tile % g.tiles_y) * LS_TY + local % LS_TY;
   return (gx < g.X && gy < g.Y) ? gx * g.Y + gy : -1;
 }
+
+// tile-major cell id -> rank without a hardware division (tile < 2^21 and tiles_y < 2^21 are
+// guaranteed by ls_check_splat_shape: (tile * magic) >> 42 is then exact)
+__device__ __forceinline__ int ls_rank_of_cell_fast(int cell, const LsGrid& g) {
+  static_assert(LS_TX == 1, "row-major shortcut assumes one x-row per tile");
+  const unsigned tile = (unsigned)cell / LS_TILE, local = (unsigned)cell % LS_TILE;
+  const unsigned gx = (unsigned)(((unsigned long long)tile * g.ty_magic) >> 42);
+  const unsigned gy = (tile - gx * (unsigned)g.tiles_y) * LS_TY + local;
+  return (int)(gx * (unsigned)g.Y + gy);
+}
+
+// ---- BEV tensor layouts (include/ls_b200.h LsBevStrides) --------------------------------
+enum LsBevOut {
+  LS_OUT_NCHW_VEC4 = 0,    // y stride 1, 16-byte aligned runs: 4x4 register transposes + 16-byte stores
+  LS_OUT_NCHW_SCALAR = 1,  // y stride 1, anything else
+  LS_OUT_NHWC_BULK = 2,    // c stride 1, dense 64-channel rows: the tile leaves as ONE bulk (TMA) store
+  LS_OUT_NHWC_ROWS = 3,    // c stride 1, any row pitch / channel count: coalesced 4-byte stores
+  LS_OUT_BAD = -1
+};
+enum LsGradIn {
+  LS_GRAD_STAGED = 0,      // NCHW gradient -> cell rows staged by ls_bwd_transpose_kernel
+  LS_GRAD_DIRECT_VEC = 1,  // channels-last gradient, 16-byte aligned rows: gathered in place
+  LS_GRAD_DIRECT_SCALAR = 2,   // channels-last gradient, unaligned rows (e.g. a 64-channel slice of 65)
+  LS_GRAD_BAD = -1
+};
 
 // Voxel coordinate of one frustum point, operation by operation as torch-CPU does it
 // (model/bev_model.py:50-55,85): p=(u*d, v*d, d); g_i=((0+m_i0*px)+m_i1*py)+m_i2*pz; g_i+=t_i;

@@ -371,9 +371,9 @@ int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* se
 // writes one 8-byte record (sort key, prob) into slot seg_start[cell] + ticket.  The ticket
 // order inside a cell is arbitrary (atomics); ls_splat_fwd re-orders each cell by key, so the
 // sums are deterministic.  key = cell_in_tile << 24 | (pixel << dbits | d).
-// With pix_recs != NULL it also emits, pixel-major, the (cell, prob) pair of every depth bin
-// of every pixel - the index the pixel-stationary backward walks (dropped points point at
-// row Vc, an all-zero row of the cell-major gradient).
+// With pix_recs != NULL it also emits, pixel-major, the (rank, prob) pair of every depth bin
+// of every pixel - the index the pixel-stationary backward walks (dropped points carry
+// rank X*Y: one past the sample's last cell).
 // CTA = (sample, camera, 32 consecutive pixels) x all depth bins; loads are coalesced over
 // pixels, the pixel-major rows are transposed through shared memory.
 // =====================================================================================
@@ -418,8 +418,9 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
           const int key = ((c[k] & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
           recs[(size_t)b * dm.Npts + sg[k] + tk[k]] = make_int2(key, wb[k]);
         }
-        // byte offset of the cell's row in the cell-major gradient block (row Vc = zeros)
-        if (pix_recs) stage[lane * Dp + d] = make_int2((c[k] >= 0 ? c[k] : grid.Vc) * dm.Cp * 4, wb[k]);
+        // row of the cell in rank order (gx*Y + gy: a row of a channels-last gradient, or of the
+        // staged cell-major copy of an NCHW one); X*Y for a dropped point
+        if (pix_recs) stage[lane * Dp + d] = make_int2(c[k] >= 0 ? ls_rank_of_cell_fast(c[k], grid) : grid.XY, wb[k]);
       }
     }
   }

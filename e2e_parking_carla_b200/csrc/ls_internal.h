@@ -3,6 +3,9 @@
 #include "ls_common.cuh"
 
 // ls_index.cu
+// placement handles at most 32 depth bins per thread of 16 depth groups, and its pixel-major
+// staging tile (32 pixels x (D|1) 8-byte records) must fit 48 KB of shared memory
+static inline int ls_max_depth_bins() { return 191; }
 int ls_launch_camera_transform(const float* intr, const float* extr, int BN, float* M, float* t, cudaStream_t s);
 int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaStream_t s);
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
@@ -31,5 +34,8 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
                         int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
                             const LsGrid& g, float* gT, cudaStream_t s);
-int ls_launch_bwd_gather(const float* gT, const void* featT, int dtype, const int2* pix_recs, const LsDims& dm,
-                         const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s);
+int ls_launch_bwd_gather(const float* rows_base, long long sample_stride, long long row_stride, int mode /* LsGradIn */,
+                         const void* featT, int dtype, const int2* pix_recs, const LsDims& dm, const LsGrid& g,
+                         float* gprob_pm, void* gfeatT, cudaStream_t s);
+int ls_classify_bev_out(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g);   // LsBevOut
+int ls_classify_grad_in(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g);   // LsGradIn

@@ -105,18 +105,24 @@ ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start
 //     added after the barrier in piece order (fixed association).
 //  C  write-out: the tile is read column-wise and written as 16-byte pieces of the
 //     [B,C,X,Y] tensor, zeros included - the BEV grid is never memset.
+//     With a channels-last BEV tensor (OUT = LS_OUT_NHWC_BULK) the tile [cell][channel] IS the
+//     memory image of 128 consecutive cells: rows are kept dense (no padding, no swizzle - the
+//     column walks that needed them are gone) and the whole tile leaves as one bulk async
+//     (TMA) store issued by a single thread.
 // kCC = 64: the common case (Cp == 64) with compile-time tile geometry; kCC = 0: any Cp.
 // =====================================================================================
-template <typename T, bool VEC4, int kCC>
+template <typename T, int OUT, int kCC>
 __global__ void __launch_bounds__(LS_THREADS, LS_SPLAT_MINB)
 ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
                     const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm, LsGrid grid,
                     float* __restrict__ bev, LsBevStrides st) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
+  static_assert(OUT != LS_OUT_NHWC_BULK || (kCC == 64 && LS_TX == 1), "bulk store: dense 64-channel rows of one x-row");
+  constexpr bool kDense = OUT == LS_OUT_NHWC_BULK;
   const LsTileGeom tgr = ls_tile_geom(dm.Cp);
   const int Cp = kCC ? kCC : dm.Cp;
-  const int stride = kCC ? kCC + 4 : tgr.stride;
-  const int nqp = kCC ? kCC / 4 : tgr.nqp;
+  const int stride = kDense ? kCC : (kCC ? kCC + 4 : tgr.stride);
+  const int nqp = kDense ? 1 : (kCC ? kCC / 4 : tgr.nqp);     // nqp == 1: no swizzle
   const int ccmax = kCC ? kCC : tgr.cc;
   float* tile = smem;                                            // [LS_TILE][stride]
   int* part_cell = reinterpret_cast<int*>(smem + LS_TILE * stride);   // [LS_QWARPS] cell of each piece's open partial sum (-1: none)
@@ -284,7 +290,34 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
     }
     LS_TICK(3);
     // ---- phase C --------------------------------------------------------------------
-    if (VEC4) {
+    if (OUT == LS_OUT_NHWC_BULK) {
+      // generic-proxy writes of the tile -> visible to the async proxy, then one thread hands the
+      // valid part of the tile (whole 256-byte rows, zeros included) to the TMA unit
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        const int valid = min(LS_TY, grid.Y - ty0);
+        float* dstp = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * kCC;
+        const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(src),
+                     "r"((unsigned)(valid * kCC * 4)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile must outlive the read
+      }
+    } else if (OUT == LS_OUT_NHWC_ROWS) {
+      // channels-last with any row pitch / channel count: a warp writes one cell's channels as
+      // consecutive 4-byte stores (the chunk of a row is contiguous in memory)
+      const int lane = tid & 31;
+      for (int cl = tid >> 5; cl < LS_TILE; cl += LS_THREADS / 32) {
+        const int ox = tx0 + cl / LS_TY, oy = ty0 + cl % LS_TY;
+        if (ox >= grid.X || oy >= grid.Y) continue;
+        float* g = bev + (size_t)b * st.b + (size_t)ox * st.x + (size_t)oy * st.y + cbase;
+        for (int cr = lane; cr < cc; cr += 32) {
+          if (cbase + cr < dm.C)
+            g[cr] = tile_empty ? 0.0f : tile[cl * stride + 4 * ls_tile_quad(cl, cr >> 2, nqp) + (cr & 3)];
+        }
+      }
+    } else if (OUT == LS_OUT_NCHW_VEC4) {
       if (inb) {
         // a thread reads one channel quad of 4 consecutive cells (4 x 16 B, conflict-free),
         // transposes the 4x4 block in registers and writes 4 channels x 4 y as 16-byte
@@ -360,32 +393,60 @@ static bool ls_bev_vec4(const float* p, const LsBevStrides& st, const LsGrid& g)
   return ((uintptr_t)p % 16 == 0) && (st.b % 4 == 0) && (st.c % 4 == 0) && (st.x % 4 == 0) && (g.Y % 4 == 0);
 }
 
+// How the splat writes a BEV tensor with these strides (include/ls_b200.h LsBevStrides).
+int ls_classify_bev_out(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g) {
+  if (st.y == 1 && (st.c != 1 || dm.C == 1)) return ls_bev_vec4(p, st, g) ? LS_OUT_NCHW_VEC4 : LS_OUT_NCHW_SCALAR;
+  if (st.c == 1) {
+    const bool dense = dm.C == 64 && dm.Cp == 64 && st.y == 64 && (uintptr_t)p % 16 == 0 && st.b % 4 == 0 && st.x % 4 == 0;
+    return dense ? LS_OUT_NHWC_BULK : LS_OUT_NHWC_ROWS;
+  }
+  return LS_OUT_BAD;
+}
+
+// cudaFuncSetAttribute is per device: remember which devices have seen it
+static bool ls_attr_needed(unsigned long long* done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ULL << dev;
+  const unsigned long long prev = __atomic_fetch_or(done_mask, bit, __ATOMIC_RELAXED);
+  return !(prev & bit);
+}
+
 template <typename T>
 static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg_start, const int* tile_order,
                              int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  if (ls_attr_needed(&attr_done)) {
     const int m = (int)ls_tile_smem_max();
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
-    attr_done = true;
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, LS_OUT_NCHW_VEC4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, LS_OUT_NCHW_VEC4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, LS_OUT_NCHW_SCALAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, LS_OUT_NHWC_BULK, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    LS_CUDA(cudaFuncSetAttribute(ls_splat_fwd_kernel<T, LS_OUT_NHWC_ROWS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
   }
-  const size_t smem = ls_tile_smem_bytes(dm);
+  const int out = ls_classify_bev_out(bev, st, dm, g);
+  if (out == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
+  size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
   LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, recs, seg_start, tile_order, dm, g, recs_sorted);
-  const bool v4 = ls_bev_vec4(bev, st, g);
   const dim3 block(LS_THREADS);
   const int2* rs = recs_sorted;
-  if (v4 && dm.Cp == 64 && dm.C == 64)
-    LS_LAUNCH((ls_splat_fwd_kernel<T, true, 64>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
-              bev, st);
-  else if (v4)
-    LS_LAUNCH((ls_splat_fwd_kernel<T, true, 0>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
-              bev, st);
-  else
-    LS_LAUNCH((ls_splat_fwd_kernel<T, false, 0>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g,
-              bev, st);
+#define LS_SPLAT(OUT, CC)                                                                                          \
+  LS_LAUNCH((ls_splat_fwd_kernel<T, OUT, CC>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g, \
+            bev, st)
+  if (out == LS_OUT_NHWC_BULK) {
+    smem = (size_t)LS_TILE * 64 * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
+    LS_SPLAT(LS_OUT_NHWC_BULK, 64);
+  } else if (out == LS_OUT_NHWC_ROWS) {
+    LS_SPLAT(LS_OUT_NHWC_ROWS, 0);
+  } else if (out == LS_OUT_NCHW_VEC4 && dm.Cp == 64 && dm.C == 64) {
+    LS_SPLAT(LS_OUT_NCHW_VEC4, 64);
+  } else if (out == LS_OUT_NCHW_VEC4) {
+    LS_SPLAT(LS_OUT_NCHW_VEC4, 0);
+  } else {
+    LS_SPLAT(LS_OUT_NCHW_SCALAR, 0);
+  }
+#undef LS_SPLAT
   return LS_OK;
 }
 
@@ -398,8 +459,10 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 }
 
 // =====================================================================================
-// K4a: grad_bev [B,C,X,Y] -> cell-major gT [B, Vc, Cp]; rows of cells nobody hit are skipped
+// K4a (NCHW gradients only): grad_bev [B,C,X,Y] -> cell-major gT [B, X*Y + 1, Cp] in rank order
+// (row X*Y = zeros: where dropped points gather from); rows of cells nobody hit are skipped
 // (they are never read).  Same tile / swizzle as the forward write-out, run backwards.
+// A channels-last gradient needs none of this: its rows are gathered in place.
 // =====================================================================================
 #ifndef LS_GOCC_ROWS
 #define LS_GOCC_ROWS 8    // rows gathered at a time by a half-warp of the register-lean gather
@@ -455,13 +518,13 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
     }
   }
   for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
-  if (tile_id == 0 && blockIdx.z == 0) {   // row Vc of every sample = zeros: where dropped points gather from
-    float* zrow = gT + ((size_t)b * (grid.Vc + 1) + grid.Vc) * dm.Cp;
+  if (tile_id == 0 && blockIdx.z == 0) {   // row X*Y of every sample = zeros: where dropped points gather from
+    float* zrow = gT + ((size_t)b * (grid.XY + 1) + grid.XY) * dm.Cp;
     for (int i = tid; i < dm.Cp; i += LS_THREADS) zrow[i] = 0.0f;
   }
   __syncthreads();
   if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
-  float* dst = gT + ((size_t)b * (grid.Vc + 1) + (size_t)tile_id * LS_TILE) * dm.Cp + cbase;
+  float* dst = gT + (size_t)b * (grid.XY + 1) * dm.Cp + cbase;     // + rank * Cp
   if (VEC4) {
     // 4x4 register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
     const int clc = xr * LS_TY + 4 * y4;
@@ -497,8 +560,8 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
     if (q < nquads) {
 #pragma unroll 4
       for (int cl = tid / kQ; cl < LS_TILE; cl += LS_THREADS / kQ) {
-        if (seg[cl + 1] != seg[cl])
-          *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + 4 * q) =
+        if (seg[cl + 1] != seg[cl])        // a hit cell is inside the grid
+          *reinterpret_cast<float4*>(dst + ((size_t)(tx0 + cl / LS_TY) * grid.Y + ty0 + cl % LS_TY) * dm.Cp + 4 * q) =
               *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
       }
     }
@@ -521,33 +584,89 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
 // K4b: gradient gather, pixel-stationary (deterministic, no atomics).
 // reference: VoxelsSumming.backward tool/geometry.py:307-317 + autograd of
 // model/bev_model.py:66,91-97.  CTA = one feature-map column of one camera (its rays sweep one
-// radial line of the BEV, so the cell-major gradient rows it gathers are re-used from L1);
+// radial line of the BEV, so the gradient rows it gathers are re-used from L1);
 // a half-warp owns a pixel: 16 lanes x float4 channels, depth bins in windows of 16:
 //   gf[c]  += prob[d] * g[cell(d), c]                     (registers, d ascending)
 //   gp[d]   = sum_c feat[c] * g[cell(d), c]               (16 dots reduced together by a
 //                                                          transposing butterfly: 15 shuffles)
 // Outputs: grad_feat NHWC-padded [pix][Cp] and grad_prob PIXEL-major [pix][D].
+// Where the rows g[cell] come from (MODE, enum LsGradIn):
+//   STAGED         the cell-major copy of an NCHW gradient (row X*Y = zeros for dropped points)
+//   DIRECT_VEC     the channels-last gradient tensor itself, 16-byte aligned rows
+//   DIRECT_SCALAR  the same with unaligned rows (a 64-channel slice of a 65-channel tensor)
+// pix_recs.x is the rank (row number) of the point's cell, X*Y for a dropped point.
 // =====================================================================================
-// kFullD: D is a multiple of 16 (no predicates on the index loads).  pix_recs.x holds the BYTE
-// offset of the cell's row inside the sample's cell-major gradient block.
-template <typename T, int NCH, bool kFullD>
+// An all-zero row (never written): where dropped points "gather" from when the rows are read in
+// place.  Selecting the ADDRESS keeps every row load unconditional, so the compiler keeps all of
+// a window's loads in flight (a predicated load needs its destination zeroed first, and ptxas
+// then serialised the window into pairs: 2x slower).
+__device__ float4 ls_zero_row[4 * LS_CCHUNK / 4];
+
+template <int MODE>
+__device__ __forceinline__ float4 ls_grad_row4(const char* __restrict__ base, const char* __restrict__ zero,
+                                               unsigned rank, unsigned row_bytes, unsigned nrows) {
+  if (MODE == LS_GRAD_STAGED) return __ldg(reinterpret_cast<const float4*>(base + (size_t)rank * row_bytes));
+  const char* p = rank < nrows ? base + (size_t)rank * row_bytes : zero;
+  if (MODE == LS_GRAD_DIRECT_VEC) return __ldg(reinterpret_cast<const float4*>(p));
+  const float* f = reinterpret_cast<const float*>(p);
+  return make_float4(__ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3));
+}
+
+// transposing butterfly over a half-warp: lane hl ends up with the sum over the 16 lanes of dot[hl]
+__device__ __forceinline__ float ls_half_butterfly(float (&dot)[16], int hl, unsigned hmask) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const bool hi = hl & 8;
+    const float send = hi ? dot[u] : dot[u + 8];
+    const float keep = hi ? dot[u + 8] : dot[u];
+    dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool hi = hl & 4;
+    const float send = hi ? dot[u] : dot[u + 4];
+    const float keep = hi ? dot[u + 4] : dot[u];
+    dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const bool hi = hl & 2;
+    const float send = hi ? dot[u] : dot[u + 2];
+    const float keep = hi ? dot[u + 2] : dot[u];
+    dot[u] = keep + __shfl_xor_sync(hmask, send, 2, 16);
+  }
+  const bool hi = hl & 1;
+  const float send = hi ? dot[0] : dot[1];
+  const float keep = hi ? dot[1] : dot[0];
+  return keep + __shfl_xor_sync(hmask, send, 1, 16);
+}
+
+// Where a sample's gradient rows live: base + b * sample_stride floats, rows row_bytes apart.
+struct LsRows {
+  const float* base;
+  long long sample_stride;
+  unsigned row_bytes;
+  unsigned nrows;       // X*Y
+};
+
+// General shape: any D, up to 4 chunks of 64 channels.
+template <typename T, int NCH, int MODE>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GATHER_MINB)
-ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
-                     LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
+                     LsDims dm, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
   ls_pdl_trigger();
   ls_pdl_wait();
-  // images in reverse order: the transposer wrote the last samples' rows last, they are the
-  // ones still in L2 when this kernel starts
+  // images in reverse order: the rows written last (staged copy) are the ones still in L2
   const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const unsigned hmask = ls_half_mask();
-  // dropped points point at row Vc: the all-zero row written by the transpose kernel
-  const char* gTb = reinterpret_cast<const char*>(gT + (size_t)b * (grid.Vc + 1) * dm.Cp + 4 * hl);
-  const unsigned zero_row = (unsigned)grid.Vc * (unsigned)dm.Cp * 4u;
   bool on[NCH];
 #pragma unroll
   for (int q = 0; q < NCH; ++q) on[q] = (q * LS_CCHUNK + 4 * hl) < dm.Cp;
+  // lanes beyond the channel count read valid bytes (lane 0's) and never store
+  const char* gb = reinterpret_cast<const char*>(rows.base + (size_t)b * rows.sample_stride);
+  const char* zrow = reinterpret_cast<const char*>(ls_zero_row);
 
   for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
     const size_t pix = (size_t)bn * dm.HW + (size_t)row * dm.fw + col;
@@ -560,24 +679,19 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
     }
     const int2* pr = pix_recs + pix * dm.D;
     for (int d0 = 0; d0 < dm.D; d0 += 16) {
-      const int n = kFullD ? 16 : min(16, dm.D - d0);
+      const int n = min(16, dm.D - d0);
       int2 r[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (kFullD) r[u] = __ldg(pr + d0 + u);                                  // half-warp-uniform
-        else r[u] = (u < n) ? __ldg(pr + d0 + u) : make_int2((int)zero_row, 0);
-      }
+      for (int u = 0; u < 16; ++u) r[u] = (u < n) ? __ldg(pr + d0 + u) : make_int2((int)rows.nrows, 0);   // half-warp-uniform
       float dot[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) dot[u] = 0.0f;
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         float4 g[16];
+        const char* gq = gb + (on[q] ? (q * LS_CCHUNK + 4 * hl) * 4 : 0);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const char* src = gTb + (unsigned)r[u].x + (unsigned)(q * LS_CCHUNK * 4);
-          g[u] = __ldg(reinterpret_cast<const float4*>(on[q] ? src : gTb + zero_row - 16 * hl));
-        }
+        for (int u = 0; u < 16; ++u) g[u] = ls_grad_row4<MODE>(gq, zrow, (unsigned)r[u].x, rows.row_bytes, rows.nrows);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const float w = __int_as_float(r[u].y);
@@ -591,35 +705,8 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
           gf[q].w = fmaf(w, g[u].w, gf[q].w);
         }
       }
-      // transposing butterfly: lane hl ends up with sum over the 16 lanes of dot[hl]
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool hi = hl & 8;
-        const float send = hi ? dot[u] : dot[u + 8];
-        const float keep = hi ? dot[u + 8] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool hi = hl & 4;
-        const float send = hi ? dot[u] : dot[u + 4];
-        const float keep = hi ? dot[u + 4] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const bool hi = hl & 2;
-        const float send = hi ? dot[u] : dot[u + 2];
-        const float keep = hi ? dot[u + 2] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 2, 16);
-      }
-      {
-        const bool hi = hl & 1;
-        const float send = hi ? dot[0] : dot[1];
-        const float keep = hi ? dot[1] : dot[0];
-        dot[0] = keep + __shfl_xor_sync(hmask, send, 1, 16);
-      }
-      if (hl < n) gprob_pm[pix * dm.D + d0 + hl] = dot[0];
+      const float mine = ls_half_butterfly(dot, hl, hmask);
+      if (hl < n) gprob_pm[pix * dm.D + d0 + hl] = mine;
     }
     T* grow = gfeatT + pix * dm.Cp + 4 * hl;
 #pragma unroll
@@ -629,27 +716,26 @@ ls_bwd_gather_kernel(const float* __restrict__ gT, const T* __restrict__ featT, 
 }
 
 // Higher-occupancy variant for the common shape (Cp <= 64, D a multiple of 16).  The random
-// 256-byte row gather from the 100 MB cell-major gradient scales with the number of resident
+// 256-byte row gather from a gradient larger than L2 scales with the number of resident
 // warps, not with the rows in flight per warp (tools/gather_bench.cu 400000: 7.8 / 11.0 / 13.7
 // TB/s at 16 / 24 / 32 warps per SM), so this version trades registers for warps: the sixteen
 // records of a depth window are loaded one per lane (a single coalesced 128-byte load per
 // half-warp, prefetched a window ahead, broadcast with 16-wide shuffles) and the rows are
 // gathered eight at a time - under 86 registers, three CTAs (24 warps) per SM.
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GOCC_MINB)
-ls_bwd_gather_occ_kernel(const float* __restrict__ gT, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
-                         LsDims dm, LsGrid grid, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
+                         LsDims dm, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
   ls_pdl_trigger();
   ls_pdl_wait();
-  // images in reverse order: the transposer wrote the last samples' rows last, they are the
-  // ones still in L2 when this kernel starts
   const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const unsigned hmask = ls_half_mask();
   const bool on = 4 * hl < dm.Cp;
   // lanes beyond the channel count read valid bytes (lane 0's) and never store
-  const char* gTb = reinterpret_cast<const char*>(gT + (size_t)b * (grid.Vc + 1) * dm.Cp + (on ? 4 * hl : 0));
+  const char* gb = reinterpret_cast<const char*>(rows.base + (size_t)b * rows.sample_stride + (on ? 4 * hl : 0));
+  const char* zrow = reinterpret_cast<const char*>(ls_zero_row);
   const int wpp = dm.D >> 4;                                                  // windows per pixel
   for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
     const size_t pix = (size_t)bn * dm.HW + (size_t)row * dm.fw + col;
@@ -666,8 +752,8 @@ ls_bwd_gather_occ_kernel(const float* __restrict__ gT, const T* __restrict__ fea
         float4 g[LS_GOCC_ROWS];
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
-          const unsigned off = (unsigned)__shfl_sync(hmask, rec.x, LS_GOCC_ROWS * h + u, 16);
-          g[u] = __ldg(reinterpret_cast<const float4*>(gTb + off));
+          const unsigned rank = (unsigned)__shfl_sync(hmask, rec.x, LS_GOCC_ROWS * h + u, 16);
+          g[u] = ls_grad_row4<MODE>(gb, zrow, rank, rows.row_bytes, rows.nrows);
         }
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
@@ -681,61 +767,37 @@ ls_bwd_gather_occ_kernel(const float* __restrict__ gT, const T* __restrict__ fea
           gf.z = fmaf(wgt, g[u].z, gf.z); gf.w = fmaf(wgt, g[u].w, gf.w);
         }
       }
-      // transposing butterfly: lane hl ends up with sum over the 16 lanes of dot[hl]
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool hi = hl & 8;
-        const float send = hi ? dot[u] : dot[u + 8];
-        const float keep = hi ? dot[u + 8] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool hi = hl & 4;
-        const float send = hi ? dot[u] : dot[u + 4];
-        const float keep = hi ? dot[u + 4] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const bool hi = hl & 2;
-        const float send = hi ? dot[u] : dot[u + 2];
-        const float keep = hi ? dot[u + 2] : dot[u];
-        dot[u] = keep + __shfl_xor_sync(hmask, send, 2, 16);
-      }
-      {
-        const bool hi = hl & 1;
-        const float send = hi ? dot[0] : dot[1];
-        const float keep = hi ? dot[1] : dot[0];
-        dot[0] = keep + __shfl_xor_sync(hmask, send, 1, 16);
-      }
-      gprob_pm[pix * dm.D + 16 * w + hl] = dot[0];
+      gprob_pm[pix * dm.D + 16 * w + hl] = ls_half_butterfly(dot, hl, hmask);
       rec = recn;
     }
     if (on) ls_store4<T>(gfeatT + pix * dm.Cp + 4 * hl, gf);
   }
 }
 
-template <typename T>
-static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pix_recs, const LsDims& dm,
-                              const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
+// How the backward reads a gradient with these strides (include/ls_b200.h LsBevStrides).
+int ls_classify_grad_in(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g) {
+  if (st.y == 1 && (st.c != 1 || dm.C == 1)) return LS_GRAD_STAGED;
+  if (st.c == 1 && dm.C == dm.Cp && st.x == (long long)g.Y * st.y && st.y >= dm.C &&
+      (unsigned long long)g.XY * (unsigned long long)st.y * 4ULL < (1ULL << 32)) {
+    const bool vec = (uintptr_t)p % 16 == 0 && st.y % 4 == 0 && st.b % 4 == 0;
+    return vec ? LS_GRAD_DIRECT_VEC : LS_GRAD_DIRECT_SCALAR;
+  }
+  return LS_GRAD_BAD;
+}
+
+template <typename T, int MODE>
+static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2* pix_recs, const LsDims& dm,
+                              float* gprob_pm, void* gfeatT, cudaStream_t s) {
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
-  const bool full = dm.D % 16 == 0;
-  if (LS_GATHER_OCC && full && nch == 1) {
-    LS_LAUNCH(ls_bwd_gather_occ_kernel<T>, grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, pix_recs, dm, g,
-              gprob_pm, (T*)gfeatT);
+  if (LS_GATHER_OCC && dm.D % 16 == 0 && nch == 1) {
+    LS_LAUNCH((ls_bwd_gather_occ_kernel<T, MODE>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT, pix_recs,
+              dm, gprob_pm, (T*)gfeatT);
     return LS_OK;
   }
 #define LS_GATHER(NCH)                                                                                        \
-  do {                                                                                                        \
-    if (full)                                                                                                 \
-      LS_LAUNCH((ls_bwd_gather_kernel<T, NCH, true>), grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, \
-                pix_recs, dm, g, gprob_pm, (T*)gfeatT);                                                       \
-    else                                                                                                      \
-      LS_LAUNCH((ls_bwd_gather_kernel<T, NCH, false>), grid, dim3(LS_GATHER_THREADS), 0, s, gT, (const T*)featT, \
-                pix_recs, dm, g, gprob_pm, (T*)gfeatT);                                                       \
-  } while (0)
+  LS_LAUNCH((ls_bwd_gather_kernel<T, NCH, MODE>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT, \
+            pix_recs, dm, gprob_pm, (T*)gfeatT)
   switch (nch) {
     case 1: LS_GATHER(1); break;
     case 2: LS_GATHER(2); break;
@@ -747,8 +809,25 @@ static int ls_gather_dispatch(const float* gT, const void* featT, const int2* pi
   return LS_OK;
 }
 
-int ls_launch_bwd_gather(const float* gT, const void* featT, int dtype, const int2* pix_recs, const LsDims& dm,
-                         const LsGrid& g, float* gprob_pm, void* gfeatT, cudaStream_t s) {
-  if (dtype == LS_F32) return ls_gather_dispatch<float>(gT, featT, pix_recs, dm, g, gprob_pm, gfeatT, s);
-  return ls_gather_dispatch<__nv_bfloat16>(gT, featT, pix_recs, dm, g, gprob_pm, gfeatT, s);
+// rows: staged (gT, mode LS_GRAD_STAGED) or the channels-last gradient itself (direct modes)
+int ls_launch_bwd_gather(const float* rows_base, long long sample_stride, long long row_stride, int mode,
+                         const void* featT, int dtype, const int2* pix_recs, const LsDims& dm, const LsGrid& g,
+                         float* gprob_pm, void* gfeatT, cudaStream_t s) {
+  LsRows rows;
+  rows.base = rows_base;
+  rows.sample_stride = sample_stride;
+  rows.row_bytes = (unsigned)(row_stride * 4);
+  rows.nrows = (unsigned)g.XY;
+#define LS_GD(TT, MODE) return ls_gather_dispatch<TT, MODE>(rows, featT, pix_recs, dm, gprob_pm, gfeatT, s)
+  if (dtype == LS_F32) {
+    if (mode == LS_GRAD_STAGED) LS_GD(float, LS_GRAD_STAGED);
+    if (mode == LS_GRAD_DIRECT_VEC) LS_GD(float, LS_GRAD_DIRECT_VEC);
+    if (mode == LS_GRAD_DIRECT_SCALAR) LS_GD(float, LS_GRAD_DIRECT_SCALAR);
+  } else {
+    if (mode == LS_GRAD_STAGED) LS_GD(__nv_bfloat16, LS_GRAD_STAGED);
+    if (mode == LS_GRAD_DIRECT_VEC) LS_GD(__nv_bfloat16, LS_GRAD_DIRECT_VEC);
+    if (mode == LS_GRAD_DIRECT_SCALAR) LS_GD(__nv_bfloat16, LS_GRAD_DIRECT_SCALAR);
+  }
+#undef LS_GD
+  return LS_ERR_UNSUPPORTED;
 }

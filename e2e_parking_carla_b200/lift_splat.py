@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import LS_BF16, LS_F32, LsBevStrides, LsShape, check
+from ._lib import LS_BF16, LS_F32, LS_FEAT_NCHW, LS_FEAT_NHWC, LsBevStrides, LsShape, check
 
 
 # --------------------------------------------------------------------------------------
@@ -63,9 +63,42 @@ def _need_cuda(*ts: torch.Tensor) -> None:
 
 
 def _bev_strides(t: torch.Tensor) -> LsBevStrides:
-    if t.dim() != 4 or t.stride(3) != 1:
-        raise ValueError("BEV tensor must be [B,C,X,Y] with unit Y stride")
-    return LsBevStrides(t.stride(0), t.stride(1), t.stride(2))
+    """Element strides of a [B,C,X,Y] tensor; the library accepts NCHW-like (unit Y stride) and
+    channels-last-like (unit C stride) tensors, including channel-slice views of either."""
+    if t.dim() != 4:
+        raise ValueError("BEV tensor must be [B,C,X,Y]")
+    return LsBevStrides(t.stride(0), t.stride(1), t.stride(2), t.stride(3))
+
+
+def _grad_layout_ok(g: torch.Tensor) -> bool:
+    """Can ls_backward read this gradient in place?  (mirrors ls_classify_grad_in)"""
+    if g.stride(3) == 1 and (g.stride(1) != 1 or g.shape[1] == 1):
+        return True
+    return (g.stride(1) == 1 and g.shape[1] % 4 == 0 and g.stride(2) == g.shape[3] * g.stride(3)
+            and g.stride(3) >= g.shape[1] and g.shape[2] * g.shape[3] * g.stride(3) * 4 < 2 ** 32)
+
+
+def _feat_layout(feat: torch.Tensor):
+    """(tensor to hand to the library, LsFeatLayout): a channels_last feature map is consumed in
+    place (no staging copy), everything else goes in as contiguous NCHW."""
+    if feat.is_contiguous():
+        return feat, LS_FEAT_NCHW
+    if feat.shape[1] % 4 == 0 and feat.is_contiguous(memory_format=torch.channels_last):
+        return feat, LS_FEAT_NHWC
+    return feat.contiguous(), LS_FEAT_NCHW
+
+
+# one transient scratch blob per (device, stream), grown on demand and reused by every call
+_scratch = {}
+
+
+def scratch_for(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
 
 
 def grid_cells(shape: LsShape) -> Tuple[int, int, int]:
@@ -184,10 +217,21 @@ def kept_counts(seg_start: torch.Tensor, shape: LsShape) -> torch.Tensor:
     return kept
 
 
-def workspace_bytes(shape: LsShape, dtype_code: int, with_backward: bool) -> int:
-    n = _lib.load().ls_workspace_bytes(C.byref(shape), dtype_code, int(with_backward))
+_UNSUPPORTED = ("unsupported lift-splat shape (need Z == 1, C <= 256, D <= 191, "
+                "N*fh*fw*2^ceil(log2 D) <= 2^24; channels_last features need C % 4 == 0)")
+
+
+def scratch_bytes(shape: LsShape, dtype_code: int, with_backward: bool) -> int:
+    n = _lib.load().ls_scratch_bytes(C.byref(shape), dtype_code, int(with_backward))
     if n == 0:
-        raise ValueError("unsupported lift-splat shape (need Z == 1, C <= 256, N*fh*fw*2^ceil(log2 D) <= 2^24)")
+        raise ValueError(_UNSUPPORTED)
+    return n
+
+
+def saved_bytes(shape: LsShape, dtype_code: int, feat_layout: int = LS_FEAT_NCHW) -> int:
+    n = _lib.load().ls_saved_bytes(C.byref(shape), dtype_code, feat_layout)
+    if n == 0:
+        raise ValueError(_UNSUPPORTED)
     return n
 
 
@@ -199,58 +243,68 @@ class LiftSplatFunction(torch.autograd.Function):
     voxelise + sort + VoxelsSumming + scatter (model/bev_model.py:64-105,
     tool/geometry.py:285-317) with one forward and one backward pipeline call.
     Gradients flow to ``feat`` and ``depth_logits`` only, as in the reference
-    (geometry is cut by ``.long()``, bev_model.py:86)."""
+    (geometry is cut by ``.long()``, bev_model.py:86).
+
+    ``bev_format``: memory format of the returned ``bev`` ([B,C,X,Y] fp32 either way).
+    ``torch.channels_last`` is the splat's native layout (a cell's channels are one row): the
+    tile leaves as one bulk store, and a channels_last gradient is gathered in place."""
 
     @staticmethod
-    def forward(ctx, feat, logits, M, t, frustum, shape: LsShape):
+    def forward(ctx, feat, logits, M, t, frustum, shape: LsShape, bev_format=torch.contiguous_format):
         _need_cuda(feat, logits, M, t, frustum)
         if feat.dtype != logits.dtype:
             raise TypeError("feat and depth logits must share a dtype")
         code = _dtype_code(feat)
-        feat_c = feat.contiguous()
+        dev = feat.device
+        feat_c, layout = _feat_layout(feat)
         logits_c = logits.contiguous()
         need_bwd = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        ws = torch.empty(workspace_bytes(shape, code, need_bwd), dtype=torch.uint8, device=feat.device)
-        bev = torch.empty(shape.B, shape.C, shape.X, shape.Y, dtype=torch.float32, device=feat.device)
+        scratch = scratch_for(scratch_bytes(shape, code, need_bwd), dev)
+        saved = torch.empty(saved_bytes(shape, code, layout), dtype=torch.uint8, device=dev) if need_bwd else None
+        bev = torch.empty((shape.B, shape.C, shape.X, shape.Y), dtype=torch.float32, device=dev,
+                          memory_format=bev_format)
         prob = torch.empty_like(logits_c)
         st = _bev_strides(bev)
-        check(_lib.load().ls_forward(_ptr(feat_c), _ptr(logits_c), code, _ptr(M.contiguous()),
-                                     _ptr(t.contiguous()), _ptr(frustum.contiguous()), C.byref(shape), _ptr(ws),
-                                     ws.numel(), int(need_bwd), _ptr(bev), C.byref(st), _ptr(prob), _stream(feat)),
-              "ls_forward")
-        ctx.shape, ctx.code, ctx.ws = shape, code, ws
-        ctx.feat_shape, ctx.logits_shape = feat.shape, logits.shape
-        ctx.save_for_backward(prob)
+        check(_lib.load().ls_forward(_ptr(feat_c), layout, _ptr(logits_c), code, _ptr(M.contiguous()),
+                                     _ptr(t.contiguous()), _ptr(frustum.contiguous()), C.byref(shape),
+                                     _ptr(scratch), scratch.numel(), _ptr(saved), 0 if saved is None else saved.numel(),
+                                     _ptr(bev), C.byref(st), _ptr(prob), _stream(feat)), "ls_forward")
+        ctx.shape, ctx.code, ctx.layout, ctx.saved_blob = shape, code, layout, saved
+        ctx.feat_shape = feat.shape
+        ctx.save_for_backward(prob, feat_c if layout == LS_FEAT_NHWC else None)
         return bev, prob
 
     @staticmethod
     def backward(ctx, grad_bev, grad_prob):
-        (prob,) = ctx.saved_tensors
-        shape, code, ws = ctx.shape, ctx.code, ctx.ws
-        if ws is None or ws.numel() < workspace_bytes(shape, code, True):
-            raise RuntimeError("lift-splat forward ran without a backward workspace")
+        prob, feat_nhwc = ctx.saved_tensors
+        shape, code, layout, saved = ctx.shape, ctx.code, ctx.layout, ctx.saved_blob
+        if saved is None:
+            raise RuntimeError("lift-splat forward ran without backward state")
         dev = prob.device
         if grad_bev is None:
             grad_bev = torch.zeros(shape.B, shape.C, shape.X, shape.Y, dtype=torch.float32, device=dev)
         grad_bev = grad_bev.to(torch.float32)
-        if grad_bev.stride(3) != 1:
+        if not _grad_layout_ok(grad_bev):
             grad_bev = grad_bev.contiguous()
         if grad_prob is not None:
             grad_prob = grad_prob.to(prob.dtype).contiguous()
-        gfeat = torch.empty(ctx.feat_shape, dtype=prob.dtype, device=dev)
-        glogits = torch.empty(ctx.logits_shape, dtype=prob.dtype, device=dev)
+        fmt = torch.channels_last if layout == LS_FEAT_NHWC else torch.contiguous_format
+        gfeat = torch.empty(ctx.feat_shape, dtype=prob.dtype, device=dev, memory_format=fmt)
+        glogits = torch.empty_like(prob)
+        scratch = scratch_for(scratch_bytes(shape, code, True), dev)
         st = _bev_strides(grad_bev)
-        check(_lib.load().ls_backward(_ptr(grad_bev), C.byref(st), _ptr(grad_prob), _ptr(prob), code,
-                                      C.byref(shape), _ptr(ws), ws.numel(), _ptr(gfeat), _ptr(glogits),
-                                      _stream(prob)), "ls_backward")
-        return gfeat, glogits, None, None, None, None
+        check(_lib.load().ls_backward(_ptr(grad_bev), C.byref(st), _ptr(grad_prob), _ptr(prob), _ptr(feat_nhwc),
+                                      layout, code, C.byref(shape), _ptr(scratch), scratch.numel(), _ptr(saved),
+                                      saved.numel(), _ptr(gfeat), _ptr(glogits), _stream(prob)), "ls_backward")
+        return gfeat, glogits, None, None, None, None, None
 
 
 def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, t: torch.Tensor,
-               frustum: torch.Tensor, grid: GridSpec) -> Tuple[torch.Tensor, torch.Tensor]:
+               frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
     """feat [B*N,C,fh,fw], depth_logits [B*N,D,fh,fw] (CamEncoder outputs,
     model/cam_encoder.py:102-111), M [B,N,3,3], t [B,N,3], frustum [D,fh,fw,3] ->
-    (bev f32[B,C,X,Y], depth_prob [B*N,D,fh,fw])."""
+    (bev f32[B,C,X,Y] in ``bev_format``, depth_prob [B*N,D,fh,fw])."""
     B, N = M.shape[:2]
     bn, Cc, fh, fw = feat.shape
     D = depth_logits.shape[1]
@@ -260,4 +314,4 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
     if tuple(frustum.shape) != (D, fh, fw, 3):
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
     shape = make_shape(B, N, D, fh, fw, Cc, grid)
-    return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape)
+    return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format)

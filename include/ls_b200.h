@@ -50,10 +50,24 @@ typedef struct LsShape {
   float res[3];        /* bev_res                                               */
 } LsShape;
 
-/* Element strides of the BEV tensor [B, C, X, Y] (Y stride must be 1). */
+/* Element strides of a BEV tensor of logical shape [B, C, X, Y] (the reference's bev_feature,
+ * model/bev_model.py:76,105, and the gradient arriving on it).  Two families are accepted:
+ *   y == 1  "NCHW"        - the reference's own layout (and channel-slice views of it, e.g. the
+ *                           gradient torch.cat's backward hands back, model/parking_model.py:45);
+ *   c == 1  "channels-last" - torch.channels_last storage [B, X, Y, C] (and channel-slice views of
+ *                           it: y >= C).  The splat accumulates cell rows, so this is the layout
+ *                           it writes with one bulk (TMA) store per tile, and the layout whose
+ *                           gradient the backward gathers from directly (no staging pass).
+ * Anything else is LS_ERR_UNSUPPORTED (make the tensor contiguous in one of the two first). */
 typedef struct LsBevStrides {
-  int64_t b, c, x;
+  int64_t b, c, x, y;
 } LsBevStrides;
+
+/* Memory layout of the per-camera feature maps handed to ls_forward / returned by ls_backward. */
+typedef enum LsFeatLayout {
+  LS_FEAT_NCHW = 0,   /* [B*N, C, fh, fw] contiguous, as CamEncoder returns them (model/cam_encoder.py:102-111) */
+  LS_FEAT_NHWC = 1    /* torch.channels_last storage [B*N, fh, fw, C]; needs C % 4 == 0 (no staging copies) */
+} LsFeatLayout;
 
 const char* ls_version(void);
 const char* ls_strerror(int status);
@@ -107,9 +121,9 @@ int ls_export_indices(const float* M, const float* t, const float* frustum, cons
  * splat's CTAs), then every
  * kept point writes an 8-byte record {key, prob bits} to recs[B,Npts] at
  * seg_start[cell] + within;  key = cell_in_tile << 24 | (pixel << ceil(log2 D) | d).
-* pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {cell * Cp * 4 (byte offset of the cell's row in
- * the cell-major gradient; cell = cells_padded, the zero row, for a dropped point), prob bits}
- * per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.  prob: [B*N,D,fh,fw] of `dtype`. */
+* pix_recs (may be NULL): i32x2[B*N*fh*fw, D] = {rank gx*Y+gy of the point's cell (X*Y for a dropped
+ * point), prob bits} per depth bin of every pixel, pixel-major - the index ls_splat_bwd walks.
+ * prob: [B*N,D,fh,fw] of `dtype`. */
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob,
             int dtype, const LsShape* s, int32_t* seg_start, int32_t* tile_order,
             int32_t* tile_scratch /* i32[B,tiles] or NULL: enables the parallel scan */, void* recs,
@@ -148,10 +162,11 @@ int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32
  * backward of the outer product: every kept point receives its cell's gradient;
  *   grad_prob[p]      = sum_c feat[pix,c] * g[c, cell(p)]
  *   grad_feat[pix, c] = sum_d prob[d,pix] * g[c, cell(d,pix)]      (pixel-stationary,
- * no atomics, fixed order).  grad_bev f32 [B,C,X,Y] with strides; gT_ws
- * f32[B,cells_padded+1,Cp] scratch (cell-major gradient, last row of each sample zero); outputs grad_prob_pm
- * f32[B*N*fh*fw, D] (PIXEL-major, consumed by ls_softmax_bwd) and grad_feat_nhwc
- * [B*N,fh,fw,Cp] of `dtype`. */
+ * no atomics, fixed order).  grad_bev f32 [B,C,X,Y] with strides: a channels-last gradient
+ * (c stride 1, x stride == Y * y stride, C % 4 == 0) is gathered in place; an NCHW one (y stride 1)
+ * is first staged as cell rows into gT_ws f32[B, X*Y+1, Cp] (may be NULL for channels-last).
+ * Outputs grad_prob_pm f32[B*N*fh*fw, D] (PIXEL-major, consumed by ls_softmax_bwd) and
+ * grad_feat_nhwc [B*N,fh,fw,Cp] of `dtype`. */
 int ls_splat_bwd(const float* grad_bev, const LsBevStrides* grad_strides, const void* feat_nhwc,
                  int dtype, const void* pix_recs, const int32_t* seg_start, const LsShape* s,
                  float* gT_ws, float* grad_prob_pm, void* grad_feat_nhwc, ls_stream_t stream);
@@ -163,24 +178,30 @@ int ls_softmax_bwd(const void* prob, const float* grad_prob_pm, const void* grad
                    const LsShape* s, void* grad_logits, ls_stream_t stream);
 
 /* ---- one-call pipelines (what BevModel.calc_bev_feature uses) -------------------
- * Workspace: one device blob, >= ls_workspace_bytes(); it carries what backward needs
- * (NHWC features, CSR offsets, pixel-major index), so keep it alive and untouched between
- * ls_forward(with_backward=1) and ls_backward of the same step. */
-size_t ls_workspace_bytes(const LsShape* s, int dtype, int with_backward);
+ * Two device blobs:
+ *   scratch  transient, >= ls_scratch_bytes(); free for other use as soon as the call's kernels
+ *            have run (the Python side keeps one per stream and reuses it for every call);
+ *   saved    >= ls_saved_bytes(); what ls_backward needs from ls_forward (NHWC feature copy for
+ *            NCHW inputs, CSR offsets, pixel-major index): keep it untouched until ls_backward
+ *            of the same step.  Pass NULL/0 to ls_forward for inference (no backward state). */
+size_t ls_scratch_bytes(const LsShape* s, int dtype, int with_backward);
+size_t ls_saved_bytes(const LsShape* s, int dtype, int feat_layout);
 
-/* feat [B*N,C,fh,fw], logits [B*N,D,fh,fw] of `dtype` (contiguous NCHW, as CamEncoder
- * returns them, model/cam_encoder.py:102-111); M/t from ls_camera_transform or from the
- * caller's own torch.inverse; frustum f32[D,fh,fw,3] (BevModel.frustum).
- * Outputs: bev f32[B,C,X,Y] (strided), prob [B*N,D,fh,fw] of `dtype` (= pred_depth). */
-int ls_forward(const void* feat, const void* logits, int dtype, const float* M, const float* t,
-               const float* frustum, const LsShape* s, void* ws, size_t ws_bytes, int with_backward,
-               float* bev, const LsBevStrides* bev_strides, void* prob, ls_stream_t stream);
+/* feat [B*N,C,fh,fw] in `feat_layout` (LsFeatLayout), logits [B*N,D,fh,fw] contiguous, both of
+ * `dtype`, as CamEncoder returns them (model/cam_encoder.py:102-111); M/t from
+ * ls_camera_transform or from the caller's own torch.inverse; frustum f32[D,fh,fw,3]
+ * (BevModel.frustum).  Outputs: bev f32[B,C,X,Y] (strided, see LsBevStrides), prob
+ * [B*N,D,fh,fw] of `dtype` (= pred_depth). */
+int ls_forward(const void* feat, int feat_layout, const void* logits, int dtype, const float* M, const float* t,
+               const float* frustum, const LsShape* s, void* scratch, size_t scratch_bytes, void* saved,
+               size_t saved_bytes, float* bev, const LsBevStrides* bev_strides, void* prob, ls_stream_t stream);
 
-/* grad_bev f32 (strided), grad_prob_ext (`dtype`, may be NULL), prob = forward's output.
- * Outputs grad_feat [B*N,C,fh,fw], grad_logits [B*N,D,fh,fw] of `dtype`. */
-int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext,
-                const void* prob, int dtype, const LsShape* s, void* ws, size_t ws_bytes,
-                void* grad_feat, void* grad_logits, ls_stream_t stream);
+/* grad_bev f32 (strided), grad_prob_ext (`dtype`, may be NULL), prob = forward's output, feat =
+ * forward's input (read only when feat_layout == LS_FEAT_NHWC: no copy of it was saved).
+ * Outputs grad_feat [B*N,C,fh,fw] in `feat_layout`, grad_logits [B*N,D,fh,fw] of `dtype`. */
+int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext, const void* prob,
+                const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch, size_t scratch_bytes,
+                const void* saved, size_t saved_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream);
 
 /* Developer aid: per-phase clock64 totals of ls_splat_fwd (summed over CTAs) since the last
  * call; LS_ERR_UNSUPPORTED unless the library was built with -DLS_PROFILE. */

@@ -32,6 +32,22 @@ def relerr(a, b) -> float:
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
+def maxerr(a, b) -> float:
+    """Largest element-wise error relative to the largest reference magnitude:
+    max|a-b| / max|b| (float64).  One wrong voxel out of millions passes a Frobenius bound;
+    it does not pass this one."""
+    a = np.asarray(a.detach().cpu().float() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().float() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def assert_close(a, b, tol, what=""):
+    """Frobenius-relative AND max-element-wise (relative to max|b|) error within tol."""
+    e, m = relerr(a, b), maxerr(a, b)
+    assert e <= tol, "%s: Frobenius-relative error %.3g > %.3g" % (what, e, tol)
+    assert m <= tol, "%s: max element-wise error %.3g (of max|ref|) > %.3g" % (what, m, tol)
+
+
 class Golden:
     """One fixture frozen from the unmodified reference (tests/golden/make_golden.py)."""
 

@@ -46,20 +46,33 @@ def test_abi_argument_checking(lib):
     from e2e_parking_carla_b200 import lift_splat as ls
     grid = ls.GridSpec((-9.95, -9.95, 0.0), (0.1, 0.1, 20.0), (200, 200, 1))
     s = ls.make_shape(1, 4, 48, 32, 32, 64, grid)
+    dummy16 = C.c_void_p(16)
     tiles, cells, stride = ls.grid_cells(s)
     tile_cells = cells // tiles
     assert tile_cells in (128, 256)
     assert tiles * tile_cells == cells >= 200 * 200 and stride == cells + 4
     assert ls.padded_channels(6) == 8 and ls.padded_channels(64) == 64
-    assert ls.workspace_bytes(s, ls.LS_F32, True) > ls.workspace_bytes(s, ls.LS_F32, False) > 0
+    assert ls.scratch_bytes(s, ls.LS_F32, True) > ls.scratch_bytes(s, ls.LS_F32, False) > 0
+    # backward state: a channels_last feature map is consumed in place, so less is saved
+    assert ls.saved_bytes(s, ls.LS_F32, ls.LS_FEAT_NCHW) > ls.saved_bytes(s, ls.LS_F32, ls.LS_FEAT_NHWC) > 0
     # null pointers
     assert lib.ls_camera_transform(None, None, 4, None, None, None) == -1
     assert lib.ls_index(None, None, None, C.byref(s), None, None, None, None, None) == -1
     # Z != 1 is unsupported for the splat (reference squeezes Z, model/bev_model.py:104)
     bad = ls.make_shape(1, 4, 48, 32, 32, 64, ls.GridSpec(grid.start, grid.res, (200, 200, 2)))
-    assert lib.ls_workspace_bytes(C.byref(bad), ls.LS_F32, 1) == 0
+    assert lib.ls_scratch_bytes(C.byref(bad), ls.LS_F32, 1) == 0
     with pytest.raises(ValueError):
-        ls.workspace_bytes(bad, ls.LS_F32, True)
+        ls.scratch_bytes(bad, ls.LS_F32, True)
+    # limits of the placement kernel are reported up front, not in the middle of ls_forward
+    deep = ls.make_shape(1, 4, 192, 32, 32, 64, grid)
+    assert lib.ls_scratch_bytes(C.byref(deep), ls.LS_F32, 1) == 0
+    assert lib.ls_scratch_bytes(C.byref(ls.make_shape(1, 4, 191, 8, 8, 64, grid)), ls.LS_F32, 1) > 0
+    # channels_last features need whole 16-byte channel quads
+    assert lib.ls_saved_bytes(C.byref(ls.make_shape(1, 4, 48, 32, 32, 6, grid)), ls.LS_F32, ls.LS_FEAT_NHWC) == 0
+    # BEV strides: neither NCHW-like (y == 1) nor channels-last-like (c == 1) is refused
+    odd = ls.LsBevStrides(64 * 200 * 200, 2, 200 * 128, 128)
+    assert lib.ls_forward(dummy16, 0, dummy16, 0, dummy16, dummy16, dummy16, C.byref(s), dummy16, 1 << 40, None, 0,
+                          dummy16, C.byref(odd), dummy16, None) == -2
     # unknown dtype code
     dummy = C.c_void_p(16)
     assert lib.ls_softmax(dummy, 7, C.byref(s), dummy, None) == -1

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import GOLDEN_SHAPES, Golden, frustum_of, grid_of, relerr, sha
+from _util import GOLDEN_SHAPES, Golden, assert_close, frustum_of, grid_of, maxerr, relerr, sha
 from e2e_parking_carla_b200.synthetic import (LiftSplatShape, make_cfg, make_encoder_outputs, make_rig,
                                               make_upstream_grads)
 
@@ -137,12 +137,10 @@ def test_sorted_ranks_bit_exact(lib, name):
         assert np.array_equal(np.sort(p), np.nonzero(r >= 0)[0])
         w = recs[b, :kept[b], 1].cpu().numpy().view(np.float32)
         assert np.array_equal(w, prob.view(sh.batch, -1)[b].cpu().numpy()[p])
-    # pixel-major index: {cell, prob} of every depth bin of every pixel
-    row_bytes = ls.padded_channels(sh.channels) * 4
-    assert bool((pix[..., 0] % row_bytes == 0).all())
-    pc = (pix[..., 0] // row_bytes).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
-    cells_padded = ls.grid_cells(s)[1]
-    assert torch.equal(pc, torch.where(cell >= 0, cell, torch.full_like(cell, cells_padded)))   # dropped -> zero row
+    # pixel-major index: {rank of the cell (X*Y when dropped), prob} of every depth bin of every pixel
+    xy = int(s.X) * int(s.Y)
+    pc = pix[..., 0].view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2).reshape(sh.batch, -1)
+    assert torch.equal(pc, torch.where(rank >= 0, rank, torch.full_like(rank, xy)))   # dropped -> one past the grid
     pw = pix[..., 1].contiguous().view(torch.float32).view(sh.batch, sh.cams, hw, D).permute(0, 1, 3, 2)
     assert torch.equal(pw.reshape(-1), prob.view(sh.batch, sh.cams, D, hw).reshape(-1))
 
@@ -179,15 +177,20 @@ def test_rig_a_end_to_end_indices_match_reference(lib):
 # ------------------------------------------------------------------------------------
 # forward / backward values
 # ------------------------------------------------------------------------------------
-def _run(shape, feat, logits, M, t, gb=None, gp=None, dtype=torch.float32):
+def _run(shape, feat, logits, M, t, gb=None, gp=None, dtype=torch.float32, bev_format=torch.contiguous_format,
+         feat_format=torch.contiguous_format):
+    """One forward (+ backward) through the autograd function.  ``bev_format`` is the memory
+    format of the BEV output AND of the upstream gradient handed to backward (torch.autograd
+    delivers exactly the tensor given to torch.autograd.backward)."""
     ls = _ls()
-    feat = feat.to(DEV, dtype).requires_grad_(gb is not None)
+    feat = feat.to(DEV, dtype).contiguous(memory_format=feat_format).requires_grad_(gb is not None)
     logits = logits.to(DEV, dtype).requires_grad_(gb is not None)
-    bev, prob = ls.lift_splat(feat, logits, _dev(M), _dev(t), _dev(frustum_of(shape)), _grid_spec(shape))
+    bev, prob = ls.lift_splat(feat, logits, _dev(M), _dev(t), _dev(frustum_of(shape)), _grid_spec(shape), bev_format)
+    assert bev.is_contiguous(memory_format=bev_format)
     out = {"bev": bev.detach(), "prob": prob.detach()}
     if gb is not None:
-        loss = (bev * gb.to(DEV)).sum() + (prob.float() * gp.to(DEV).float()).sum()
-        loss.backward()
+        g_bev = gb.to(DEV).contiguous(memory_format=bev_format)
+        torch.autograd.backward([bev, prob], [g_bev, gp.to(DEV, prob.dtype)])
         out["grad_feat"], out["grad_logits"] = feat.grad, logits.grad
     return out
 
@@ -531,3 +534,198 @@ def test_many_tiles_single_cta_scan(lib):
     assert relerr(out["bev"], bev_o) <= FP32_TOL
     assert relerr(out["grad_feat"], gf_o) <= FP32_TOL
     assert relerr(out["grad_logits"], gl_o) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------
+# round 2: layouts (channels_last BEV / gradient / features), real channel counts in bf16,
+# C > 64, the stress grid at C = 64, full-size values, max element-wise bounds
+# ------------------------------------------------------------------------------------
+def _oracle_case(shape, rig_seed, in_seed, relu=True):
+    """Inputs + numpy-oracle outputs (exact float64 segment sums) for one configuration."""
+    from oracle import lift_splat_oracle as lo
+    intr, extr = make_rig(shape.batch, shape.cams, jitter=True, seed=rig_seed)
+    feat, logits = make_encoder_outputs(shape, seed=in_seed, relu=relu)
+    gb, gp = make_upstream_grads(shape, seed=in_seed)
+    res, start, dim = grid_of(shape)
+    gb = gb[:, :, :int(dim[0]), :int(dim[1])].contiguous()
+    M, t = lo.camera_transform(intr.numpy(), extr.numpy())
+    _, _, rank = lo.voxel_index(lo.geometry(M, t, frustum_of(shape)), start, res, dim)
+    return {"feat": feat, "logits": logits, "gb": gb, "gp": gp, "M": M, "t": t, "rank": rank, "dim": dim}
+
+
+def _oracle_outputs(shape, c, dtype=torch.float32):
+    """The oracle on the values the kernels actually see (inputs rounded to ``dtype`` first)."""
+    from oracle import lift_splat_oracle as lo
+    f = c["feat"].to(dtype).float().numpy()
+    z = c["logits"].to(dtype).float().numpy()
+    gp = c["gp"].to(dtype).float().numpy()
+    bev_o, prob_o = lo.splat_forward(f, z, c["rank"], c["dim"], shape.cams)
+    gf_o, gl_o = lo.splat_backward(f, z, c["rank"], c["dim"], shape.cams, c["gb"].numpy(), gp)
+    return {"bev": bev_o, "prob": prob_o, "grad_feat": gf_o, "grad_logits": gl_o}
+
+
+def _check_all(out, ref, tol, prob_tol=None):
+    assert_close(out["bev"], ref["bev"], tol, "bev")
+    assert_close(out["prob"], ref["prob"], prob_tol or tol, "prob")
+    assert_close(out["grad_feat"], ref["grad_feat"], tol, "grad_feat")
+    assert_close(out["grad_logits"], ref["grad_logits"], tol, "grad_logits")
+    assert np.array_equal(out["bev"].cpu().numpy() == 0, ref["bev"] == 0) or tol > 1e-4, "zero pattern"
+
+
+@pytest.mark.parametrize("channels", [64, 16, 6])
+def test_channels_last_bev_bit_identical_to_nchw(lib, channels):
+    """channels_last BEV output + channels_last gradient (the splat's native layout: bulk tile
+    stores forward, gradient rows gathered in place backward) give the SAME BITS as the
+    reference's NCHW layout.  C=64: bulk-store kernel + 16-byte row gathers; C=16: row-store
+    kernel; C=6: channels_last output, gradient falls back to the staged path."""
+    shape = LiftSplatShape(batch=2, channels=channels)
+    c = _oracle_case(shape, rig_seed=41, in_seed=13)
+    a = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
+    b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], bev_format=torch.channels_last)
+    assert b["bev"].stride(1) == 1 and a["bev"].stride(3) == 1
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    _check_all(b, _oracle_outputs(shape, c), FP32_TOL, 1e-6)
+
+
+def test_channels_last_gradient_slice_of_65_channels(lib):
+    """Downstream of a channels_last torch.cat with the target channel (model/parking_model.py:45)
+    the gradient is a 64-channel slice of a [B,X,Y,65] tensor: rows 260 bytes apart, not 16-byte
+    aligned -> the scalar in-place gather.  Also the forward writing INTO such a slice."""
+    ls = _ls()
+    shape = LiftSplatShape(batch=2, channels=64)
+    c = _oracle_case(shape, rig_seed=42, in_seed=14)
+    a = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
+    f = c["feat"].to(DEV).requires_grad_(True)
+    z = c["logits"].to(DEV).requires_grad_(True)
+    bev, prob = ls.lift_splat(f, z, _dev(c["M"]), _dev(c["t"]), _dev(frustum_of(shape)), _grid_spec(shape),
+                              torch.channels_last)
+    wide = torch.cat([bev, torch.zeros(2, 200, 200, 1, device=DEV).permute(0, 3, 1, 2)], dim=1)
+    assert wide.is_contiguous(memory_format=torch.channels_last)
+    gwide = torch.cat([c["gb"].to(DEV), torch.ones(2, 1, 200, 200, device=DEV)], dim=1).contiguous(
+        memory_format=torch.channels_last)
+    torch.autograd.backward([wide, prob], [gwide, c["gp"].to(DEV)])
+    assert torch.equal(f.grad, a["grad_feat"]) and torch.equal(z.grad, a["grad_logits"])
+    # forward straight into channels 0..63 of a 65-channel channels_last buffer (row-store kernel)
+    buf = torch.full((2, 65, 200, 200), -7.0, device=DEV).contiguous(memory_format=torch.channels_last)
+    s = _ls_shape(shape)
+    prob2 = torch.empty_like(prob)
+    scratch = ls.scratch_for(ls.scratch_bytes(s, ls.LS_F32, False), torch.device(DEV))
+    view = buf[:, :64]
+    st = ls._bev_strides(view)
+    assert (st.c, st.y) == (1, 65)
+    import ctypes as C
+    from e2e_parking_carla_b200 import _lib
+    P = lambda x: C.c_void_p(x.data_ptr())
+    fr = _dev(frustum_of(shape))
+    Md, td = _dev(c["M"]), _dev(c["t"])
+    ls.check(_lib.load().ls_forward(P(f.detach()), ls.LS_FEAT_NCHW, P(z.detach()), ls.LS_F32, P(Md), P(td), P(fr),
+                                    C.byref(s), P(scratch), scratch.numel(), None, 0, P(view), C.byref(st), P(prob2),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ls_forward")
+    assert torch.equal(buf[:, :64], a["bev"]) and bool((buf[:, 64] == -7.0).all())
+
+
+def test_channels_last_features_in_place(lib):
+    """A channels_last feature map (what a channels_last CamEncoder emits) is consumed without the
+    NHWC staging copy and its gradient comes back channels_last - same bits as the NCHW route."""
+    shape = LiftSplatShape(batch=2, channels=64)
+    c = _oracle_case(shape, rig_seed=43, in_seed=15)
+    for dtype in (torch.float32, torch.bfloat16):
+        a = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype)
+        b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
+                 bev_format=torch.channels_last, feat_format=torch.channels_last)
+        assert b["grad_feat"].is_contiguous(memory_format=torch.channels_last)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (k, dtype)
+
+
+@pytest.mark.parametrize("bev_format", [torch.contiguous_format, torch.channels_last])
+def test_bf16_real_channel_count_vs_oracle(lib, bev_format):
+    """bf16 at C=64 on the jittered rig, B=2, forward + backward <= 2e-2 (north_star) against the
+    float64 oracle - the kernels bench.py --dtype bf16 times (ls_splat_fwd_kernel<bf16,...,64>,
+    every lane of ls_bwd_gather_occ_kernel<bf16>)."""
+    shape = LiftSplatShape(batch=2, channels=64)
+    c = _oracle_case(shape, rig_seed=44, in_seed=16)
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=torch.bfloat16,
+               bev_format=bev_format)
+    assert out["bev"].dtype == torch.float32 and out["grad_feat"].dtype == torch.bfloat16
+    # against the oracle on the original float32 inputs: the north_star bound
+    _check_all(out, _oracle_outputs(shape, c), BF16_TOL)
+    # against the oracle on the bf16-rounded inputs the error is the kernels' own: prob is
+    # rounded to bf16 once (2^-9), everything is accumulated in float32
+    ref = _oracle_outputs(shape, c, torch.bfloat16)
+    assert relerr(out["bev"], ref["bev"]) <= 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stress_grid_real_channel_count_vs_oracle(lib, dtype):
+    """BASELINE.json configs[3] geometry (6 cameras, 96 depth bins, 400x400 at 0.05 m) at C=64,
+    B=2, against the numpy oracle: placement with 6 bins per thread, 1 600 tiles, 590 k points."""
+    from oracle import lift_splat_oracle as lo
+    shape = LiftSplatShape.stress(batch=2)
+    assert shape.channels == 64 and shape.cams == 6 and shape.depth_bins == 96
+    c = _oracle_case(shape, rig_seed=45, in_seed=17)
+    ls = _ls()
+    r = ls.index(_dev(c["M"]), _dev(c["t"]), _dev(frustum_of(shape)), _ls_shape(shape)).cpu().numpy()
+    assert np.array_equal(r, c["rank"].astype(np.int32))
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
+               bev_format=torch.channels_last)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    _check_all(out, _oracle_outputs(shape, c), tol, 1e-6 if dtype == torch.float32 else None)
+    if dtype == torch.float32:
+        nchw = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
+        for k in out:
+            assert torch.equal(out[k], nchw[k]), k
+
+
+@pytest.mark.parametrize("channels,dtype", [(96, torch.float32), (128, torch.float32), (256, torch.float32),
+                                            (130, torch.float32), (128, torch.bfloat16)])
+def test_more_than_64_channels(lib, channels, dtype):
+    """C > 64: the splat's channel-chunk loop (tile re-zeroed per 64-channel pass) and the
+    2-/3-/4-chunk gradient gathers, in both BEV layouts."""
+    shape = LiftSplatShape(batch=1, channels=channels)
+    c = _oracle_case(shape, rig_seed=46, in_seed=18)
+    ref = _oracle_outputs(shape, c)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    a = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype)
+    _check_all(a, ref, tol, 1e-6 if dtype == torch.float32 else None)
+    b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
+             bev_format=torch.channels_last)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_more_than_256_channels_rejected(lib):
+    ls = _ls()
+    with pytest.raises(ValueError):
+        ls.scratch_bytes(_ls_shape(LiftSplatShape(batch=1, channels=260)), ls.LS_F32, True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_many_depth_bins_serial_softmax(lib, dtype):
+    """D = 130 > 128: the one-thread-per-pixel softmax forward/backward kernels, placement with
+    9 bins per thread, D not a multiple of 16 in the gather."""
+    shape = LiftSplatShape(batch=1, cams=2, channels=8, d_bound=[0.5, 13.5, 0.1], final_dim=[64, 96])
+    assert shape.depth_bins == 130
+    c = _oracle_case(shape, rig_seed=47, in_seed=19)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype)
+    _check_all(out, _oracle_outputs(shape, c), tol, 1e-6 if dtype == torch.float32 else None)
+
+
+def test_full_size_values_on_sampled_batch_indices(lib):
+    """BASELINE.json configs[1] at its full size (B=16, C=64): the BEV features and gradients of
+    three batch indices against the oracle's values (the rest of the batch is covered by the
+    properties of test_full_size_properties)."""
+    shape = LiftSplatShape(batch=16, channels=64)
+    c = _oracle_case(shape, rig_seed=1, in_seed=20)
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], bev_format=torch.channels_last)
+    n = shape.cams
+    one = LiftSplatShape(batch=1, channels=64)
+    for b in (0, 7, 15):
+        sub = {"feat": c["feat"][b * n:(b + 1) * n], "logits": c["logits"][b * n:(b + 1) * n],
+               "gb": c["gb"][b:b + 1], "gp": c["gp"][b * n:(b + 1) * n], "rank": c["rank"][b:b + 1], "dim": c["dim"]}
+        ref = _oracle_outputs(one, sub)
+        got = {"bev": out["bev"][b:b + 1], "prob": out["prob"][b * n:(b + 1) * n],
+               "grad_feat": out["grad_feat"][b * n:(b + 1) * n], "grad_logits": out["grad_logits"][b * n:(b + 1) * n]}
+        _check_all(got, ref, FP32_TOL, 1e-6)
