@@ -140,31 +140,52 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle/torch_port.py) on the host cores
+# reference arm: the reference's own torch algorithm on the host cores (or, as a separate
+# key, on the same GPU).  The unmodified reference when its tree is present (this container:
+# /root/reference; a driver-provided baseline/_ref), else its port oracle/torch_port.py.
 # --------------------------------------------------------------------------------------
-def cpu_reference_run(shape: LiftSplatShape, sample_batch: int, steps: int, warmup: int, dtype):
+def reference_run(shape: LiftSplatShape, sample_batch: int, steps: int, warmup: int, device: str = "cpu"):
+    from e2e_parking_carla_b200.synthetic import make_cfg
     from oracle import lift_splat_oracle as lo
+    from oracle import ref_harness as rh
     from oracle import torch_port as tp
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    dev = torch.device(device)
     sub = LiftSplatShape(**{**shape.__dict__, "batch": sample_batch})
     intr, extr = make_rig(sample_batch, sub.cams, jitter=True, seed=1)
     feat, logits = make_encoder_outputs(sub, seed=0)
     gb, gp = make_upstream_grads(sub, seed=0)
     res, start, dim = lo.bev_grid_params(sub.bev_x_bound, sub.bev_y_bound, sub.bev_z_bound)
     fr = torch.from_numpy(lo.create_frustum(sub.d_bound, sub.final_dim, sub.bev_down_sample))
-    a = (feat, logits, intr, extr, fr, torch.from_numpy(start), torch.from_numpy(res), torch.from_numpy(dim), gb, gp)
+    if rh.available():
+        kind, impl = "reference", "the UNMODIFIED reference BevModel (%s) through oracle/ref_harness.py" % rh.reference_root()
+        ref_step = rh.reference_stepper(make_cfg(sub))
+        a = tuple(x.to(dev) for x in (feat, logits, intr, extr, gb, gp))
+        step = lambda: ref_step(*a)
+    else:
+        kind, impl = "port", "the reference's own aten op chain restated in oracle/torch_port.py"
+        a = tuple(x.to(dev) for x in (feat, logits, intr, extr, fr, torch.from_numpy(start), torch.from_numpy(res),
+                                      torch.from_numpy(dim), gb, gp))
+        step = lambda: tp.fwd_bwd_step(*a)
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+
     for _ in range(warmup):
-        tp.fwd_bwd_step(*a)
+        step()
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
-        tp.fwd_bwd_step(*a)
+        step()
+    sync()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": sample_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d step(s) of fwd+bwd on a %d-sample slice of the workload, torch %s CPU ops (the "
-                      "reference's own aten op chain, oracle/torch_port.py), %d threads"
-                      % (steps, sample_batch, torch.__version__, threads),
-            "ms_per_step": dt * 1e3}
+    where = ("%d host threads" % threads) if dev.type == "cpu" else "torch CUDA ops on the same GPU (its per-sample host syncs included)"
+    return {"value": sample_batch / dt, "unit": UNIT, "cores": threads if dev.type == "cpu" else 0, "kind": kind,
+            "sample": "%d step(s) of fwd+bwd on %d sample(s) of the workload (%s), torch %s, %s"
+                      % (steps, sample_batch, impl, torch.__version__, where),
+            "ms_per_step": dt * 1e3, "batch": sample_batch, "device": dev.type}
 
 
 # --------------------------------------------------------------------------------------
@@ -401,6 +422,74 @@ class Stepper:
         return {n: v / steps for n, v in acc.items()}
 
 
+def main_model_workloads(args):
+    """--workload train (BASELINE.json configs[2]) and --workload agent (configs[4]): the lift-splat library
+    inside a stock-PyTorch stand-in for the rest of ParkingModel (harness/parking_stack.py).
+    --impl reference swaps the library for the reference's own torch op chain on the same GPU(s)."""
+    from harness import run as hr
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload %s needs a CUDA device" % args.workload)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    ls_impl = "torch" if args.impl == "reference" else "b200"
+    sampler = ClockSampler(local)
+    from e2e_parking_carla_b200 import _lib
+    lib = _lib.load() if ls_impl == "b200" else None
+    l0 = lib.ls_launch_count() if lib else 0
+    if args.workload == "train":
+        if rank == 0:
+            sampler.start()
+        r = hr.train_benchmark(args.train_batch, args.steps, max(3, args.warmup), rank, world, device, ls_impl,
+                               channels_last=not args.no_channels_last)
+        if rank == 0:
+            line = {"metric": "train_samples_per_s", "value": r["samples_per_s"], "unit": UNIT, "n_gpus": world,
+                    "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 convolutions: torch default)",
+                    "data": "synthetic",
+                    "config": {"workload": "full ParkingModel training step (stand-in camera encoder + lift-splat + BEV encoder + "
+                                           "fusion transformer + control decoder + seg head, 3 losses, Adam), per-GPU batch %d, "
+                                           "DDP over NCCL (BASELINE.json configs[2])" % args.train_batch,
+                               "per_gpu_batch": args.train_batch, "global_batch": args.train_batch * world,
+                               "parallelism": "ddp%d (gradient all-reduce %.1f MB/step, gradient_as_bucket_view, static_graph)"
+                                              % (world, r["allreduce_bytes_per_step"] / 1e6),
+                               "lift_splat": "libls_b200.so" if ls_impl == "b200" else "reference torch op chain (oracle/torch_port.py) on the GPU",
+                               "channels_last": r["channels_last"], "trainable_params": r["trainable_params"],
+                               "l2": "inputs and activations (>1 GB per step) far exceed the 126 MB L2"},
+                    "e2e": {"value": r["e2e_samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                            "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"],
+                            "what": "batch dict copied from pinned host memory every step, loss.item() read back"},
+                    "gpu_launches": int(lib.ls_launch_count() - l0) if lib else 0, "loss": r["loss"],
+                    "clocks": sampler.stop()}
+            if args.impl == "reference":
+                line["impl"] = "reference"
+            print(json.dumps(line))
+    else:
+        if rank != 0:
+            return
+        sampler.start()
+        r = hr.agent_benchmark(max(50, args.steps if args.steps != 50 else 1000), 50, device, ls_impl)
+        best = r.get("graph", r["stream"])
+        line = {"metric": "agent_step_latency_ms_p50", "value": best["wall_ms"]["p50"], "unit": "ms", "n_gpus": 1,
+                "steps": r["iters"], "warmup": r["warmup"], "ms_per_step": best["wall_ms"]["mean"],
+                "higher_is_better": False, "scaling": "replicas only", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "closed-loop agent step without CARLA: ParkingModel.predict (encoder + 3 decode steps) "
+                                       "+ on-device next-target centroid, batch 1, 4 cameras (BASELINE.json configs[4])",
+                           "lift_splat": "libls_b200.so" if ls_impl == "b200" else "reference torch op chain on the GPU",
+                           "published_context": "74.92 ms on a Quadro RTX 5000 (paper, whole reference model)"},
+                "latency": r, "gpu_launches": int(lib.ls_launch_count() - l0) if lib else 0, "clocks": sampler.stop()}
+        if args.impl == "reference":
+            line["impl"] = "reference"
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,19 +497,33 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "stress"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "stress", "train", "agent"],
+                    help="cfg2 / stress: the lift-splat hot path (BASELINE.json configs[1] / [3]); train: full "
+                         "ParkingModel training step under DDP (configs[2]); agent: closed-loop predict() latency "
+                         "(configs[4])")
+    ap.add_argument("--train-batch", type=int, default=12, help="per-GPU batch of the training step (config/training.yaml:12)")
+    ap.add_argument("--no-channels-last", action="store_true", help="train/agent: keep the conv stacks and the BEV NCHW")
+    ap.add_argument("--no-train", action="store_true", help="skip the short `train` measurement appended to the default line")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--bev-format", default="channels_last", choices=["channels_last", "nchw"],
                     help="memory format of the BEV output and of the gradient arriving on it")
     ap.add_argument("--feat-format", default="nchw", choices=["channels_last", "nchw"],
                     help="memory format of the encoder's feature maps (and of their gradient)")
-    ap.add_argument("--cpu-batch", type=int, default=4, help="samples in the bounded CPU-baseline slice")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="samples per step of the CPU reference (default: the whole per-GPU batch under "
+                         "--impl reference, a 4-sample slice for the cpu_baseline key of our arm)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: run the reference's torch ops on the host cores (default, the "
+                         "contract) or on the GPU")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the gpu_reference key of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step kernel by kernel instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.workload in ("train", "agent"):
+        return main_model_workloads(args)
     shape = workload(args)
     dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     s_in = 4 if args.dtype == "fp32" else 2
@@ -441,7 +544,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference_run(shape, args.cpu_batch, max(1, args.steps), max(1, min(args.warmup, 2)), dtype)
+        rb = args.cpu_batch or shape.batch          # the whole batch of the workload: same config as our arm
+        cb = reference_run(shape, rb, max(1, args.steps), max(1, min(args.warmup, 2)), args.ref_device)
+        config["reference_batch"] = rb
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -565,8 +670,16 @@ def main():
                 "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": step_gbs / peak},
                 "stage_ms": stages, "clocks": clocks}
+        if not args.no_gpu_reference:
+            # the reference's torch op chain on THIS GPU, full batch, its host syncs included (SURVEY.md 8d
+            # "GPU reference (the real bar)"); context for `value`, like cpu_baseline
+            del st
+            torch.cuda.empty_cache()
+            gr = reference_run(shape, shape.batch, 3, 2, "cuda")
+            line["gpu_reference"] = {k: gr[k] for k in ("value", "unit", "kind", "sample", "ms_per_step")}
+            line["gpu_reference"]["speedup_device"] = value / world / gr["value"]
         if not args.no_cpu_baseline:
-            cb = cpu_reference_run(shape, args.cpu_batch, 3, 1, dtype)
+            cb = reference_run(shape, args.cpu_batch or min(4, shape.batch), 3, 1, "cpu")
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if dist is not None:

@@ -9,5 +9,7 @@ Python cannot import a hyphenated name.
 from .bev_model import BevModel, calculate_birds_eye_view_parameters  # noqa: F401
 from . import lift_splat  # noqa: F401  (module: lift_splat.lift_splat(...) is the functional entry point)
 from .lift_splat import GridSpec, LiftSplatFunction  # noqa: F401
+from .depth_loss import DepthLoss  # noqa: F401
+from .target_bev import add_target_bev  # noqa: F401
 
-__all__ = ["BevModel", "calculate_birds_eye_view_parameters", "GridSpec", "LiftSplatFunction", "lift_splat"]
+__all__ = ["BevModel", "calculate_birds_eye_view_parameters", "GridSpec", "LiftSplatFunction", "lift_splat", "DepthLoss", "add_target_bev"]

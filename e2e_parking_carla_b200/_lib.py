@@ -52,6 +52,11 @@ PROTOTYPES = {
     "ls_splat_fwd": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _SH, _P, _ST, _P]),
     "ls_splat_bwd": (C.c_int, [_P, _ST, _P, C.c_int, _P, _P, _SH, _P, _P, _P, _P]),
     "ls_softmax_bwd": (C.c_int, [_P, _P, _P, C.c_int, _SH, _P, _P]),
+    "ls_target_bev": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "ls_depth_loss_ws_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "ls_depth_loss_fwd": (C.c_int, [_P, C.c_int, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_float, _P, _P, C.c_size_t, _P, _P]),
+    "ls_depth_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ls_scratch_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
     "ls_saved_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
     "ls_forward": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _SH, _P, C.c_size_t, _P, C.c_size_t, _P, _ST, _P,

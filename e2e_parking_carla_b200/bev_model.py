@@ -55,10 +55,13 @@ class BevModel(nn.Module):
         when the consumer keeps the format (``add_target_bev`` below, ``F.interpolate``,
         ``conv1`` do) the gradient comes back channels_last and is gathered in place.
         ``torch.contiguous_format`` reproduces the reference's strides (model/bev_model.py:76,105).
+    spare_channels : with channels_last, allocate the BEV as the first C channels of a
+        ``[B, X, Y, C + spare]`` buffer; ``target_bev.add_target_bev`` then writes the target
+        channel (model/parking_model.py:28-46) in place instead of ``torch.cat``-copying the BEV.
     """
 
     def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native",
-                 bev_memory_format=torch.channels_last):
+                 bev_memory_format=torch.channels_last, spare_channels: int = 0):
         super().__init__()
         self.cfg = cfg
         if geometry not in ("native", "torch"):
@@ -67,6 +70,7 @@ class BevModel(nn.Module):
             raise ValueError("bev_memory_format must be torch.channels_last or torch.contiguous_format")
         self.geometry_mode = geometry
         self.bev_memory_format = bev_memory_format
+        self.spare_channels = int(spare_channels)
         if not getattr(cfg, "use_depth_distribution", 1):
             # the reference crashes in this mode too (depth is None at bev_model.py:64)
             raise ValueError("use_depth_distribution=0 is not supported (nor by the reference)")
@@ -155,7 +159,7 @@ class BevModel(nn.Module):
         feat, depth_logits = self.cam_encoder(images.view(b * n, c, h, w))
         M, t = self.camera_transform(intrinsics, extrinsics)
         bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid,
-                                                self.bev_memory_format)
+                                                self.bev_memory_format, self.spare_channels)
         return bev_feature, pred_depth
 
     def forward(self, images, intrinsics, extrinsics):

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libls_b200.so")
-SOURCES = ["ls_index.cu", "ls_dense.cu", "ls_splat.cu", "ls_api.cu"]
+SOURCES = ["ls_index.cu", "ls_dense.cu", "ls_splat.cu", "ls_loss.cu", "ls_api.cu"]
 HEADERS = ["ls_common.cuh", "ls_internal.h", os.path.join(REPO_ROOT, "include", "ls_b200.h")]
 
 NVCC_FLAGS = [

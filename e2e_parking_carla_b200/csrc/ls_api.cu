@@ -335,6 +335,13 @@ int ls_splat_bwd(const float* grad_bev, const LsBevStrides* gst, const void* fea
                               grad_prob_pm, grad_feat_nhwc, (cudaStream_t)stream);
 }
 
+int ls_target_bev(const int32_t* target_pix, int32_t B, int32_t X, int32_t Y, float* out, int64_t stride_b,
+                  int64_t stride_x, int64_t stride_y, ls_stream_t stream) {
+  if (!target_pix || !out || B <= 0 || X <= 0 || Y <= 0) return LS_ERR_BAD_ARG;
+  if ((long long)X * Y >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
+  return ls_launch_target_bev(target_pix, B, X, Y, out, stride_b, stride_x, stride_y, (cudaStream_t)stream);
+}
+
 size_t ls_scratch_bytes(const LsShape* s, int dtype, int with_backward) {
   if (ls_check_splat_shape(s) || !ls_dtype_ok(dtype)) return 0;
   // sized for the layout that needs most (NCHW features and gradients), so one blob serves any call

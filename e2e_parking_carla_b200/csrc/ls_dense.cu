@@ -296,3 +296,40 @@ int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, i
               (__nv_bfloat16*)dst);
   return LS_OK;
 }
+
+// =====================================================================================
+// Target channel of ParkingModel.add_target_bev (model/parking_model.py:28-46): an 8x8 stamp
+// of ones around the (noised) target pixel, zeros elsewhere, written straight into its channel
+// of the BEV tensor (any strides: a [B,1,X,Y] tensor of its own, or channel C of a
+// channels-last [B,X,Y,C+1] buffer whose first C channels the splat wrote) - no torch.zeros,
+// no per-sample python loop, no torch.cat copy of the 10 MB/sample BEV.
+// The slice bounds follow python's semantics exactly (negative starts wrap, then clamp).
+// =====================================================================================
+__device__ __forceinline__ int ls_py_slice_bound(int v, int n) {
+  if (v < 0) v += n;
+  return v < 0 ? 0 : (v > n ? n : v);
+}
+
+__global__ void __launch_bounds__(256)
+ls_target_bev_kernel(const int* __restrict__ pix, int X, int Y, float* __restrict__ out, long long sb, long long sx,
+                     long long sy) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int b = blockIdx.y;
+  const int px = pix[2 * b + 0], py = pix[2 * b + 1];
+  const int x0 = ls_py_slice_bound(px - 4, X), x1 = ls_py_slice_bound(px + 4, X);
+  const int y0 = ls_py_slice_bound(py - 4, Y), y1 = ls_py_slice_bound(py + 4, Y);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < X * Y; i += gridDim.x * blockDim.x) {
+    const int x = i / Y, y = i % Y;
+    const bool in = x >= x0 && x < x1 && y >= y0 && y < y1;
+    out[(size_t)b * sb + (size_t)x * sx + (size_t)y * sy] = in ? 1.0f : 0.0f;
+  }
+}
+
+int ls_launch_target_bev(const int* pix, int B, int X, int Y, float* out, long long sb, long long sx, long long sy,
+                         cudaStream_t s) {
+  const int blocks = (X * Y + 255) / 256;
+  LS_LAUNCH(ls_target_bev_kernel, dim3(blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks), B), dim3(256), 0, s, pix, X, Y,
+            out, sb, sx, sy);
+  return LS_OK;
+}

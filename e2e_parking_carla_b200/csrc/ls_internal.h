@@ -27,6 +27,9 @@ int ls_launch_softmax_bwd(const void* prob, const float* gprob_pm, const void* g
 int ls_launch_to_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
 int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, int HW, void* dst, cudaStream_t s);
 
+int ls_launch_target_bev(const int* pix, int B, int X, int Y, float* out, long long sb, long long sx, long long sy,
+                         cudaStream_t s);
+
 // ls_splat.cu
 int ls_debug_fetch_phase_cycles(unsigned long long* out8);   // only with -DLS_PROFILE
 size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g);   // per sample, in 8-byte records

@@ -250,7 +250,8 @@ class LiftSplatFunction(torch.autograd.Function):
     tile leaves as one bulk store, and a channels_last gradient is gathered in place."""
 
     @staticmethod
-    def forward(ctx, feat, logits, M, t, frustum, shape: LsShape, bev_format=torch.contiguous_format):
+    def forward(ctx, feat, logits, M, t, frustum, shape: LsShape, bev_format=torch.contiguous_format,
+                spare_channels: int = 0):
         _need_cuda(feat, logits, M, t, frustum)
         if feat.dtype != logits.dtype:
             raise TypeError("feat and depth logits must share a dtype")
@@ -261,8 +262,14 @@ class LiftSplatFunction(torch.autograd.Function):
         need_bwd = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         scratch = scratch_for(scratch_bytes(shape, code, need_bwd), dev)
         saved = torch.empty(saved_bytes(shape, code, layout), dtype=torch.uint8, device=dev) if need_bwd else None
-        bev = torch.empty((shape.B, shape.C, shape.X, shape.Y), dtype=torch.float32, device=dev,
+        if spare_channels and bev_format != torch.channels_last:
+            raise ValueError("spare BEV channels need the channels_last layout")
+        # spare_channels: the BEV is the first C channels of a channels-last [B,X,Y,C+spare] buffer, so
+        # that add_target_bev (model/parking_model.py:28-46) fills in its channel without a torch.cat copy
+        bev = torch.empty((shape.B, shape.C + spare_channels, shape.X, shape.Y), dtype=torch.float32, device=dev,
                           memory_format=bev_format)
+        if spare_channels:
+            bev = bev[:, :shape.C]
         prob = torch.empty_like(logits_c)
         st = _bev_strides(bev)
         check(_lib.load().ls_forward(_ptr(feat_c), layout, _ptr(logits_c), code, _ptr(M.contiguous()),
@@ -296,11 +303,11 @@ class LiftSplatFunction(torch.autograd.Function):
         check(_lib.load().ls_backward(_ptr(grad_bev), C.byref(st), _ptr(grad_prob), _ptr(prob), _ptr(feat_nhwc),
                                       layout, code, C.byref(shape), _ptr(scratch), scratch.numel(), _ptr(saved),
                                       saved.numel(), _ptr(gfeat), _ptr(glogits), _stream(prob)), "ls_backward")
-        return gfeat, glogits, None, None, None, None, None
+        return gfeat, glogits, None, None, None, None, None, None
 
 
 def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, t: torch.Tensor,
-               frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format
+               frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format, spare_channels: int = 0
                ) -> Tuple[torch.Tensor, torch.Tensor]:
     """feat [B*N,C,fh,fw], depth_logits [B*N,D,fh,fw] (CamEncoder outputs,
     model/cam_encoder.py:102-111), M [B,N,3,3], t [B,N,3], frustum [D,fh,fw,3] ->
@@ -314,4 +321,4 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
     if tuple(frustum.shape) != (D, fh, fw, 3):
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
     shape = make_shape(B, N, D, fh, fw, Cc, grid)
-    return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format)
+    return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format, spare_channels)

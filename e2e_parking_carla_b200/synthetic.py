@@ -189,3 +189,25 @@ def make_upstream_grads(shape: LiftSplatShape, seed: int = 0, dtype=torch.float3
     gb = torch.from_numpy(_irwin_hall_normal(rng, (shape.batch, shape.channels, x, y)))
     gp = torch.from_numpy(_irwin_hall_normal(rng, (shape.batch * shape.cams, shape.depth_bins, shape.fh, shape.fw)))
     return gb, gp.to(dtype)
+
+
+def make_depth_labels(shape: LiftSplatShape, seed: int = 0) -> torch.Tensor:
+    """Synthetic metric ground-truth depth f32[B, N, H, W] for DepthLoss (data['depth'] of
+    dataset/carla_dataset.py:379-423): 0.5 .. 15 m on a 1.25 cm lattice (so that many values sit
+    EXACTLY on depth-bin boundaries, every 20th lattice point at 0.25 m bins), ~12 % zeros
+    ("no return", ignored by the min-pool), and whole 8x8 blocks of zeros (background pixels).
+    Built from integer draws and two float32 ops: bit-identical on every host."""
+    rng = np.random.RandomState(2000 + seed)
+    h, w = shape.final_dim
+    n = (shape.batch, shape.cams, h, w)
+    ds = shape.bev_down_sample
+    # a base depth per ds x ds block (so the min-pool covers every bin) plus 0 .. 0.5 m of per-pixel relief
+    base = rng.randint(0, 1121, size=(shape.batch, shape.cams, h // ds, w // ds))
+    k = (np.repeat(np.repeat(base, ds, axis=2), ds, axis=3) + rng.randint(0, 41, size=n)).astype(np.float32)
+    depth = (k * np.float32(0.0125) + np.float32(0.5)).astype(np.float32)
+    depth[rng.randint(0, 100, size=n) < 12] = 0.0
+    blocks = rng.randint(0, 100, size=(shape.batch, shape.cams, h // ds, w // ds)) < 7
+    depth[np.repeat(np.repeat(blocks, ds, axis=2), ds, axis=3)] = 0.0
+    # a band of far depths whose min-pool lands beyond the last bin (label 0 through the range test)
+    depth[:, :, : 2 * ds, :] = np.where(depth[:, :, : 2 * ds, :] > 0, depth[:, :, : 2 * ds, :] + np.float32(12.5), 0.0)
+    return torch.from_numpy(depth)

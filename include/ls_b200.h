@@ -203,6 +203,31 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
                 const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch, size_t scratch_bytes,
                 const void* saved, size_t saved_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream);
 
+/* ---- consumer of bev: ParkingModel.add_target_bev (model/parking_model.py:28-46) ----------
+ * Writes the target channel: ones on [px-4, px+4) x [py-4, py+4) (python slice semantics) around
+ * target_pix i32[B,2] = the (noised) target pixel, zeros elsewhere, into `out` with element
+ * strides (b, x, y) - a [B,1,X,Y] tensor, or channel C of a channels-last [B,X,Y,C+1] buffer
+ * whose first C channels ls_forward wrote (no torch.cat copy of the BEV). */
+int ls_target_bev(const int32_t* target_pix, int32_t B, int32_t X, int32_t Y, float* out, int64_t stride_b,
+                  int64_t stride_x, int64_t stride_y, ls_stream_t stream);
+
+/* ---- consumer of pred_depth: DepthLoss (loss/depth_loss.py:18-48) ------------------------
+ * prob [BN,D,fh,fw] of `dtype` (ls_forward's pred_depth), gt_depth f32[BN, fh*down, fw*down]
+ * (metric depth per pixel, 0 = no return; data['depth'] of dataset/carla_dataset.py viewed as
+ * [B*N,H,W]).  d_off = float32(d_bound[0] - d_bound[2]), d_step = float32(d_bound[2]).
+ * Outputs: labels i32[BN*fh*fw] (0 background, k >= 1: depth bin k-1 is the positive class;
+ * kept for the backward), out2 f32[2] = {loss, 1 / max(1, #foreground pixels)}.
+ * ws: >= ls_depth_loss_ws_bytes() of scratch (per-CTA partial sums; sums have a fixed order). */
+size_t ls_depth_loss_ws_bytes(int32_t BN, int32_t fh, int32_t fw);
+int ls_depth_loss_fwd(const void* prob, int dtype, const float* gt_depth, int32_t BN, int32_t D, int32_t fh,
+                      int32_t fw, int32_t down, float d_off, float d_step, int32_t* labels, void* ws,
+                      size_t ws_bytes, float* out2, ls_stream_t stream);
+/* grad_prob [BN,D,fh,fw] of `dtype` = grad_out * d loss / d prob (aten's binary_cross_entropy
+ * backward, zero on background pixels); grad_out: device scalar (NULL = 1). */
+int ls_depth_loss_bwd(const void* prob, int dtype, const int32_t* labels, const float* fwd_out2,
+                      const float* grad_out, int32_t BN, int32_t D, int32_t fh, int32_t fw, void* grad_prob,
+                      ls_stream_t stream);
+
 /* Developer aid: per-phase clock64 totals of ls_splat_fwd (summed over CTAs) since the last
  * call; LS_ERR_UNSUPPORTED unless the library was built with -DLS_PROFILE. */
 int ls_debug_phase_cycles(uint64_t* out8);

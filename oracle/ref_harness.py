@@ -25,7 +25,10 @@ import types
 import torch
 from torch import nn
 
-REFERENCE_ROOTS = ("/root/reference",)
+# /root/reference in the build container; baseline/_ref/ is where a driver-provided copy of the
+# reference would sit on the GPU box (git-ignored; this repo never writes it)
+REFERENCE_ROOTS = ("/root/reference",
+                   os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"))
 
 
 def reference_root():
@@ -129,6 +132,26 @@ def run_reference(cfg, feat, logits, intrinsics, extrinsics, double=False, backw
         out["grad_feat"] = feat.grad.detach()
         out["grad_logits"] = logits.grad.detach()
     return out
+
+
+def reference_stepper(cfg):
+    """A callable running one forward+backward of the unmodified reference BevModel on preset
+    encoder outputs (what bench.py times as kind "reference" when the tree is present):
+    step(feat, logits, intrinsics, extrinsics, grad_bev, grad_prob) -> (bev, prob, gfeat, glogits)."""
+    model = reference_bev_model(cfg)
+
+    def step(feat, logits, intrinsics, extrinsics, grad_bev, grad_prob):
+        model.to(feat.device)
+        b, n = intrinsics.shape[:2]
+        f = feat.detach().requires_grad_(True)
+        z = logits.detach().requires_grad_(True)
+        model.cam_encoder.preset = (f, z)
+        images = torch.zeros(b, n, 3, 1, 1, device=feat.device)
+        bev, prob = model(images, intrinsics, extrinsics)
+        torch.autograd.backward([bev, prob], [grad_bev, grad_prob])
+        return bev.detach(), prob.detach(), f.grad, z.grad
+
+    return step
 
 
 def reference_indices(cfg, intrinsics, extrinsics):

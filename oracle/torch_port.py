@@ -115,3 +115,20 @@ def fwd_bwd_step(feat, depth_logits, intrinsics, extrinsics, frustum, bev_start,
     bev, prob = lift_splat_cpu(f, z, intrinsics, extrinsics, frustum, bev_start, bev_res, bev_dim)
     torch.autograd.backward([bev, prob], [grad_bev, grad_prob])
     return bev.detach(), prob.detach(), f.grad, z.grad
+
+
+def add_target_bev_ref(bev_feature, target_point, x_res, y_res, noise=True):
+    """model/parking_model.py:28-46 restated (test oracle): zero map, 8x8 stamp of ones around
+    the noised target pixel via python slices (negative bounds wrap like python's), channel cat.
+    Draws its noise with the same ``torch.rand_like`` call, so a seeded generator reproduces it."""
+    b, c, h, w = bev_feature.shape
+    target_map = torch.zeros((b, 1, h, w), dtype=torch.float, device=bev_feature.device)
+    px = (h / 2 + target_point[:, 0] / x_res).unsqueeze(0).T.int()
+    py = (w / 2 + target_point[:, 1] / y_res).unsqueeze(0).T.int()
+    pix = torch.cat([px, py], dim=1)
+    if noise:
+        pix = pix + (torch.rand_like(pix, dtype=torch.float) * 10 - 5).int()
+    for i in range(b):
+        cx, cy = int(pix[i, 0]), int(pix[i, 1])
+        target_map[i, 0][cx - 4:cx + 4, cy - 4:cy + 4] = 1.0
+    return torch.cat([bev_feature, target_map], dim=1), target_map

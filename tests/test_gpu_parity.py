@@ -729,3 +729,119 @@ def test_full_size_values_on_sampled_batch_indices(lib):
         got = {"bev": out["bev"][b:b + 1], "prob": out["prob"][b * n:(b + 1) * n],
                "grad_feat": out["grad_feat"][b * n:(b + 1) * n], "grad_logits": out["grad_logits"][b * n:(b + 1) * n]}
         _check_all(got, ref, FP32_TOL, 1e-6)
+
+
+# ------------------------------------------------------------------------------------
+# DepthLoss kernels (loss/depth_loss.py:18-48)
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depth_loss_vs_golden_and_oracle(lib, dtype):
+    """ls_depth_loss_fwd/bwd against the fixture frozen from the unmodified reference and
+    against the float64 oracle: bin labels bit-exact, loss and gradient <= 1e-5 (fp32)."""
+    from oracle import depth_loss_oracle as dlo
+    from e2e_parking_carla_b200 import DepthLoss
+    from e2e_parking_carla_b200.synthetic import make_depth_labels
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_loss_b1.npz"))
+    shape = LiftSplatShape(batch=1, channels=4)
+    _, logits = make_encoder_outputs(shape, seed=31)
+    gt = make_depth_labels(shape, seed=31)
+    prob = logits.softmax(dim=1).to(DEV, dtype).requires_grad_(True)
+    crit = DepthLoss(make_cfg(shape))
+    assert crit.depth_channels == 48
+    loss = crit(prob, gt.to(DEV))
+    (3.0 * loss).backward()
+    lo_loss, lo_grad, labels = dlo.depth_loss(prob.detach().float().cpu().numpy(), gt.numpy(), shape.d_bound, 8)
+    assert np.array_equal(labels, z["labels"].astype(np.int64))
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert abs(loss.item() - lo_loss) <= tol * abs(lo_loss)
+    assert_close(prob.grad.float() / 3.0, lo_grad, tol, "grad_prob")
+    if dtype == torch.float32:
+        assert abs(loss.item() - float(z["loss32"])) <= 1e-6 * abs(lo_loss)
+        assert_close(prob.grad / 3.0, z["grad32"], FP32_TOL, "grad_prob vs reference")
+        # labels as the kernel saw them (saved for backward): zero gradient exactly on background pixels
+        bg = torch.from_numpy(labels == 0).view(4, 32, 32).to(DEV)
+        assert float(prob.grad.permute(0, 2, 3, 1)[bg].abs().max()) == 0.0
+    # deterministic
+    prob2 = prob.detach().clone().requires_grad_(True)
+    loss2 = crit(prob2, gt.to(DEV))
+    assert torch.equal(loss2, loss)
+
+
+def test_depth_loss_edge_cases(lib):
+    """No foreground at all -> loss 0 (division by max(1, 0)); probabilities of exactly 0 and 1
+    hit aten's log clamp (-100) and the backward's 1e-12 floor; odd down-sample / sizes."""
+    from oracle import depth_loss_oracle as dlo
+    from e2e_parking_carla_b200 import DepthLoss
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(d_bound=[1.0, 9.0, 0.5], bev_down_sample=4)
+    crit = DepthLoss(cfg)
+    D = crit.depth_channels
+    assert D == 16
+    gen = torch.Generator().manual_seed(5)
+    prob = torch.rand(6, D, 5, 7, generator=gen).softmax(dim=1)
+    prob[0, 3] = 0.0
+    prob[1, 2] = 1.0
+    gt = torch.rand(2, 3, 20, 28, generator=gen) * 10.0
+    gt[0, 0, :8] = 0.0
+    p = prob.to(DEV).requires_grad_(True)
+    loss = crit(p, gt.to(DEV))
+    loss.backward()
+    lo_loss, lo_grad, _ = dlo.depth_loss(prob.numpy(), gt.numpy(), cfg.d_bound, 4)
+    assert abs(loss.item() - lo_loss) <= 1e-5 * abs(lo_loss)
+    assert_close(p.grad, lo_grad, 1e-5, "grad")
+    p0 = prob.to(DEV).requires_grad_(True)
+    loss0 = crit(p0, torch.zeros(2, 3, 20, 28, device=DEV))
+    loss0.backward()
+    assert loss0.item() == 0.0 and float(p0.grad.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------
+# add_target_bev (model/parking_model.py:28-46): the BEV's immediate consumer
+# ------------------------------------------------------------------------------------
+def test_add_target_bev_matches_reference_semantics(lib):
+    """Same values as the reference's zero-map + python-slice stamp + torch.cat (including its
+    torch.rand_like noise under the same seed and python's negative-slice wrap at the border),
+    for an NCHW BEV, a channels_last BEV (cat stays channels_last) and the in-place variant
+    (BevModel(spare_channels=1): no copy of the BEV); the gradient reaches the encoder outputs
+    through the 65-channel tensor and is bit-identical in all three."""
+    from oracle import torch_port as tp
+    from e2e_parking_carla_b200 import BevModel, add_target_bev
+
+    class Preset(torch.nn.Module):
+        def forward(self, images):
+            return self.feat, self.logits
+
+    shape = LiftSplatShape(batch=4, channels=64)
+    cfg = make_cfg(shape)
+    intr, extr = make_rig(4, 4, jitter=True, seed=51)
+    feat, logits = make_encoder_outputs(shape, seed=21)
+    # targets: inside, near the low border (negative slice start -> python wraps: empty stamp), far corner
+    target = torch.tensor([[1.3, -2.7, 0.0], [-9.9, 0.2, 0.0], [7.9, 7.9, 0.0], [-3.3, 9.7, 0.0]], device=DEV)
+    images = torch.zeros(4, 4, 3, 8, 8, device=DEV)
+    conv = torch.nn.Conv2d(65, 4, 3, padding=1).to(DEV)
+    results = []
+    for fmt, spare in ((torch.contiguous_format, 0), (torch.channels_last, 0), (torch.channels_last, 1)):
+        enc = Preset()
+        enc.feat = feat.to(DEV).requires_grad_(True)
+        enc.logits = logits.to(DEV).requires_grad_(True)
+        model = BevModel(cfg, cam_encoder=enc, bev_memory_format=fmt, spare_channels=spare).to(DEV)
+        bev, depth = model(images, intr.to(DEV), extr.to(DEV))
+        torch.manual_seed(77)
+        wide, tmap = add_target_bev(bev, target, cfg)
+        torch.manual_seed(77)
+        wide_ref, tmap_ref = tp.add_target_bev_ref(bev.detach(), target, cfg.bev_x_bound[2], cfg.bev_y_bound[2])
+        assert tuple(wide.shape) == (4, 65, 200, 200) and tuple(tmap.shape) == (4, 1, 200, 200)
+        assert torch.equal(wide, wide_ref) and torch.equal(tmap, tmap_ref)
+        assert float(tmap.sum()) > 0
+        if fmt == torch.channels_last:
+            assert wide.is_contiguous(memory_format=torch.channels_last)
+        if spare:
+            assert wide.data_ptr() == bev.data_ptr()          # nothing was copied
+        conv.zero_grad()
+        (conv(wide).square().sum() + depth.sum()).backward()
+        results.append((bev.detach().clone(), enc.feat.grad.clone(), enc.logits.grad.clone()))
+    for r in results[1:]:
+        assert torch.equal(r[0], results[0][0])
+        # the gradient handed to the backward differs only in layout; conv's own backward may pick
+        # another algorithm per layout, so compare to tolerance, not bits
+        assert relerr(r[1], results[0][1]) < 1e-5 and relerr(r[2], results[0][2]) < 1e-5

@@ -5,6 +5,8 @@ the pin is (a) fixtures frozen from the UNMODIFIED reference run in the build co
 (tests/golden/make_golden.py) and (b), when /root/reference is present, the live
 reference itself.  No GPU needed.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -175,3 +177,52 @@ def test_live_reference_equals_port_and_oracle():
     assert np.array_equal(vox_o, vox.numpy()) and np.array_equal(keep_o, keep.numpy())
     bev_o, _ = lo.splat_forward(feat.numpy(), logits.numpy(), rank_o, dim, shape.cams)
     assert relerr(bev_o, ref64["bev"]) < 5e-7
+
+
+# ------------------------------------------------------------------------------------
+# DepthLoss (loss/depth_loss.py:18-48): the consumer of pred_depth
+# ------------------------------------------------------------------------------------
+def _depth_loss_case():
+    from e2e_parking_carla_b200.synthetic import make_depth_labels
+    shape = LiftSplatShape(batch=1, channels=4)
+    _, logits = make_encoder_outputs(shape, seed=31)
+    return shape, logits, make_depth_labels(shape, seed=31)
+
+
+def test_depth_loss_oracle_vs_golden():
+    """The numpy restatement reproduces the unmodified reference DepthLoss: identical bin labels
+    (min-pool ignoring zeros, truncation, range test), loss and gradient of its float32 run."""
+    from oracle import depth_loss_oracle as dlo
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "depth_loss_b1.npz"))
+    shape, logits, gt = _depth_loss_case()
+    prob = logits.softmax(dim=1).numpy()
+    loss, grad, labels = dlo.depth_loss(prob, gt.numpy(), shape.d_bound, shape.bev_down_sample)
+    assert np.array_equal(labels, z["labels"].astype(np.int64))
+    assert int((labels > 0).sum()) == int(z["fg"]) and set(np.unique(labels)) == set(range(49))
+    assert abs(loss - float(z["loss32"])) <= 1e-6 * abs(loss)
+    assert np.abs(grad - z["grad32"]).max() <= 1e-6 * np.abs(z["grad32"]).max()
+
+
+def test_depth_loss_live_reference():
+    """Against the live reference module when the tree is mounted (labels with exact-boundary
+    depths, all-zero blocks and out-of-range blocks)."""
+    import sys
+    if not os.path.isfile("/root/reference/loss/depth_loss.py"):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, "/root/reference")
+    from loss.depth_loss import DepthLoss as RefLoss
+    from oracle import depth_loss_oracle as dlo
+    from e2e_parking_carla_b200.synthetic import make_cfg, make_depth_labels
+    shape = LiftSplatShape(batch=2, channels=4)
+    _, logits = make_encoder_outputs(shape, seed=32)
+    gt = make_depth_labels(shape, seed=32)
+    prob = logits.softmax(dim=1).requires_grad_(True)
+    ref = RefLoss(make_cfg(shape))
+    loss_ref = ref(prob, gt)
+    loss_ref.backward()
+    loss, grad, labels = dlo.depth_loss(prob.detach().numpy(), gt.numpy(), shape.d_bound, 8)
+    onehot = ref.get_down_sampled_gt_depth(gt)
+    lab_ref = torch.where(onehot.sum(1) > 0, onehot.argmax(1) + 1, torch.zeros(onehot.shape[0], dtype=torch.long))
+    assert np.array_equal(labels, lab_ref.numpy())
+    assert abs(loss - loss_ref.item()) <= 1e-6 * abs(loss)
+    assert np.abs(grad - prob.grad.numpy()).max() <= 1e-6 * np.abs(grad).max()
