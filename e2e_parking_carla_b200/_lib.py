@@ -14,12 +14,14 @@ from .build import LIB_PATH
 LS_OK = 0
 LS_F32, LS_BF16 = 0, 1
 LS_FEAT_NCHW, LS_FEAT_NHWC = 0, 1
+LS_GEOM_TORCH_CPU, LS_GEOM_TORCH_CUDA = 0, 1
 
 
 class LsShape(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("fh", C.c_int32),
                 ("fw", C.c_int32), ("C", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32),
-                ("Z", C.c_int32), ("start", C.c_float * 3), ("res", C.c_float * 3)]
+                ("Z", C.c_int32), ("start", C.c_float * 3), ("res", C.c_float * 3),
+                ("geom_policy", C.c_int32)]
 
 
 class LsBevStrides(C.Structure):
@@ -43,6 +45,7 @@ PROTOTYPES = {
     "ls_camera_transform": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "ls_geometry": (C.c_int, [_P, _P, _P, _SH, _P, _P]),
     "ls_index": (C.c_int, [_P, _P, _P, _SH, _P, _P, _P, _P, _P]),
+    "ls_index_geom": (C.c_int, [_P, _SH, _P, _P, _P, _P, _P]),
     "ls_export_indices": (C.c_int, [_P, _P, _P, _SH, _P, _P, _P, _P]),
     "ls_sort": (C.c_int, [_P, _P, _P, _P, C.c_int, _SH, _P, _P, _P, _P, _P, _P]),
     "ls_export_cell_counts": (C.c_int, [_P, _SH, C.c_int32, _P, _P, _P]),

@@ -47,8 +47,11 @@ class BevModel(nn.Module):
         The reference constructs ``CamEncoder(cfg, D)`` itself (model/bev_model.py:26);
         when ``None`` we do the same if the reference's ``model.cam_encoder`` is importable.
     geometry : ``"native"`` (default) computes E^-1, K^-1 in ``ls_camera_transform``
-        (no host sync, graph-capturable); ``"torch"`` calls ``torch.inverse`` exactly as
-        model/bev_model.py:46,53 does, for bit-parity with the reference on the same device.
+        (no host sync, graph-capturable) and evaluates the per-point transform in torch-CPU's
+        float32 order (what the golden fixtures pin).  ``"torch"`` reproduces the reference running
+        on THIS device: ``torch.inverse`` / ``matmul`` exactly as model/bev_model.py:46,53 calls
+        them, and the per-point transform in the order torch's CUDA matmul uses
+        (``LS_GEOM_TORCH_CUDA``) - voxel ranks then equal the reference's on the same GPU bit for bit.
     bev_memory_format : memory format of the returned ``bev_feature`` ([B,C,X,Y] fp32 with the
         reference's values either way).  ``torch.channels_last`` (default) is the splat's native
         layout: a cell's channels are one 256-byte row, tiles leave as bulk (TMA) stores, and
@@ -124,9 +127,14 @@ class BevModel(nn.Module):
             return rot.matmul(torch.inverse(intrinsics)).contiguous(), trans.contiguous()
         return ls.camera_transform(intrinsics, extrinsics)
 
+    @property
+    def geom_policy(self):
+        from ._lib import LS_GEOM_TORCH_CPU, LS_GEOM_TORCH_CUDA
+        return LS_GEOM_TORCH_CUDA if self.geometry_mode == "torch" else LS_GEOM_TORCH_CPU
+
     def _shape(self, batch, cams, channels):
         d, fh, fw, _ = self.frustum.shape
-        return ls.make_shape(batch, cams, d, fh, fw, channels, self._grid)
+        return ls.make_shape(batch, cams, d, fh, fw, channels, self._grid, self.geom_policy)
 
     def get_geometry(self, intrinsics, extrinsics):
         """Ego-frame coordinates of every frustum point, f32[B,N,D,h,w,3].  Kept for API
@@ -149,9 +157,11 @@ class BevModel(nn.Module):
 
     # ---- a6: model/bev_model.py:74-107 ------------------------------------------------
     def proj_bev_feature(self, geom, image_feature):
-        raise NotImplementedError(
-            "proj_bev_feature(geom, x) consumes the materialised frustum tensor; use "
-            "calc_bev_feature / forward, which fuse lift and splat")
+        """Reference-shaped projection of a MATERIALISED lift: ``geom`` [B,N,D,h,w,3] (from
+        ``get_geometry``) and ``image_feature`` [B,N,D,h,w,C] (from ``encoder_forward``) ->
+        bev f32[B,C,X,Y].  Compatibility path (same kernels, one point = one feature row); the fused
+        ``calc_bev_feature`` never builds either tensor."""
+        return ls.proj_bev(geom, image_feature, self._grid, self.bev_memory_format)
 
     # ---- a8: model/bev_model.py:109-117 -----------------------------------------------
     def calc_bev_feature(self, images, intrinsics, extrinsics):
@@ -159,7 +169,7 @@ class BevModel(nn.Module):
         feat, depth_logits = self.cam_encoder(images.view(b * n, c, h, w))
         M, t = self.camera_transform(intrinsics, extrinsics)
         bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid,
-                                                self.bev_memory_format, self.spare_channels)
+                                                self.bev_memory_format, self.spare_channels, self.geom_policy)
         return bev_feature, pred_depth
 
     def forward(self, images, intrinsics, extrinsics):

@@ -99,6 +99,7 @@ static int ls_check_shape(const LsShape* s) {
   if (!s) return LS_ERR_BAD_ARG;
   if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fh <= 0 || s->fw <= 0 || s->C <= 0) return LS_ERR_BAD_ARG;
   if (s->X <= 0 || s->Y <= 0 || s->Z <= 0) return LS_ERR_BAD_ARG;
+  if (s->geom_policy != LS_GEOM_TORCH_CPU && s->geom_policy != LS_GEOM_TORCH_CUDA) return LS_ERR_BAD_ARG;
   if ((long long)s->X * s->Y * s->Z >= (1LL << 28)) return LS_ERR_UNSUPPORTED;
   if ((long long)s->B * s->N * s->D * s->fh * s->fw >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
   return LS_OK;
@@ -252,6 +253,18 @@ int ls_index(const float* M, const float* t, const float* frustum, const LsShape
   if (!sorting && !rank) return LS_ERR_BAD_ARG;
   if (sorting && (rc = ls_check_splat_shape(s))) return rc;
   return ls_launch_index(M, t, frustum, ls_dims(s), ls_grid(s), rank, cell, within, counts, (cudaStream_t)stream);
+}
+
+int ls_index_geom(const float* geom, const LsShape* s, int32_t* rank, int32_t* cell, int32_t* within,
+                  int32_t* counts, ls_stream_t stream) {
+  int rc = ls_check_shape(s);
+  if (rc) return rc;
+  if (!geom) return LS_ERR_BAD_ARG;
+  const bool sorting = cell || within || counts;
+  if (sorting && !(cell && within && counts)) return LS_ERR_BAD_ARG;
+  if (!sorting && !rank) return LS_ERR_BAD_ARG;
+  if (sorting && (rc = ls_check_splat_shape(s))) return rc;
+  return ls_launch_index_geom(geom, ls_dims(s), ls_grid(s), rank, cell, within, counts, (cudaStream_t)stream);
 }
 
 int ls_sort(const int32_t* cell, const int32_t* within, const int32_t* counts, const void* prob, int dtype,

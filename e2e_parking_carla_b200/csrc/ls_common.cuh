@@ -52,6 +52,7 @@ struct LsDims {
   int DHW;     // D*fh*fw   points per camera
   int Npts;    // N*D*fh*fw points per sample
   int dbits;   // ceil(log2(D)): sort key = cell_in_tile<<24 | (pix << dbits | d)
+  int policy;  // LsGeomPolicy
 };
 
 static inline LsDims ls_dims(const LsShape* s) {
@@ -63,6 +64,7 @@ static inline LsDims ls_dims(const LsShape* s) {
   d.Npts = s->N * d.DHW;
   d.dbits = 0;
   while ((1 << d.dbits) < s->D) ++d.dbits;
+  d.policy = s->geom_policy;
   return d;
 }
 
@@ -127,16 +129,25 @@ enum LsGradIn {
 
 // Voxel coordinate of one frustum point, operation by operation as torch-CPU does it
 // (model/bev_model.py:50-55,85): p=(u*d, v*d, d); g_i=((0+m_i0*px)+m_i1*py)+m_i2*pz; g_i+=t_i;
-// c_i=(g_i-off_i)/res_i.  No FMA contraction, IEEE divide.
+// c_i=(g_i-off_i)/res_i.  No FMA contraction, IEEE divide.  kPolicy = LS_GEOM_TORCH_CUDA instead
+// follows torch's CUDA matmul (include/ls_b200.h LsGeomPolicy).
+template <int kPolicy>
 __device__ __forceinline__ void ls_point_geom(const float* __restrict__ m, const float* __restrict__ t,
                                               float u, float v, float d, float g[3]) {
   const float px = __fmul_rn(u, d);
   const float py = __fmul_rn(v, d);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    float a = __fadd_rn(0.0f, __fmul_rn(m[3 * i + 0], px));
-    a = __fadd_rn(a, __fmul_rn(m[3 * i + 1], py));
-    a = __fadd_rn(a, __fmul_rn(m[3 * i + 2], d));
+    float a;
+    if (kPolicy == LS_GEOM_TORCH_CUDA) {
+      // torch-CUDA (cuBLAS batched 3x3 . 3x1): the first two terms share one fused multiply-add
+      a = __fmaf_rn(m[3 * i + 1], py, __fmul_rn(m[3 * i + 0], px));
+      a = __fadd_rn(a, __fmul_rn(m[3 * i + 2], d));
+    } else {
+      a = __fadd_rn(0.0f, __fmul_rn(m[3 * i + 0], px));
+      a = __fadd_rn(a, __fmul_rn(m[3 * i + 1], py));
+      a = __fadd_rn(a, __fmul_rn(m[3 * i + 2], d));
+    }
     g[i] = __fadd_rn(a, t[i]);
   }
 }

@@ -100,7 +100,9 @@ int ls_launch_camera_transform(const float* intr, const float* extr, int BN, flo
 #define LS_IDX_ILP 2
 #endif
 
-template <bool kExport>
+// kGeomIn: the ego-frame coordinates are given (proj_bev_feature(geom, x) of the reference API,
+// model/bev_model.py:74-107) instead of computed from the camera transform and the frustum.
+template <bool kExport, bool kGeomIn, int kPolicy>
 __global__ void __launch_bounds__(256)
 ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const float* __restrict__ frustum,
                 LsDims dm, LsGrid grid, int* __restrict__ rank, int* __restrict__ cell, int* __restrict__ within,
@@ -110,10 +112,12 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   ls_pdl_wait();
   const int b = blockIdx.z, n = blockIdx.y;
   float cam[12];   // warp-uniform loads: every thread keeps the camera's 3x3 + translation in registers
+  if (!kGeomIn) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) cam[k] = __ldg(M + (b * dm.N + n) * 9 + k);
+    for (int k = 0; k < 9; ++k) cam[k] = __ldg(M + (b * dm.N + n) * 9 + k);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) cam[9 + k] = __ldg(t + (b * dm.N + n) * 3 + k);
+    for (int k = 0; k < 3; ++k) cam[9 + k] = __ldg(t + (b * dm.N + n) * 3 + k);
+  }
   // LS_IDX_ILP points per thread (strided by the CTA width): their loads, divisions and the
   // histogram atomics are independent, so the returning atomics overlap instead of serialising
   const int i0 = blockIdx.x * (blockDim.x * LS_IDX_ILP) + threadIdx.x;
@@ -122,16 +126,19 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   for (int k = 0; k < LS_IDX_ILP; ++k) {
     const int i = i0 + k * blockDim.x;
     const bool in = i < dm.DHW;
-    u[k] = in ? __ldg(frustum + 3 * i + 0) : 0.0f;
-    v[k] = in ? __ldg(frustum + 3 * i + 1) : 0.0f;
-    d[k] = in ? __ldg(frustum + 3 * i + 2) : 0.0f;
+    // kGeomIn: `frustum` is geom[B,Npts,3]; (u,v,d) carry the point's coordinates
+    const float* src = kGeomIn ? frustum + 3 * ((size_t)b * dm.Npts + (size_t)n * dm.DHW + i) : frustum + 3 * i;
+    u[k] = in ? __ldg(src + 0) : 0.0f;
+    v[k] = in ? __ldg(src + 1) : 0.0f;
+    d[k] = in ? __ldg(src + 2) : 0.0f;
   }
   bool keep[LS_IDX_ILP];
   int vx[LS_IDX_ILP][3], cid[LS_IDX_ILP], tk[LS_IDX_ILP];
   float g[LS_IDX_ILP][3], c[LS_IDX_ILP][3];
 #pragma unroll
   for (int k = 0; k < LS_IDX_ILP; ++k) {
-    ls_point_geom(cam, cam + 9, u[k], v[k], d[k], g[k]);
+    if (kGeomIn) { g[k][0] = u[k]; g[k][1] = v[k]; g[k][2] = d[k]; }
+    else ls_point_geom<kPolicy>(cam, cam + 9, u[k], v[k], d[k], g[k]);
     keep[k] = ls_point_voxel(g[k], grid, c[k], vx[k]) && (i0 + k * blockDim.x < dm.DHW);
     cid[k] = -1;
     tk[k] = 0;
@@ -189,16 +196,33 @@ int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaSt
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
   dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
-  LS_LAUNCH(ls_index_kernel<false>, grid, dim3(256), 0, s, M, t, frustum, dm, g, rank, cell, within, counts,
-            (float*)nullptr, (long long*)nullptr, (unsigned char*)nullptr, (long long*)nullptr);
+  if (dm.policy == LS_GEOM_TORCH_CUDA)
+    LS_LAUNCH((ls_index_kernel<false, false, LS_GEOM_TORCH_CUDA>), grid, dim3(256), 0, s, M, t, frustum, dm, g, rank,
+              cell, within, counts, (float*)nullptr, (long long*)nullptr, (unsigned char*)nullptr, (long long*)nullptr);
+  else
+    LS_LAUNCH((ls_index_kernel<false, false, LS_GEOM_TORCH_CPU>), grid, dim3(256), 0, s, M, t, frustum, dm, g, rank,
+              cell, within, counts, (float*)nullptr, (long long*)nullptr, (unsigned char*)nullptr, (long long*)nullptr);
+  return LS_OK;
+}
+
+int ls_launch_index_geom(const float* geom, const LsDims& dm, const LsGrid& g, int* rank, int* cell, int* within,
+                         int* counts, cudaStream_t s) {
+  dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
+  LS_LAUNCH((ls_index_kernel<false, true, LS_GEOM_TORCH_CPU>), grid, dim3(256), 0, s, (const float*)nullptr, (const float*)nullptr, geom,
+            dm, g, rank, cell, within, counts, (float*)nullptr, (long long*)nullptr, (unsigned char*)nullptr,
+            (long long*)nullptr);
   return LS_OK;
 }
 
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                      float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s) {
   dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
-  ls_index_kernel<true><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, nullptr, nullptr, nullptr, nullptr, geom, vox,
-                                             keep, rank64);
+  if (dm.policy == LS_GEOM_TORCH_CUDA)
+    ls_index_kernel<true, false, LS_GEOM_TORCH_CUDA><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, nullptr, nullptr, nullptr,
+                                                                          nullptr, geom, vox, keep, rank64);
+  else
+    ls_index_kernel<true, false, LS_GEOM_TORCH_CPU><<<grid, 256, 0, s>>>(M, t, frustum, dm, g, nullptr, nullptr, nullptr,
+                                                                         nullptr, geom, vox, keep, rank64);
   LS_LAUNCHED();
   return LS_OK;
 }

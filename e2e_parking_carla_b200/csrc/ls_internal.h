@@ -10,6 +10,8 @@ int ls_launch_camera_transform(const float* intr, const float* extr, int BN, flo
 int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaStream_t s);
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s);
+int ls_launch_index_geom(const float* geom, const LsDims& dm, const LsGrid& g, int* rank, int* cell, int* within,
+                         int* counts, cudaStream_t s);
 int ls_launch_export(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                      float* geom, long long* vox, unsigned char* keep, long long* rank64, cudaStream_t s);
 int ls_launch_scan(const int* counts, const LsDims& dm, const LsGrid& g, int* seg_start, int* tile_order,

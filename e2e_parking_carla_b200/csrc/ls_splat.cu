@@ -2,6 +2,8 @@
 // (cell-major gradient staging + pixel-stationary gather).  Reference semantics:
 // model/bev_model.py:66-72,99-105 and VoxelsSumming (tool/geometry.py:285-317).
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "ls_internal.h"
 
@@ -360,6 +362,149 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
   }
 }
 
+// =====================================================================================
+// K3c: forward splat for a dense channels-last BEV tensor, WITHOUT the shared-memory tile.
+// With rows as the unit of both accumulation and output there is nothing to transpose: a
+// quarter-warp that finishes a cell writes its 256-byte row straight to global memory, cells
+// nobody hits get their zero rows from the warp that owns them, and cells cut by a piece
+// boundary are finished with read-modify-writes of the row after the barrier (same fixed
+// association as the tile version, so the same bits).  What this buys: the 32 KB per CTA that
+// the tile took from the unified L1/shared array stay L1 - the feature rows a tile re-reads
+// (the same ray crosses it in consecutive depth bins) are served on-chip instead of going back
+// to L2, which the tile version saturates (9.6 of ~12.4 TB/s of L2 throughput).
+// =====================================================================================
+#ifndef LS_SPLATD_MINB
+#define LS_SPLATD_MINB 6
+#endif
+template <typename T>
+__global__ void __launch_bounds__(LS_THREADS, LS_SPLATD_MINB)
+ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
+                           const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm,
+                           LsGrid grid, float* __restrict__ bev, LsBevStrides st) {
+  constexpr int kC = 64;
+  __shared__ int part_cell[LS_QWARPS];
+  __shared__ int ends[2];
+  const int b = blockIdx.x % dm.B;
+  const int tid = threadIdx.x;
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
+  const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
+  const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  float* tile0 = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * kC;
+  // row of cell-in-tile cl (floats from tile0)
+  auto row_off = [&](unsigned cl) -> size_t { return (size_t)(cl / LS_TY) * (size_t)st.x + (size_t)(cl % LS_TY) * kC; };
+  {
+    // this thread's cell: empty cells inside the grid get a zero row (the BEV tensor is never memset)
+    const int a = __ldg(segg + tid), e = __ldg(segg + tid + 1);
+    if (tid == 0) ends[0] = a;
+    if (tid == LS_TILE - 1) ends[1] = e;
+    const bool in_grid = (tx0 + tid / LS_TY) < grid.X && (ty0 + tid % LS_TY) < grid.Y;
+    unsigned m = __ballot_sync(0xffffffffu, in_grid && a == e);
+    const int lane = tid & 31, wbase = tid & ~31;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    while (m) {                                   // two rows per trip: 16 lanes x 16 B each
+      const int c0 = __ffs(m) - 1;
+      m &= m - 1;
+      int c1 = -1;
+      if (m) { c1 = __ffs(m) - 1; m &= m - 1; }
+      const int c = lane < 16 ? c0 : c1;
+      if (c >= 0) __stcs(reinterpret_cast<float4*>(tile0 + row_off(wbase + c)) + (lane & 15), z);
+    }
+  }
+  __syncthreads();
+  const int s0 = ends[0], s1 = ends[1];
+  if (s0 == s1) return;
+  const int ql = tid & 7, qw = tid >> 3, n = s1 - s0;
+  const T* fbase = featT + (size_t)b * dm.N * dm.HW * kC;
+  const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
+  unsigned row_bytes = (unsigned)(kC * sizeof(T));
+  asm volatile("" : "+r"(row_bytes));
+  int idx = s0 + (int)(((long long)qw * n) / LS_QWARPS);
+  const int end = s0 + (int)(((long long)(qw + 1) * n) / LS_QWARPS);
+  const char* f0 = reinterpret_cast<const char*>(fbase + 4 * ql);
+  const unsigned f1off = (unsigned)(32 * sizeof(T));
+  float* lane0 = tile0 + 4 * ql;                  // this lane's first quad of row 0
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pc = -1;
+  if (idx < end) {
+    const int xl = __ldg(&rs[end - 1].x);
+    if (!(xl & LS_REC_LAST)) pc = xl & 255;
+    const int2* p = rs + idx;
+    int2 r[LS_QWIN], rn[LS_QWIN];
+#pragma unroll
+    for (int u = 0; u < LS_QWIN; ++u) {
+      r[u] = p[u];
+      if (idx + u >= end) r[u] = make_int2(0, 0);
+    }
+#define LS_SPLATD_WINDOW(cur, nxt)                                                                   \
+  {                                                                                                  \
+    float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
+      const char* row = f0 + (unsigned long long)((unsigned)cur[u].x >> 12) * row_bytes;             \
+      fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));                                          \
+      fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));                                  \
+    }                                                                                                \
+    idx += LS_QWIN;                                                                                  \
+    p += LS_QWIN;                                                                                    \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) nxt[u] = (idx + u < end) ? p[u] : make_int2(0, 0); \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
+      if (cur[u].x & LS_REC_VALID) {                                                                 \
+        const float wt = __int_as_float(cur[u].y);                                                   \
+        acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);                      \
+        acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);                      \
+        acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);                      \
+        acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);                      \
+      }                                                                                              \
+      if (cur[u].x & LS_REC_LAST) {                                                                  \
+        float* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                       \
+        __stcs(reinterpret_cast<float4*>(g), acc0);                                                  \
+        __stcs(reinterpret_cast<float4*>(g + 32), acc1);                                             \
+        acc0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
+        acc1 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
+      }                                                                                              \
+    }                                                                                                \
+  }
+    for (;;) {
+      LS_SPLATD_WINDOW(r, rn);
+      if (idx >= end) break;
+      LS_SPLATD_WINDOW(rn, r);
+      if (idx >= end) break;
+    }
+#undef LS_SPLATD_WINDOW
+  }
+  if (ql == 0) part_cell[qw] = pc;
+  __syncthreads();
+  // open partial sums of cells cut by piece boundaries: same rounds as the tile version, the
+  // read-modify-write goes to the row in global memory (L2: the stores above are visible after
+  // the barrier; ld.cg never looks at a stale L1 line)
+  int depth = 0, maxd = -1;
+  {
+    int run = 0, prev = -1;
+#pragma unroll
+    for (int j = 0; j < LS_QWARPS; ++j) {
+      const int c = part_cell[j];
+      if (c >= 0) {
+        run = (c == prev) ? run + 1 : 0;
+        maxd = max(maxd, run);
+        prev = c;
+      }
+      if (j == qw) depth = run;
+    }
+  }
+  for (int rd = 0; rd <= maxd; ++rd) {
+    if (pc >= 0 && depth == rd) {
+      float* g = lane0 + row_off((unsigned)pc);
+      float4 t0 = __ldcg(reinterpret_cast<const float4*>(g)), t1 = __ldcg(reinterpret_cast<const float4*>(g + 32));
+      t0.x += acc0.x; t0.y += acc0.y; t0.z += acc0.z; t0.w += acc0.w;
+      t1.x += acc1.x; t1.y += acc1.y; t1.z += acc1.z; t1.w += acc1.w;
+      __stcg(reinterpret_cast<float4*>(g), t0);
+      __stcg(reinterpret_cast<float4*>(g + 32), t1);
+    }
+    __syncthreads();
+  }
+}
+
 int ls_debug_fetch_phase_cycles(unsigned long long* out8) {
 #ifdef LS_PROFILE
   unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -434,7 +579,12 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
 #define LS_SPLAT(OUT, CC)                                                                                          \
   LS_LAUNCH((ls_splat_fwd_kernel<T, OUT, CC>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g, \
             bev, st)
-  if (out == LS_OUT_NHWC_BULK) {
+  // dense channels-last rows: direct row stores (no shared-memory tile, L1 kept for the feature
+  // rows) unless LS_SPLAT_OUT=bulk asks for the one-bulk-store-per-tile (TMA) variant
+  static const bool want_bulk = getenv("LS_SPLAT_OUT") && !strcmp(getenv("LS_SPLAT_OUT"), "bulk");
+  if (out == LS_OUT_NHWC_BULK && !want_bulk) {
+    LS_LAUNCH(ls_splat_fwd_direct_kernel<T>, grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+  } else if (out == LS_OUT_NHWC_BULK) {
     smem = (size_t)LS_TILE * 64 * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
     LS_SPLAT(LS_OUT_NHWC_BULK, 64);
   } else if (out == LS_OUT_NHWC_ROWS) {

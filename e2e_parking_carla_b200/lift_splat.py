@@ -30,8 +30,9 @@ class GridSpec:
     dim: Tuple[int, int, int]
 
 
-def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec) -> LsShape:
+def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec, geom_policy: int = 0) -> LsShape:
     s = LsShape()
+    s.geom_policy = geom_policy
     s.B, s.N, s.D, s.fh, s.fw, s.C = B, N, D, fh, fw, Cc
     s.X, s.Y, s.Z = grid.dim
     for i in range(3):
@@ -307,8 +308,8 @@ class LiftSplatFunction(torch.autograd.Function):
 
 
 def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, t: torch.Tensor,
-               frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format, spare_channels: int = 0
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+               frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format, spare_channels: int = 0,
+               geom_policy: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """feat [B*N,C,fh,fw], depth_logits [B*N,D,fh,fw] (CamEncoder outputs,
     model/cam_encoder.py:102-111), M [B,N,3,3], t [B,N,3], frustum [D,fh,fw,3] ->
     (bev f32[B,C,X,Y] in ``bev_format``, depth_prob [B*N,D,fh,fw])."""
@@ -320,5 +321,82 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
                          (tuple(feat.shape), tuple(depth_logits.shape), B, N))
     if tuple(frustum.shape) != (D, fh, fw, 3):
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
-    shape = make_shape(B, N, D, fh, fw, Cc, grid)
+    shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy)
     return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format, spare_channels)
+
+
+# --------------------------------------------------------------------------------------
+# compatibility: proj_bev_feature(geom, x) on a MATERIALISED frustum tensor
+# --------------------------------------------------------------------------------------
+class ProjBevFunction(torch.autograd.Function):
+    """``BevModel.proj_bev_feature(geom, image_feature)`` of the reference API
+    (model/bev_model.py:74-107): voxelise the given ego-frame coordinates, keep / rank / sort,
+    VoxelsSumming, scatter - for callers that already hold the B x N x D x h x w x C tensor the
+    fused path never builds.  Runs on the same kernels: every frustum point is treated as a
+    "pixel" of its own with one depth bin of weight 1, its C-vector as that pixel's feature row
+    (so the only extra cost is the contiguous [B*Npts, C] copy of ``image_feature``).
+    Gradient: every kept point receives its cell's gradient row (tool/geometry.py:307-317);
+    ``geom`` gets none (cut by ``.long()``, bev_model.py:86)."""
+
+    @staticmethod
+    def forward(ctx, geom, x, grid: GridSpec, bev_format):
+        _need_cuda(geom, x)
+        lib = _lib.load()
+        B = x.shape[0]
+        Cc = x.shape[-1]
+        npts = x[0].numel() // Cc
+        if geom.shape[0] != B or geom[0].numel() != 3 * npts:
+            raise ValueError("geom %s does not match image_feature %s" % (tuple(geom.shape), tuple(x.shape)))
+        code = _dtype_code(x)
+        cp = padded_channels(Cc)
+        rows = x.reshape(B * npts, Cc)
+        if cp != Cc:
+            rows = torch.nn.functional.pad(rows, (0, cp - Cc))
+        rows = rows.contiguous()
+        # one "camera", one depth bin, fh x fw = Npts pseudo-pixels (fw: any divisor, for grid shapes)
+        fw = next(f for f in (1024, 512, 256, 128, 64, 32, 16, 8, 4, 2, 1) if npts % f == 0)
+        shape = make_shape(B, 1, 1, npts // fw, fw, Cc, grid)
+        dev = x.device
+        g32 = geom.detach().to(torch.float32).reshape(B, npts, 3).contiguous()
+        tiles, cells, stride = grid_cells(shape)
+        cell = torch.empty(B, npts, dtype=torch.int32, device=dev)
+        within = torch.empty_like(cell)
+        counts = torch.zeros(B, cells, dtype=torch.int32, device=dev)
+        check(lib.ls_index_geom(_ptr(g32), C.byref(shape), None, _ptr(cell), _ptr(within), _ptr(counts), _stream(x)),
+              "ls_index_geom")
+        ones = torch.ones(B, 1, npts // fw, fw, dtype=x.dtype, device=dev)
+        need_bwd = bool(ctx.needs_input_grad[1])
+        seg, order, recs, pix = sort(cell, within, counts, ones, shape, with_pixel_index=need_bwd)
+        recs2 = torch.empty(B, int(lib.ls_sorted_records(C.byref(shape))), 2, dtype=torch.int32, device=dev)
+        bev = torch.empty((B, Cc, shape.X, shape.Y), dtype=torch.float32, device=dev, memory_format=bev_format)
+        st = _bev_strides(bev)
+        check(lib.ls_splat_fwd(_ptr(rows), code, _ptr(recs), _ptr(seg), _ptr(order), _ptr(recs2), C.byref(shape),
+                               _ptr(bev), C.byref(st), _stream(x)), "ls_splat_fwd")
+        ctx.shape, ctx.code, ctx.x_shape, ctx.cp = shape, code, x.shape, cp
+        if need_bwd:
+            ctx.save_for_backward(rows, pix, seg)
+        return bev
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        rows, pix, seg = ctx.saved_tensors
+        shape, code = ctx.shape, ctx.code
+        dev = rows.device
+        grad_bev = grad_bev.to(torch.float32)
+        if not _grad_layout_ok(grad_bev):
+            grad_bev = grad_bev.contiguous()
+        npts = rows.shape[0] // shape.B
+        gT = torch.empty(shape.B, shape.X * shape.Y + 1, ctx.cp, dtype=torch.float32, device=dev)
+        gprob = torch.empty(rows.shape[0], dtype=torch.float32, device=dev)
+        grows = torch.empty_like(rows)
+        st = _bev_strides(grad_bev)
+        check(_lib.load().ls_splat_bwd(_ptr(grad_bev), C.byref(st), _ptr(rows), code, _ptr(pix), _ptr(seg),
+                                       C.byref(shape), _ptr(gT), _ptr(gprob), _ptr(grows), _stream(rows)),
+              "ls_splat_bwd")
+        return None, grows[:, :ctx.x_shape[-1]].reshape(ctx.x_shape), None, None
+
+
+def proj_bev(geom: torch.Tensor, image_feature: torch.Tensor, grid: GridSpec,
+             bev_format=torch.contiguous_format) -> torch.Tensor:
+    """geom [B,N,D,h,w,3], image_feature [B,N,D,h,w,C] -> bev f32[B,C,X,Y]."""
+    return ProjBevFunction.apply(geom, image_feature, grid, bev_format)

@@ -175,8 +175,10 @@ class ControlStandIn(nn.Module):
     def _decode(self, memory, tgt, emb):
         L = tgt.shape[1]
         causal = torch.full((L, L), float("-inf"), device=tgt.device).triu(1)
+        # tgt_is_causal=False: use the mask as given; the default (None) makes torch compare it with a
+        # causal mask on the host (a device->host sync per call, and not capturable in a CUDA graph)
         y = self.decoder(tgt=emb.transpose(0, 1), memory=memory.transpose(0, 1), tgt_mask=causal,
-                         tgt_key_padding_mask=(tgt == self.pad))
+                         tgt_key_padding_mask=(tgt == self.pad), tgt_is_causal=False)
         return self.out(y.transpose(0, 1))
 
     def forward(self, memory, tgt):

@@ -102,50 +102,47 @@ def agent_benchmark(iters, warmup, device, lift_splat="b200", use_graph=True):
         centroid = torch.stack([(slot.float().sum(1) * xs).sum() / n, (slot.float().sum(0) * xs).sum() / n])
         return tokens, centroid
 
+    def measure(run_once):
+        dev_ms, wall_ms = [], []
+        for i in range(iters + warmup):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            tokens, centroid = run_once()
+            e1.record()
+            host = (tokens.cpu(), centroid.cpu())         # what the agent consumes next (syncs)
+            t1 = time.perf_counter()
+            if i >= warmup:
+                dev_ms.append(e0.elapsed_time(e1))
+                wall_ms.append((t1 - t0) * 1e3)
+        dev_ms.sort()
+        wall_ms.sort()
+        q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]
+        return {"device_ms": {"p50": q(dev_ms, 0.5), "p99": q(dev_ms, 0.99), "mean": statistics.fmean(dev_ms)},
+                "wall_ms": {"p50": q(wall_ms, 0.5), "p99": q(wall_ms, 0.99), "mean": statistics.fmean(wall_ms)}}
+
+    res = {}
     with torch.no_grad():
         for _ in range(warmup):
             tick()
         torch.cuda.synchronize()
-        graph = None
+        res["stream"] = measure(tick)
         if use_graph:
+            # the whole tick as one CUDA graph (the library is capture-safe: no allocation, no host sync;
+            # the target-pixel noise draws from the graph-registered generator)
             try:
                 g = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    tick()
-                torch.cuda.current_stream().wait_stream(side)
                 with torch.cuda.graph(g):
                     out = tick()
-                graph = (g, out)
-            except Exception as exc:      # keep the stream-launched path
-                graph = None
-                graph_error = repr(exc)[:200]
-        res = {}
-        for name in (["stream"] + (["graph"] if graph else [])):
-            dev_ms, wall_ms = [], []
-            for i in range(iters + warmup):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                e0.record()
-                if name == "graph":
-                    graph[0].replay()
-                    tokens, centroid = graph[1]
-                else:
-                    tokens, centroid = tick()
-                e1.record()
-                host = (tokens.cpu(), centroid.cpu())         # what the agent consumes next
-                t1 = time.perf_counter()
-                if i >= warmup:
-                    dev_ms.append(e0.elapsed_time(e1))
-                    wall_ms.append((t1 - t0) * 1e3)
-            dev_ms.sort()
-            wall_ms.sort()
-            q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]
-            res[name] = {"device_ms": {"p50": q(dev_ms, 0.5), "p99": q(dev_ms, 0.99), "mean": statistics.fmean(dev_ms)},
-                         "wall_ms": {"p50": q(wall_ms, 0.5), "p99": q(wall_ms, 0.99), "mean": statistics.fmean(wall_ms)}}
-        if use_graph and not graph:
-            res["graph_error"] = graph_error
+
+                def replay():
+                    g.replay()
+                    return out
+
+                res["graph"] = measure(replay)
+            except Exception as exc:
+                res["graph_error"] = repr(exc)[:400]
     res["iters"], res["warmup"], res["lift_splat"] = iters, warmup, lift_splat
     return res

@@ -48,7 +48,17 @@ typedef struct LsShape {
   int32_t X, Y, Z;     /* bev_dim                                               */
   float start[3];      /* bev_start_pos                                         */
   float res[3];        /* bev_res                                               */
+  int32_t geom_policy; /* LsGeomPolicy: float32 evaluation order of M.(u*d, v*d, d) + t    */
 } LsShape;
+
+/* model/bev_model.py:54 is a broadcast batched 3x3 matmul; its float32 rounding depends on the
+ * device the reference runs on, and 1 ulp decides voxel indices of points on cell boundaries:
+ *   LS_GEOM_TORCH_CPU   ((m0*px + m1*py) + m2*pz) + t, every product and sum rounded (aten's CPU
+ *                       kernel; what the golden fixtures pin)
+ *   LS_GEOM_TORCH_CUDA  (fma(m1, py, m0*px) + m2*pz) + t: what torch's CUDA matmul (cuBLAS batched
+ *                       SGEMM, m=3 n=1 k=3) computes on a B200 - probed bit for bit with
+ *                       tools/geom_policy_probe.py, pinned by tests/test_gpu_parity.py */
+typedef enum LsGeomPolicy { LS_GEOM_TORCH_CPU = 0, LS_GEOM_TORCH_CUDA = 1 } LsGeomPolicy;
 
 /* Element strides of a BEV tensor of logical shape [B, C, X, Y] (the reference's bev_feature,
  * model/bev_model.py:76,105, and the gradient arriving on it).  Two families are accepted:
@@ -107,6 +117,12 @@ int ls_geometry(const float* M, const float* t, const float* frustum, const LsSh
  *   counts i32[B,cells_padded] per-cell histogram (int atomics)} on entry            */
 int ls_index(const float* M, const float* t, const float* frustum, const LsShape* s,
              int32_t* rank, int32_t* cell, int32_t* within, int32_t* counts, ls_stream_t stream);
+
+/* a6.1-a6.3 from GIVEN coordinates - the index half of proj_bev_feature(geom, x)
+ * (model/bev_model.py:74-107, the reference's public method that takes a materialised geom):
+ * geom f32[B,Npts,3] in the reference's point order; outputs as ls_index. */
+int ls_index_geom(const float* geom, const LsShape* s, int32_t* rank, int32_t* cell, int32_t* within,
+                  int32_t* counts, ls_stream_t stream);
 
 /* Debug/test export in the reference's own convention (model/bev_model.py:85-97):
  * vox i64[B,Npts,3] = .long() of the voxel coordinate (INT64_MIN where x86 gives

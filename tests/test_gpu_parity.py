@@ -501,12 +501,14 @@ def test_plain_stream_order_matches(lib):
         "for k in ('bev', 'prob', 'gfeat', 'glogits'): h.update(getattr(st, k).cpu().numpy().tobytes())\n"
         "print('DIGEST', h.hexdigest())\n" % root)
     digests = []
-    for extra in ({}, {"LS_NO_PDL": "1", "LS_NO_SIDE_STREAMS": "1"}):
+    # ... and LS_SPLAT_OUT=bulk: the shared-memory-tile splat that leaves as one bulk (TMA) store per tile
+    # instead of the default direct row stores
+    for extra in ({}, {"LS_NO_PDL": "1", "LS_NO_SIDE_STREAMS": "1"}, {"LS_SPLAT_OUT": "bulk"}):
         env = dict(os.environ, **extra)
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
-    assert digests[0] == digests[1]
+    assert digests[0] == digests[1] == digests[2]
 
 
 def test_many_tiles_single_cta_scan(lib):
@@ -819,6 +821,8 @@ def test_add_target_bev_matches_reference_semantics(lib):
     target = torch.tensor([[1.3, -2.7, 0.0], [-9.9, 0.2, 0.0], [7.9, 7.9, 0.0], [-3.3, 9.7, 0.0]], device=DEV)
     images = torch.zeros(4, 4, 3, 8, 8, device=DEV)
     conv = torch.nn.Conv2d(65, 4, 3, padding=1).to(DEV)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False       # the consumer conv is not what is under test
     results = []
     for fmt, spare in ((torch.contiguous_format, 0), (torch.channels_last, 0), (torch.channels_last, 1)):
         enc = Preset()
@@ -840,8 +844,74 @@ def test_add_target_bev_matches_reference_semantics(lib):
         conv.zero_grad()
         (conv(wide).square().sum() + depth.sum()).backward()
         results.append((bev.detach().clone(), enc.feat.grad.clone(), enc.logits.grad.clone()))
+    torch.backends.cudnn.allow_tf32 = tf32
     for r in results[1:]:
         assert torch.equal(r[0], results[0][0])
-        # the gradient handed to the backward differs only in layout; conv's own backward may pick
+        # the gradient handed to the backward differs only in layout; conv's own backward picks
         # another algorithm per layout, so compare to tolerance, not bits
-        assert relerr(r[1], results[0][1]) < 1e-5 and relerr(r[2], results[0][2]) < 1e-5
+        assert relerr(r[1], results[0][1]) < 1e-4 and relerr(r[2], results[0][2]) < 1e-4
+
+
+def test_proj_bev_feature_compat_api(lib):
+    """The reference's three-call form get_geometry -> encoder_forward -> proj_bev_feature
+    (model/bev_model.py:109-113) on the materialised tensors gives the fused path's result
+    (forward <= 1e-5; identical zero pattern) and gradients reach the encoder."""
+    from e2e_parking_carla_b200 import BevModel
+
+    class Preset(torch.nn.Module):
+        def forward(self, images):
+            return self.feat, self.logits
+
+    shape = LiftSplatShape(batch=2, channels=8)
+    c = _oracle_case(shape, rig_seed=52, in_seed=22)
+    ref = _oracle_outputs(shape, c)
+    intr, extr = make_rig(2, 4, jitter=True, seed=52)
+    images = torch.zeros(2, 4, 3, 8, 8, device=DEV)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        enc = Preset()
+        enc.feat = c["feat"].to(DEV).requires_grad_(True)
+        enc.logits = c["logits"].to(DEV).requires_grad_(True)
+        model = BevModel(make_cfg(shape), cam_encoder=enc, bev_memory_format=fmt).to(DEV)
+        geom = model.get_geometry(intr.to(DEV), extr.to(DEV))
+        x, prob = model.encoder_forward(images)
+        assert tuple(x.shape) == (2, 4, 48, 32, 32, 8)
+        bev = model.proj_bev_feature(geom, x)
+        assert_close(bev, ref["bev"], FP32_TOL, "bev")
+        assert np.array_equal(bev.detach().cpu().numpy() == 0, ref["bev"] == 0)
+        torch.autograd.backward([bev, prob], [c["gb"].to(DEV), c["gp"].to(DEV)])
+        assert_close(enc.feat.grad, ref["grad_feat"], FP32_TOL, "grad_feat")
+        assert_close(enc.logits.grad, ref["grad_logits"], FP32_TOL, "grad_logits")
+
+
+# ------------------------------------------------------------------------------------
+# a4 on the reference's own device: geometry="torch" == the reference's torch ops on this GPU
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["rigA_b1", "rigB_b16", "stress_b2"])
+def test_torch_geometry_same_device_rank_parity(lib, case):
+    """The reference hard-codes .cuda() (model/bev_model.py:46,53): its real path inverts with
+    cuSOLVER and multiplies with cuBLAS.  BevModel(geometry="torch") takes M, t from the same
+    torch calls and evaluates the per-point transform in cuBLAS's float32 order
+    (LS_GEOM_TORCH_CUDA, probed with tools/geom_policy_probe.py): every voxel rank equals the one
+    the reference's own op chain (oracle/torch_port.py on CUDA tensors) produces on this GPU."""
+    from oracle import torch_port as tp
+    from e2e_parking_carla_b200 import BevModel
+    ls = _ls()
+    shape, jitter, seed = {"rigA_b1": (LiftSplatShape(batch=1, channels=4), False, 0),
+                           "rigB_b16": (LiftSplatShape(batch=16, channels=4), True, 1),
+                           "stress_b2": (LiftSplatShape.stress(batch=2), True, 61)}[case]
+    intr, extr = make_rig(shape.batch, shape.cams, jitter=jitter, seed=seed)
+    res, start, dim = grid_of(shape)
+    fr = _dev(frustum_of(shape))
+    want = tp.ranks_cpu(intr.to(DEV), extr.to(DEV), fr, _dev(start), _dev(res), [int(v) for v in dim])
+    model = BevModel(make_cfg(shape), cam_encoder=torch.nn.Identity(), geometry="torch").to(DEV)
+    M, t = model.camera_transform(intr.to(DEV), extr.to(DEV))
+    s = model._shape(shape.batch, shape.cams, 4)
+    assert s.geom_policy == 1
+    got = ls.index(M, t, fr, s)
+    flips = int((got.long() != want).sum())
+    assert flips == 0, "%d of %d ranks differ from the reference's torch-CUDA run" % (flips, want.numel())
+    # the CPU-order policy on the same M, t is NOT the same function (that is the point of the policy)
+    s_cpu = ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw, 4, _grid_spec(shape))
+    geom_cuda = ls.geometry(M, t, fr, s)
+    assert not torch.equal(geom_cuda, ls.geometry(M, t, fr, s_cpu))
+    assert torch.equal(geom_cuda, tp.camera_geometry(fr, intr.to(DEV), extr.to(DEV)))

@@ -64,6 +64,13 @@ def main():
     for name, g in cands.items():
         _, _, r = lo.voxel_index(g, start, res, dim)
         out[name] = {"coords_differ": int((g != geom_gpu).sum()), "rank_flips": int((r != rank_gpu).sum())}
+    # a slice for offline search of the evaluation order: camera (0,0), every 13th point
+    sel = np.arange(0, geom_gpu[0, 0].size // 3, 13)
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "geom_probe_sample.npz"), M=M[0, 0], t=t[0, 0],
+                        px=np.broadcast_to(px, geom_gpu.shape[:-1])[0, 0].reshape(-1)[sel],
+                        py=np.broadcast_to(py, geom_gpu.shape[:-1])[0, 0].reshape(-1)[sel],
+                        pz=np.broadcast_to(pz, geom_gpu.shape[:-1])[0, 0].reshape(-1)[sel],
+                        geom=geom_gpu[0, 0].reshape(-1, 3)[sel])
     print(json.dumps(out))
 
 
