@@ -90,6 +90,37 @@ def measured_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and the pinned host buffers it allocates from now on: first touch) to the
+    NUMA node the GPU hangs off.  Without it every rank of an 8-GPU run stages its 2 x 206 MB per step
+    through whatever node the allocator happened to pick, and the host-to-host number stops scaling
+    long before PCIe does (round 1: 0.19 efficiency at 8 GPUs).  Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+def unbind_cpus(saved):
+    try:
+        os.sched_setaffinity(0, saved)
+    except Exception:
+        pass
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML polled every
     ~2 ms from a thread (the timed loop blocks in CUDA calls with the GIL released).  Falls
@@ -203,8 +234,9 @@ class Stepper:
         model = BevModel(make_cfg(shape), cam_encoder=torch.nn.Identity())
         self.grid = model._grid
         self.frustum = model.frustum.data.to(device)
+        self.tile_x = ls.pick_tile_x(shape.channels, bev_format == "channels_last")
         self.s = ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw, shape.channels,
-                               self.grid)
+                               self.grid, 0, self.tile_x)
         self.code = ls.LS_F32 if dtype == torch.float32 else ls.LS_BF16
         intr, extr = make_rig(shape.batch, shape.cams, jitter=True, seed=1 + seed)
         feat, logits = make_encoder_outputs(shape, seed=seed)
@@ -305,7 +337,7 @@ class Stepper:
             sizes = _e2e_sizes(sh.batch, chunks)
             starts = [sum(sizes[:i]) for i in range(len(sizes))]
             groups = [(lo, lo + sz) for lo, sz in zip(starts, sizes)]
-            shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid)
+            shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid, 0, self.tile_x)
                       for lo, hi in groups]
             self._e2e = {"chunks": chunks, "groups": groups, "shapes": shapes, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
                          "scratch": [torch.empty(ls.scratch_bytes(sc, self.code, True), dtype=torch.uint8,
@@ -562,6 +594,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = bind_to_gpu_numa_node(local)
+    config["host_numa_node"] = numa_node
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -603,6 +638,7 @@ def main():
     e1.record()
     barrier()
     launches = st.graph_launches * args.steps if use_graph else int(lib.ls_launch_count() - l0)
+    graph_kernels = st.graph_launches if use_graph else None
     ms = e0.elapsed_time(e1)
     # end to end: host buffers in/out, same number of steps
     for _ in range(2):
@@ -632,25 +668,44 @@ def main():
     e2e_value = shape.batch * world / (ms_e2e / e2e_steps * 1e-3)
     h2d, d2h = st.e2e_bytes()
 
+    stages = st.stage_times(min(args.steps, 20)) if rank == 0 else None
+    graph_launches = st.graph_launches if use_graph else 0
+    del st
+    if use_graph:
+        del graph
+    torch.cuda.empty_cache()
+    train = None
+    if not args.no_train:
+        # BASELINE.json configs[2] in short: the full training step with DDP's NCCL gradient all-reduce in
+        # the timed region, on every rank (python bench.py --workload train runs it longer, on its own)
+        from harness import run as hr
+        try:
+            train = hr.train_benchmark(args.train_batch, 8, 3, rank, world, device, "b200", e2e_steps=4)
+        except Exception as exc:          # never lose the hot-path line to the harness
+            train = {"error": repr(exc)[:300]}
+    unbind_cpus(all_cpus)
     if rank == 0:
-        stages = st.stage_times(min(args.steps, 20))
         peak, peak_src = measured_peak()
         ab = algorithmic_bytes(shape, s_in)
-        # dominant kernel of the step and its own algorithmic traffic
+        # dominant kernel group of the step and its own algorithmic traffic
         cand = {"splat_fwd": stages["splat_fwd"], "splat_bwd(transpose+gather)": stages["splat_bwd(transpose+gather)"]}
         dom = max(cand, key=cand.get)
+        staged = args.bev_format == "nchw"
         dom_bytes = (ab["splat_fwd"] if dom == "splat_fwd" else ab["bwd_transpose"] + ab["bwd_gather"]) * shape.batch
         achieved = dom_bytes / (cand[dom] * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:   # DRAM bytes (read+write) per launch of that stage from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = "%s/%s" % (args.workload, args.dtype)
+            key = "%s/%s/%s" % (args.workload, args.dtype, args.bev_format)
             if key in tj and dom in tj[key]:
                 traffic, traffic_src = tj[key][dom], tj.get("source")
         except Exception:
             pass
         step_bytes = (ab["fwd"] + ab["bwd"]) * shape.batch
         step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+        kernels = {"splat_fwd": "ls_canon_kernel + ls_splat_fwd_direct_kernel" if not staged else "ls_canon_kernel + ls_splat_fwd_kernel",
+                   "splat_bwd(transpose+gather)": "ls_bwd_gather_occ_kernel (gradient rows gathered in place)" if not staged
+                   else "ls_bwd_transpose_kernel + ls_bwd_gather_occ_kernel"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
@@ -663,18 +718,18 @@ def main():
                                 "gradients arrive (H2D / compute / D2H streams, one CUDA graph)"
                                 % "+".join(str(v) for v in _e2e_sizes(shape.batch, E2E_CHUNKS))},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "roofline": {"bound": "hbm", "kernel": dom, "kernels": kernels[dom], "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": cand[dom]},
                 "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": step_gbs / peak},
                 "stage_ms": stages, "clocks": clocks}
+        if train is not None:
+            line["train"] = train
         if not args.no_gpu_reference:
             # the reference's torch op chain on THIS GPU, full batch, its host syncs included (SURVEY.md 8d
             # "GPU reference (the real bar)"); context for `value`, like cpu_baseline
-            del st
-            torch.cuda.empty_cache()
             gr = reference_run(shape, shape.batch, 3, 2, "cuda")
             line["gpu_reference"] = {k: gr[k] for k in ("value", "unit", "kind", "sample", "ms_per_step")}
             line["gpu_reference"]["speedup_device"] = value / world / gr["value"]

@@ -9,18 +9,22 @@
 #include "ls_b200.h"
 
 // ---- BEV tiling ---------------------------------------------------------------------
-// The grid is cut into LS_TX x LS_TY voxel tiles; cells are numbered tile-major
-// (cell = tile*LS_TILE + lx*LS_TY + ly).  A tile is one CTA of the splat and of the gradient
-// transposer.  Tiles are small on purpose (many CTAs in different phases hide each other's
-// latencies) and long along y: a tile row is a contiguous run of the [B,C,X,Y] tensors, and
-// 512-byte runs (1 x 128) measured 3 % faster per step than 128-byte runs (4 x 32).
+// The grid is cut into tiles of LS_TILE = 128 cells, tx x ty (LsShape.tile_x; tx a power of two
+// dividing 128); cells are numbered tile-major (cell = tile*128 + lx*ty + ly).  A tile is one CTA
+// of the canonicaliser and of the splat.
+//   1 x 128  long runs of one x-row: what the NCHW write-out / gradient staging need (a tile row is
+//            a contiguous 512-byte run of every channel plane) - LS_TX / LS_TY below, compile time;
+//   8 x 16   (or any other tx) for the channels-last direct splat, whose output unit is a cell's own
+//            256-byte row, so the tile can be square: a ray then stays inside the tile for ~3.6
+//            consecutive depth bins instead of 1.15 and its feature row is re-read from L1, not L2.
 #ifndef LS_TX
-#define LS_TX 1                      // x-rows per tile (LS_TX * LS_TY must be 128 or 256)
+#define LS_TX 1                      // x-rows per tile of the compile-time (NCHW) geometry
 #endif
 #ifndef LS_TY
-#define LS_TY 128                    // y-columns per tile
+#define LS_TY 128                    // y-columns per tile of the compile-time (NCHW) geometry
 #endif
 #define LS_TILE (LS_TX * LS_TY)      // cells per tile (cell-in-tile fits 8 bits)
+static_assert(LS_TX == 1 && LS_TY == 128, "the tile kernels of the NCHW path assume 1 x 128 strips");
 #define LS_CCHUNK 64                 // channels per pass
 #define LS_THREADS LS_TILE           // tile kernels: one thread per cell of the tile
 #ifndef LS_GATHER_THREADS
@@ -36,6 +40,8 @@
 struct LsGrid {
   int X, Y, Z;
   int XY;          // X * Y: cells of one sample in the reference's row-major rank order
+  int tx, ty;      // tile shape (tx * ty == LS_TILE), powers of two
+  int tx_shift, ty_shift;
   int tiles_x, tiles_y, tiles;
   int Vc;          // padded cell count = tiles * LS_TILE
   int seg_stride;  // Vc + LS_SEG_PAD
@@ -71,8 +77,14 @@ static inline LsDims ls_dims(const LsShape* s) {
 static inline LsGrid ls_grid(const LsShape* s) {
   LsGrid g;
   g.X = s->X; g.Y = s->Y; g.Z = s->Z;
-  g.tiles_x = (s->X + LS_TX - 1) / LS_TX;
-  g.tiles_y = (s->Y + LS_TY - 1) / LS_TY;
+  g.tx = s->tile_x > 0 ? s->tile_x : 1;
+  g.ty = LS_TILE / g.tx;
+  g.tx_shift = 0;
+  while ((1 << g.tx_shift) < g.tx) ++g.tx_shift;
+  g.ty_shift = 0;
+  while ((1 << g.ty_shift) < g.ty) ++g.ty_shift;
+  g.tiles_x = (s->X + g.tx - 1) / g.tx;
+  g.tiles_y = (s->Y + g.ty - 1) / g.ty;
   g.tiles = g.tiles_x * g.tiles_y;
   g.Vc = g.tiles * LS_TILE;
   g.seg_stride = g.Vc + LS_SEG_PAD;
@@ -90,25 +102,25 @@ static inline LsGrid ls_grid(const LsShape* s) {
 }
 
 // (gx, gy) -> tile-major cell id (Z == 1)
-__host__ __device__ __forceinline__ int ls_cell_of_xy(int gx, int gy, int tiles_y) {
-  const int tile = (gx / LS_TX) * tiles_y + (gy / LS_TY);
-  return tile * LS_TILE + (gx % LS_TX) * LS_TY + (gy % LS_TY);
+__host__ __device__ __forceinline__ int ls_cell_of_xy(int gx, int gy, const LsGrid& g) {
+  const int tile = (gx >> g.tx_shift) * g.tiles_y + (gy >> g.ty_shift);
+  return tile * LS_TILE + ((gx & (g.tx - 1)) << g.ty_shift) + (gy & (g.ty - 1));
 }
 // tile-major cell id -> reference rank gx*Y + gy (-1 for padding cells outside the grid)
 __host__ __device__ __forceinline__ int ls_rank_of_cell(int cell, const LsGrid& g) {
   const int tile = cell / LS_TILE, local = cell % LS_TILE;
-  const int gx = (tile / g.tiles_y) * LS_TX + local / LS_TY;
-  const int gy = (tile % g.tiles_y) * LS_TY + local % LS_TY;
+  const int gx = (tile / g.tiles_y) * g.tx + (local >> g.ty_shift);
+  const int gy = (tile % g.tiles_y) * g.ty + (local & (g.ty - 1));
   return (gx < g.X && gy < g.Y) ? gx * g.Y + gy : -1;
 }
 
-// tile-major cell id -> rank without a hardware division (tile < 2^21 and tiles_y < 2^21 are
-// guaranteed by ls_check_splat_shape: (tile * magic) >> 42 is then exact)
+// the same for a cell known to lie inside the grid, without a hardware division (tile < 2^21 and
+// tiles_y < 2^21 are guaranteed by ls_check_splat_shape: (tile * magic) >> 42 is then exact)
 __device__ __forceinline__ int ls_rank_of_cell_fast(int cell, const LsGrid& g) {
-  static_assert(LS_TX == 1, "row-major shortcut assumes one x-row per tile");
   const unsigned tile = (unsigned)cell / LS_TILE, local = (unsigned)cell % LS_TILE;
-  const unsigned gx = (unsigned)(((unsigned long long)tile * g.ty_magic) >> 42);
-  const unsigned gy = (tile - gx * (unsigned)g.tiles_y) * LS_TY + local;
+  const unsigned tgx = (unsigned)(((unsigned long long)tile * g.ty_magic) >> 42);
+  const unsigned gx = (tgx << g.tx_shift) + (local >> g.ty_shift);
+  const unsigned gy = ((tile - tgx * (unsigned)g.tiles_y) << g.ty_shift) + (local & (unsigned)(g.ty - 1));
   return (int)(gx * (unsigned)g.Y + gy);
 }
 
@@ -118,6 +130,8 @@ enum LsBevOut {
   LS_OUT_NCHW_SCALAR = 1,  // y stride 1, anything else
   LS_OUT_NHWC_BULK = 2,    // c stride 1, dense 64-channel rows: the tile leaves as ONE bulk (TMA) store
   LS_OUT_NHWC_ROWS = 3,    // c stride 1, any row pitch / channel count: coalesced 4-byte stores
+  LS_OUT_NHWC_DIRECT_VEC = 4,     // c stride 1, 64 channels of a wider 16-byte aligned row: direct row stores
+  LS_OUT_NHWC_DIRECT_SCALAR = 5,  // the same with unaligned rows (64 of 65 channels)
   LS_OUT_BAD = -1
 };
 enum LsGradIn {

@@ -147,7 +147,7 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
 #pragma unroll
     for (int k = 0; k < LS_IDX_ILP; ++k) {
       if (keep[k]) {
-        cid[k] = ls_cell_of_xy(vx[k][0], vx[k][1], grid.tiles_y);
+        cid[k] = ls_cell_of_xy(vx[k][0], vx[k][1], grid);
         tk[k] = atomicAdd(&counts[(size_t)b * grid.Vc + cid[k]], 1);
       }
     }

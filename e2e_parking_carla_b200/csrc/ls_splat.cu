@@ -366,9 +366,7 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
 // K3c: forward splat for a dense channels-last BEV tensor, WITHOUT the shared-memory tile.
 // With rows as the unit of both accumulation and output there is nothing to transpose: a
 // quarter-warp that finishes a cell writes its 256-byte row straight to global memory, cells
-// nobody hits get their zero rows from the warp that owns them, and cells cut by a piece
-// boundary are finished with read-modify-writes of the row after the barrier (same fixed
-// association as the tile version, so the same bits).  What this buys: the 32 KB per CTA that
+// nobody hits get their zero rows from the warp that owns them.  What this buys: the 32 KB per CTA that
 // the tile took from the unified L1/shared array stay L1 - the feature rows a tile re-reads
 // (the same ray crosses it in consecutive depth bins) are served on-chip instead of going back
 // to L2, which the tile version saturates (9.6 of ~12.4 TB/s of L2 throughput).
@@ -376,30 +374,42 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
 #ifndef LS_SPLATD_MINB
 #define LS_SPLATD_MINB 6
 #endif
-template <typename T>
+// 16 bytes of a row: one vector access when rows are 16-byte aligned (row pitch a multiple of 4
+// floats), four scalar ones otherwise (a 64-channel slice of a 65-channel tensor: 260-byte pitch)
+template <bool kVec> __device__ __forceinline__ void ls_row_store4(float* g, float4 v) {
+  if (kVec) { __stcs(reinterpret_cast<float4*>(g), v); }
+  else { __stcs(g, v.x); __stcs(g + 1, v.y); __stcs(g + 2, v.z); __stcs(g + 3, v.w); }
+}
+template <bool kVec> __device__ __forceinline__ float4 ls_row_load4_cg(const float* g) {
+  if (kVec) return __ldcg(reinterpret_cast<const float4*>(g));
+  return make_float4(__ldcg(g), __ldcg(g + 1), __ldcg(g + 2), __ldcg(g + 3));
+}
+
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(LS_THREADS, LS_SPLATD_MINB)
 ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
                            const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm,
                            LsGrid grid, float* __restrict__ bev, LsBevStrides st) {
   constexpr int kC = 64;
-  __shared__ int part_cell[LS_QWARPS];
-  __shared__ int ends[2];
+  __shared__ int seg[LS_TILE + 1];
   const int b = blockIdx.x % dm.B;
   const int tid = threadIdx.x;
   ls_pdl_trigger();
   ls_pdl_wait();
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
-  const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
+  const int tx0 = (tile_id / grid.tiles_y) << grid.tx_shift, ty0 = (tile_id % grid.tiles_y) << grid.ty_shift;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
-  float* tile0 = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * kC;
-  // row of cell-in-tile cl (floats from tile0)
-  auto row_off = [&](unsigned cl) -> size_t { return (size_t)(cl / LS_TY) * (size_t)st.x + (size_t)(cl % LS_TY) * kC; };
+  float* tile0 = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * st.y;
+  // row of cell-in-tile cl (floats from tile0): tile row cl / ty, column cl % ty
+  const unsigned ty_shift = (unsigned)grid.ty_shift, ty_mask = (unsigned)grid.ty - 1u;
+  const unsigned sxu = (unsigned)st.x, syu = (unsigned)st.y;      // < 2^32 floats (checked by the classifier)
+  auto row_off = [&](unsigned cl) -> size_t { return (size_t)((cl >> ty_shift) * sxu) + (size_t)((cl & ty_mask) * syu); };
   {
     // this thread's cell: empty cells inside the grid get a zero row (the BEV tensor is never memset)
     const int a = __ldg(segg + tid), e = __ldg(segg + tid + 1);
-    if (tid == 0) ends[0] = a;
-    if (tid == LS_TILE - 1) ends[1] = e;
-    const bool in_grid = (tx0 + tid / LS_TY) < grid.X && (ty0 + tid % LS_TY) < grid.Y;
+    seg[tid] = a;
+    if (tid == LS_TILE - 1) seg[LS_TILE] = e;
+    const bool in_grid = (tx0 + (int)((unsigned)tid >> ty_shift)) < grid.X && (ty0 + (int)((unsigned)tid & ty_mask)) < grid.Y;
     unsigned m = __ballot_sync(0xffffffffu, in_grid && a == e);
     const int lane = tid & 31, wbase = tid & ~31;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -409,34 +419,46 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
       int c1 = -1;
       if (m) { c1 = __ffs(m) - 1; m &= m - 1; }
       const int c = lane < 16 ? c0 : c1;
-      if (c >= 0) __stcs(reinterpret_cast<float4*>(tile0 + row_off(wbase + c)) + (lane & 15), z);
+      if (c >= 0) ls_row_store4<kVec>(tile0 + row_off(wbase + c) + 4 * (lane & 15), z);
     }
   }
   __syncthreads();
-  const int s0 = ends[0], s1 = ends[1];
+  const int s0 = seg[0], s1 = seg[LS_TILE];
   if (s0 == s1) return;
+  // Pieces: quarter-warp q takes the records from the start of the cell that holds record
+  // s0 + q*n/16 to the start of the cell that holds record s0 + (q+1)*n/16 - equal shares rounded
+  // down to cell boundaries, so every cell is summed by ONE quarter-warp, front to back, in
+  // canonical order: the bits of a cell do not depend on the tiling or on where the cuts fall.
   const int ql = tid & 7, qw = tid >> 3, n = s1 - s0;
+  auto cut = [&](int q) -> int {
+    if (q >= LS_QWARPS) return s1;
+    const int target = s0 + (int)(((long long)q * n) / LS_QWARPS);
+    int lo = 0, hi = LS_TILE;                    // largest cell with seg[cell] <= target
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (seg[mid] <= target) lo = mid; else hi = mid - 1;
+    }
+    return seg[lo];
+  };
+  int idx = cut(qw);
+  const int end = cut(qw + 1);
+  if (idx >= end) return;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * kC;
   const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
   unsigned row_bytes = (unsigned)(kC * sizeof(T));
   asm volatile("" : "+r"(row_bytes));
-  int idx = s0 + (int)(((long long)qw * n) / LS_QWARPS);
-  const int end = s0 + (int)(((long long)(qw + 1) * n) / LS_QWARPS);
   const char* f0 = reinterpret_cast<const char*>(fbase + 4 * ql);
   const unsigned f1off = (unsigned)(32 * sizeof(T));
   float* lane0 = tile0 + 4 * ql;                  // this lane's first quad of row 0
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int pc = -1;
-  if (idx < end) {
-    const int xl = __ldg(&rs[end - 1].x);
-    if (!(xl & LS_REC_LAST)) pc = xl & 255;
-    const int2* p = rs + idx;
-    int2 r[LS_QWIN], rn[LS_QWIN];
+  const int2* p = rs + idx;
+  int2 r[LS_QWIN], rn[LS_QWIN];
 #pragma unroll
-    for (int u = 0; u < LS_QWIN; ++u) {
-      r[u] = p[u];
-      if (idx + u >= end) r[u] = make_int2(0, 0);
-    }
+  for (int u = 0; u < LS_QWIN; ++u) {
+    r[u] = p[u];
+    if (idx + u >= end) r[u] = make_int2(0, 0);
+  }
 #define LS_SPLATD_WINDOW(cur, nxt)                                                                   \
   {                                                                                                  \
     float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
@@ -458,51 +480,20 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
       }                                                                                              \
       if (cur[u].x & LS_REC_LAST) {                                                                  \
         float* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                       \
-        __stcs(reinterpret_cast<float4*>(g), acc0);                                                  \
-        __stcs(reinterpret_cast<float4*>(g + 32), acc1);                                             \
+        ls_row_store4<kVec>(g, acc0);                                                                \
+        ls_row_store4<kVec>(g + 32, acc1);                                                           \
         acc0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
         acc1 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
       }                                                                                              \
     }                                                                                                \
   }
-    for (;;) {
-      LS_SPLATD_WINDOW(r, rn);
-      if (idx >= end) break;
-      LS_SPLATD_WINDOW(rn, r);
-      if (idx >= end) break;
-    }
+  for (;;) {
+    LS_SPLATD_WINDOW(r, rn);
+    if (idx >= end) break;
+    LS_SPLATD_WINDOW(rn, r);
+    if (idx >= end) break;
+  }
 #undef LS_SPLATD_WINDOW
-  }
-  if (ql == 0) part_cell[qw] = pc;
-  __syncthreads();
-  // open partial sums of cells cut by piece boundaries: same rounds as the tile version, the
-  // read-modify-write goes to the row in global memory (L2: the stores above are visible after
-  // the barrier; ld.cg never looks at a stale L1 line)
-  int depth = 0, maxd = -1;
-  {
-    int run = 0, prev = -1;
-#pragma unroll
-    for (int j = 0; j < LS_QWARPS; ++j) {
-      const int c = part_cell[j];
-      if (c >= 0) {
-        run = (c == prev) ? run + 1 : 0;
-        maxd = max(maxd, run);
-        prev = c;
-      }
-      if (j == qw) depth = run;
-    }
-  }
-  for (int rd = 0; rd <= maxd; ++rd) {
-    if (pc >= 0 && depth == rd) {
-      float* g = lane0 + row_off((unsigned)pc);
-      float4 t0 = __ldcg(reinterpret_cast<const float4*>(g)), t1 = __ldcg(reinterpret_cast<const float4*>(g + 32));
-      t0.x += acc0.x; t0.y += acc0.y; t0.z += acc0.z; t0.w += acc0.w;
-      t1.x += acc1.x; t1.y += acc1.y; t1.z += acc1.z; t1.w += acc1.w;
-      __stcg(reinterpret_cast<float4*>(g), t0);
-      __stcg(reinterpret_cast<float4*>(g + 32), t1);
-    }
-    __syncthreads();
-  }
 }
 
 int ls_debug_fetch_phase_cycles(unsigned long long* out8) {
@@ -542,8 +533,11 @@ static bool ls_bev_vec4(const float* p, const LsBevStrides& st, const LsGrid& g)
 int ls_classify_bev_out(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g) {
   if (st.y == 1 && (st.c != 1 || dm.C == 1)) return ls_bev_vec4(p, st, g) ? LS_OUT_NCHW_VEC4 : LS_OUT_NCHW_SCALAR;
   if (st.c == 1) {
-    const bool dense = dm.C == 64 && dm.Cp == 64 && st.y == 64 && (uintptr_t)p % 16 == 0 && st.b % 4 == 0 && st.x % 4 == 0;
-    return dense ? LS_OUT_NHWC_BULK : LS_OUT_NHWC_ROWS;
+    const bool vec = (uintptr_t)p % 16 == 0 && st.b % 4 == 0 && st.x % 4 == 0 && st.y % 4 == 0;
+    if (dm.C == 64 && st.y == 64 && vec) return LS_OUT_NHWC_BULK;            // dense rows: bulk or direct
+    if (dm.C == 64 && st.y >= 64 && st.x < (1LL << 32) && st.y < (1LL << 32))
+      return vec ? LS_OUT_NHWC_DIRECT_VEC : LS_OUT_NHWC_DIRECT_SCALAR;      // 64 channels of a wider row
+    return LS_OUT_NHWC_ROWS;
   }
   return LS_OUT_BAD;
 }
@@ -582,8 +576,13 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   // dense channels-last rows: direct row stores (no shared-memory tile, L1 kept for the feature
   // rows) unless LS_SPLAT_OUT=bulk asks for the one-bulk-store-per-tile (TMA) variant
   static const bool want_bulk = getenv("LS_SPLAT_OUT") && !strcmp(getenv("LS_SPLAT_OUT"), "bulk");
-  if (out == LS_OUT_NHWC_BULK && !want_bulk) {
-    LS_LAUNCH(ls_splat_fwd_direct_kernel<T>, grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+  const bool direct = out == LS_OUT_NHWC_DIRECT_VEC || out == LS_OUT_NHWC_DIRECT_SCALAR ||
+                      (out == LS_OUT_NHWC_BULK && !(want_bulk && g.tx == 1));
+  if (!direct && g.tx != 1) return LS_ERR_UNSUPPORTED;      // the tile kernels know 1 x 128 strips only
+  if (direct && out != LS_OUT_NHWC_DIRECT_SCALAR) {
+    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+  } else if (direct) {
+    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, false>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
   } else if (out == LS_OUT_NHWC_BULK) {
     smem = (size_t)LS_TILE * 64 * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
     LS_SPLAT(LS_OUT_NHWC_BULK, 64);
@@ -639,17 +638,18 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
   extern __shared__ float smem[];
   const LsTileGeom tg = ls_tile_geom(min(dm.Cp, LS_TCHUNK));
   float* tile = smem;
-  int* seg = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);
-  const int b = blockIdx.y, tile_id = blockIdx.x, tid = threadIdx.x;
+  int* hit = reinterpret_cast<int*>(smem + LS_TILE * tg.stride);      // [LS_TILE] does anybody read this cell's row?
+  // this kernel's own strips: 128 consecutive y of one x-row, whatever tiling the forward used
+  const int strips_y = (grid.Y + LS_TY - 1) / LS_TY;
+  const int b = blockIdx.y, strip = blockIdx.x, tid = threadIdx.x;
   const int cbase = blockIdx.z * LS_TCHUNK;
-  const int tx0 = (tile_id / grid.tiles_y) * LS_TX, ty0 = (tile_id % grid.tiles_y) * LS_TY;
-  const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  const int tx0 = strip / strips_y, ty0 = (strip % strips_y) * LS_TY;
   const int nquads = min(tg.cc, dm.Cp - cbase) >> 2;
   // thread = (4 consecutive y, x-row, channel quad): four 16-byte loads (4 channels) per pass.
-  // The gradient loads do not depend on the tile's offsets, so they are issued first and
+  // The gradient loads do not depend on the cell offsets, so they are issued first and
   // both round trips overlap.
-  const int y4 = tid % (LS_TY / 4), xr = (tid / (LS_TY / 4)) % LS_TX, q0 = tid / (LS_TILE / 4);
-  const int gx = tx0 + xr, gy = ty0 + 4 * y4;
+  const int y4 = tid % (LS_TY / 4), q0 = tid / (LS_TILE / 4);
+  const int gx = tx0, gy = ty0 + 4 * y4;
   constexpr int kPasses = LS_TCHUNK / 16;
   float4 c[kPasses][4];
   if (VEC4) {
@@ -667,17 +667,25 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
       }
     }
   }
-  for (int i = tid; i <= LS_TILE; i += LS_THREADS) seg[i] = segg[i];
-  if (tile_id == 0 && blockIdx.z == 0) {   // row X*Y of every sample = zeros: where dropped points gather from
-    float* zrow = gT + ((size_t)b * (grid.XY + 1) + grid.XY) * dm.Cp;
-    for (int i = tid; i < dm.Cp; i += LS_THREADS) zrow[i] = 0.0f;
+  {
+    // cell tid of the strip in the forward's tile-major numbering: hit by any point?
+    const int cy = ty0 + tid;
+    int h = 0;
+    if (cy < grid.Y) {
+      const int* seg = seg_start + (size_t)b * grid.seg_stride + ls_cell_of_xy(gx, cy, grid);
+      h = __ldg(seg + 1) != __ldg(seg);
+    }
+    hit[tid] = h;
+    if (strip == 0 && blockIdx.z == 0) {   // row X*Y of every sample = zeros: where dropped points gather from
+      float* zrow = gT + ((size_t)b * (grid.XY + 1) + grid.XY) * dm.Cp;
+      for (int i = tid; i < dm.Cp; i += LS_THREADS) zrow[i] = 0.0f;
+    }
+    if (!__syncthreads_or(h)) return;          // nobody reads this strip's gradient
   }
-  __syncthreads();
-  if (seg[0] == seg[LS_TILE]) return;          // nobody reads this tile's gradient
-  float* dst = gT + (size_t)b * (grid.XY + 1) * dm.Cp + cbase;     // + rank * Cp
+  float* dst = gT + ((size_t)b * (grid.XY + 1) + (size_t)gx * grid.Y + ty0) * dm.Cp + cbase;     // + cl * Cp
   if (VEC4) {
     // 4x4 register transpose, four 16-byte conflict-free shared stores (4 cells, one quad each)
-    const int clc = xr * LS_TY + 4 * y4;
+    const int clc = 4 * y4;
     const int swz = (clc >> 3) & (tg.nqp - 1);
 #pragma unroll
     for (int ps = 0; ps < kPasses; ++ps) {
@@ -692,26 +700,25 @@ ls_bwd_transpose_kernel(const float* __restrict__ gbev, LsBevStrides st, const i
     }
   } else {
     for (int idx = tid; idx < 4 * nquads * LS_TILE; idx += LS_THREADS) {
-      const int y = idx % LS_TY, x = (idx / LS_TY) % LS_TX, cr = idx / LS_TILE;
+      const int y = idx % LS_TY, cr = idx / LS_TILE;
       const int ch = cbase + cr;
-      const int ox = tx0 + x, oy = ty0 + y;
+      const int oy = ty0 + y;
       float v = 0.0f;
-      if (ch < dm.C && ox < grid.X && oy < grid.Y)
-        v = gbev[(size_t)b * st.b + (size_t)ch * st.c + (size_t)ox * st.x + oy];
-      const int cl = x * LS_TY + y;
-      tile[cl * tg.stride + 4 * ls_tile_quad(cl, cr >> 2, tg.nqp) + (cr & 3)] = v;
+      if (ch < dm.C && gx < grid.X && oy < grid.Y)
+        v = gbev[(size_t)b * st.b + (size_t)ch * st.c + (size_t)gx * st.x + oy];
+      tile[y * tg.stride + 4 * ls_tile_quad(y, cr >> 2, tg.nqp) + (cr & 3)] = v;
     }
   }
   __syncthreads();
-  // rows of non-empty cells: thread = (quad, cell), 16 B per lane, LS_TCHUNK*4 B per cell
+  // rows of hit cells: thread = (quad, cell), 16 B per lane, LS_TCHUNK*4 B per cell
   {
     constexpr int kQ = LS_TCHUNK / 4;
     const int q = tid % kQ;
     if (q < nquads) {
 #pragma unroll 4
       for (int cl = tid / kQ; cl < LS_TILE; cl += LS_THREADS / kQ) {
-        if (seg[cl + 1] != seg[cl])        // a hit cell is inside the grid
-          *reinterpret_cast<float4*>(dst + ((size_t)(tx0 + cl / LS_TY) * grid.Y + ty0 + cl % LS_TY) * dm.Cp + 4 * q) =
+        if (hit[cl])
+          *reinterpret_cast<float4*>(dst + (size_t)cl * dm.Cp + 4 * q) =
               *reinterpret_cast<const float4*>(tile + cl * tg.stride + 4 * ls_tile_quad(cl, q, tg.nqp));
       }
     }
@@ -722,7 +729,7 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
                             const LsGrid& g, float* gT, cudaStream_t s) {
   const LsTileGeom tg = ls_tile_geom(dm.Cp < LS_TCHUNK ? dm.Cp : LS_TCHUNK);
   const size_t smem = (size_t)LS_TILE * tg.stride * sizeof(float) + (LS_TILE + 1) * sizeof(int);
-  dim3 grid(g.tiles, dm.B, (dm.Cp + LS_TCHUNK - 1) / LS_TCHUNK);
+  dim3 grid(g.X * ((g.Y + LS_TY - 1) / LS_TY), dm.B, (dm.Cp + LS_TCHUNK - 1) / LS_TCHUNK);
   if (ls_bev_vec4(gbev, st, g))
     LS_LAUNCH(ls_bwd_transpose_kernel<true>, grid, dim3(LS_THREADS), smem, s, gbev, st, seg_start, dm, g, gT);
   else

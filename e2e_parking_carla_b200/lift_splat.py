@@ -30,9 +30,24 @@ class GridSpec:
     dim: Tuple[int, int, int]
 
 
-def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec, geom_policy: int = 0) -> LsShape:
+def pick_tile_x(channels: int, bev_channels_last: bool) -> int:
+    """Internal BEV tiling for a call (LsShape.tile_x).  1 x 128 strips are the default everywhere:
+    the NCHW write-out and the bulk-store variant need them, and for the channels-last direct splat
+    (which accepts any tile shape) square tiles measured SLOWER on a B200 although a ray stays 3.6
+    depth bins inside an 8 x 16 tile against 1.15 inside a strip - that kernel is bound by L1 data-pipe
+    wavefronts and issue slots, not by L2 reads (profiles/r02_summary.md).  LS_TILE_X=2..64 selects
+    square-ish tiles for the 64-channel channels-last splat (developer knob, covered by the tests)."""
+    import os
+    if not (bev_channels_last and channels == 64) or os.environ.get("LS_SPLAT_OUT") == "bulk":
+        return 1
+    return int(os.environ.get("LS_TILE_X", "1"))
+
+
+def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec, geom_policy: int = 0,
+               tile_x: int = 1) -> LsShape:
     s = LsShape()
     s.geom_policy = geom_policy
+    s.tile_x = tile_x
     s.B, s.N, s.D, s.fh, s.fw, s.C = B, N, D, fh, fw, Cc
     s.X, s.Y, s.Z = grid.dim
     for i in range(3):
@@ -321,7 +336,8 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
                          (tuple(feat.shape), tuple(depth_logits.shape), B, N))
     if tuple(frustum.shape) != (D, fh, fw, 3):
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
-    shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy)
+    shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy,
+                       pick_tile_x(Cc, bev_format == torch.channels_last))
     return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format, spare_channels)
 
 

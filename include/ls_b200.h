@@ -49,6 +49,10 @@ typedef struct LsShape {
   float start[3];      /* bev_start_pos                                         */
   float res[3];        /* bev_res                                               */
   int32_t geom_policy; /* LsGeomPolicy: float32 evaluation order of M.(u*d, v*d, d) + t    */
+  int32_t tile_x;      /* internal BEV tiling: tiles of 128 cells, tile_x x (128 / tile_x); 0 or 1 =
+                        * 1 x 128 strips (required for NCHW BEV tensors), 8 = 8 x 16 (what the
+                        * channels-last 64-channel splat wants); a power of two <= 128.  Use the
+                        * same value for every call of one forward/backward pair.            */
 } LsShape;
 
 /* model/bev_model.py:54 is a broadcast batched 3x3 matmul; its float32 rounding depends on the
@@ -83,9 +87,9 @@ const char* ls_version(void);
 const char* ls_strerror(int status);
 const char* ls_last_cuda_error(void);
 
-/* Internal BEV tiling: the grid is cut into tiles of 128 consecutive cells of one x-row
- * (a build-time choice); cells are numbered tile-major.  cells_padded = tiles * cells per
- * tile (>= X*Y); seg_stride = row stride of seg_start. */
+/* Internal BEV tiling: the grid is cut into tiles of 128 cells (LsShape.tile_x rows each);
+ * cells are numbered tile-major.  cells_padded = tiles * 128 (>= X*Y); seg_stride = row
+ * stride of seg_start. */
 int ls_grid_cells(const LsShape* s, int32_t* tiles, int32_t* cells_padded, int32_t* seg_stride);
 
 /* Channel count of the internal NHWC staging rows: C rounded up to a multiple of 4. */

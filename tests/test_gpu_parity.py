@@ -37,10 +37,10 @@ def _grid_spec(shape: LiftSplatShape):
     return ls.GridSpec(tuple(float(v) for v in start), tuple(float(v) for v in res), tuple(int(v) for v in dim))
 
 
-def _ls_shape(shape: LiftSplatShape, channels=None):
+def _ls_shape(shape: LiftSplatShape, channels=None, tile_x=1):
     ls = _ls()
     return ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw,
-                         channels or shape.channels, _grid_spec(shape))
+                         channels or shape.channels, _grid_spec(shape), 0, tile_x)
 
 
 def _dev(a, dtype=None):
@@ -93,13 +93,15 @@ def test_export_indices_and_geometry_vs_oracle(lib, name):
     assert np.array_equal(rank.cpu().numpy(), rank_o)
 
 
+@pytest.mark.parametrize("tile_x", [1, 8, 32])
 @pytest.mark.parametrize("name", list(GOLDEN_SHAPES))
-def test_sorted_ranks_bit_exact(lib, name):
+def test_sorted_ranks_bit_exact(lib, name, tile_x):
     """ranks[ranks.argsort()] (model/bev_model.py:96-97) and the segment count of
-    VoxelsSumming (tool/geometry.py:295-296), from the CSR the counting sort builds."""
+    VoxelsSumming (tool/geometry.py:295-296), from the CSR the counting sort builds - for the
+    1 x 128 strips of the NCHW path and the square tiles of the channels-last splat."""
     ls = _ls()
     g = Golden(name)
-    s = _ls_shape(g.shape)
+    s = _ls_shape(g.shape, tile_x=tile_x)
     sh = g.shape
     rank, cell, within, counts = ls.index(_dev(g["M_ref"]), _dev(g["t_ref"]), _dev(frustum_of(sh)), s, for_sort=True)
     assert np.array_equal(rank.cpu().numpy(), g["rank_ref"])
@@ -508,7 +510,10 @@ def test_plain_stream_order_matches(lib):
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
-    assert digests[0] == digests[1] == digests[2]
+    assert digests[0] == digests[1]
+    # the bulk (shared-memory tile) variant cuts its pieces inside cells: same gradients, BEV equal up to
+    # the last bit - checked on values in test_bulk_store_variant_matches, here it only has to run
+    assert len(digests[2]) > 10
 
 
 def test_many_tiles_single_cta_scan(lib):
@@ -574,6 +579,18 @@ def _check_all(out, ref, tol, prob_tol=None):
     assert np.array_equal(out["bev"].cpu().numpy() == 0, ref["bev"] == 0) or tol > 1e-4, "zero pattern"
 
 
+def _same_across_layouts(a, b):
+    """Gradients and probabilities: the same bits in every layout (the backward's arithmetic does not
+    depend on it).  BEV features: every cell is summed in the same canonical record order, but the
+    NCHW tile kernel cuts its quarter-warp pieces inside cells (partial sums merged afterwards)
+    while the channels-last kernel sums each cell front to back - last-bit differences allowed."""
+    for k in ("prob", "grad_feat", "grad_logits"):
+        if k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert maxerr(a["bev"], b["bev"]) <= 1e-6
+    assert torch.equal(a["bev"] == 0, b["bev"] == 0)
+
+
 @pytest.mark.parametrize("channels", [64, 16, 6])
 def test_channels_last_bev_bit_identical_to_nchw(lib, channels):
     """channels_last BEV output + channels_last gradient (the splat's native layout: bulk tile
@@ -585,8 +602,7 @@ def test_channels_last_bev_bit_identical_to_nchw(lib, channels):
     a = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
     b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], bev_format=torch.channels_last)
     assert b["bev"].stride(1) == 1 and a["bev"].stride(3) == 1
-    for k in a:
-        assert torch.equal(a[k], b[k]), k
+    _same_across_layouts(a, b)
     _check_all(b, _oracle_outputs(shape, c), FP32_TOL, 1e-6)
 
 
@@ -624,7 +640,7 @@ def test_channels_last_gradient_slice_of_65_channels(lib):
     ls.check(_lib.load().ls_forward(P(f.detach()), ls.LS_FEAT_NCHW, P(z.detach()), ls.LS_F32, P(Md), P(td), P(fr),
                                     C.byref(s), P(scratch), scratch.numel(), None, 0, P(view), C.byref(st), P(prob2),
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ls_forward")
-    assert torch.equal(buf[:, :64], a["bev"]) and bool((buf[:, 64] == -7.0).all())
+    assert maxerr(buf[:, :64], a["bev"]) <= 1e-6 and bool((buf[:, 64] == -7.0).all())
 
 
 def test_channels_last_features_in_place(lib):
@@ -637,8 +653,7 @@ def test_channels_last_features_in_place(lib):
         b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
                  bev_format=torch.channels_last, feat_format=torch.channels_last)
         assert b["grad_feat"].is_contiguous(memory_format=torch.channels_last)
-        for k in a:
-            assert torch.equal(a[k], b[k]), (k, dtype)
+        _same_across_layouts(a, b)
 
 
 @pytest.mark.parametrize("bev_format", [torch.contiguous_format, torch.channels_last])
@@ -676,8 +691,7 @@ def test_stress_grid_real_channel_count_vs_oracle(lib, dtype):
     _check_all(out, _oracle_outputs(shape, c), tol, 1e-6 if dtype == torch.float32 else None)
     if dtype == torch.float32:
         nchw = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
-        for k in out:
-            assert torch.equal(out[k], nchw[k]), k
+        _same_across_layouts(nchw, out)
 
 
 @pytest.mark.parametrize("channels,dtype", [(96, torch.float32), (128, torch.float32), (256, torch.float32),
@@ -693,8 +707,7 @@ def test_more_than_64_channels(lib, channels, dtype):
     _check_all(a, ref, tol, 1e-6 if dtype == torch.float32 else None)
     b = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
              bev_format=torch.channels_last)
-    for k in a:
-        assert torch.equal(a[k], b[k]), k
+    _same_across_layouts(a, b)
 
 
 def test_more_than_256_channels_rejected(lib):
@@ -846,7 +859,7 @@ def test_add_target_bev_matches_reference_semantics(lib):
         results.append((bev.detach().clone(), enc.feat.grad.clone(), enc.logits.grad.clone()))
     torch.backends.cudnn.allow_tf32 = tf32
     for r in results[1:]:
-        assert torch.equal(r[0], results[0][0])
+        assert maxerr(r[0], results[0][0]) <= 1e-6
         # the gradient handed to the backward differs only in layout; conv's own backward picks
         # another algorithm per layout, so compare to tolerance, not bits
         assert relerr(r[1], results[0][1]) < 1e-4 and relerr(r[2], results[0][2]) < 1e-4
@@ -913,5 +926,75 @@ def test_torch_geometry_same_device_rank_parity(lib, case):
     # the CPU-order policy on the same M, t is NOT the same function (that is the point of the policy)
     s_cpu = ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw, 4, _grid_spec(shape))
     geom_cuda = ls.geometry(M, t, fr, s)
-    assert not torch.equal(geom_cuda, ls.geometry(M, t, fr, s_cpu))
-    assert torch.equal(geom_cuda, tp.camera_geometry(fr, intr.to(DEV), extr.to(DEV)))
+    if jitter:      # (the axis-aligned CARLA rig has too many exact zeros in M for the orders to differ)
+        assert not torch.equal(geom_cuda, ls.geometry(M, t, fr, s_cpu))
+    # coordinates: bit-equal to torch-CUDA's everywhere except the tail of its batched matmul (the last
+    # ~30 points of the last camera of the batch go through another cuBLAS code path and differ by
+    # <= 4 ulp; tools/geom_policy_probe.py --library: 76 of 9 437 184 coordinates at B=16)
+    bad = geom_cuda != tp.camera_geometry(fr, intr.to(DEV), extr.to(DEV))
+    assert int(bad.sum()) <= 128
+    assert int(bad.view(shape.batch * shape.cams, -1)[:-1].sum()) == 0          # only the last camera
+    assert int(bad[-1, -1].reshape(-1, 3)[:-64].sum()) == 0                     # only its last points
+
+
+def test_bulk_store_variant_matches(lib):
+    """LS_SPLAT_OUT=bulk (shared-memory tile leaving as ONE bulk/TMA store per tile, the first
+    channels-last design) against the default direct-row-store splat: a child process per variant
+    dumps the BEV tensor, values must agree to the last bit or two."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("direct", "bulk"):
+            path = os.path.join(tmp, mode + ".pt")
+            code = (
+                "import sys, torch; sys.path.insert(0, %r); import bench\n"
+                "from e2e_parking_carla_b200.synthetic import LiftSplatShape\n"
+                "st = bench.Stepper(LiftSplatShape(batch=3, channels=64), torch.float32, torch.device('cuda:0'))\n"
+                "st.step(); torch.cuda.synchronize()\n"
+                "torch.save({k: getattr(st, k).cpu() for k in ('bev', 'prob', 'gfeat', 'glogits')}, %r)\n" % (root, path))
+            env = dict(os.environ, LS_SPLAT_OUT=mode)
+            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            outs.append(torch.load(path))
+    a, b = outs
+    assert a["bev"].abs().sum() > 0
+    assert maxerr(a["bev"], b["bev"]) <= 1e-6 and torch.equal(a["bev"] == 0, b["bev"] == 0)
+    for k in ("prob", "gfeat", "glogits"):
+        assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("tile_x", [8, 32])
+def test_square_tiles_same_bits_as_strips(lib, tile_x):
+    """The channels-last splat with tile_x x (128 / tile_x) tiles (LsShape.tile_x) against 1 x 128
+    strips: every cell is summed front to back in canonical order by one quarter-warp, so the BEV
+    tensor has the same bits whatever the tiling; gradients do not depend on it at all."""
+    import ctypes as C
+    from e2e_parking_carla_b200 import _lib
+    ls = _ls()
+    shape = LiftSplatShape(batch=3, channels=64)
+    c = _oracle_case(shape, rig_seed=48, in_seed=23)
+    lib_ = _lib.load()
+    P = lambda x: C.c_void_p(x.data_ptr())
+    fr, Md, td = _dev(frustum_of(shape)), _dev(c["M"]), _dev(c["t"])
+    feat, logits = c["feat"].to(DEV), c["logits"].to(DEV)
+    gb = c["gb"].to(DEV).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for tx in (1, tile_x):
+        s = _ls_shape(shape, tile_x=tx)
+        scratch = torch.empty(ls.scratch_bytes(s, ls.LS_F32, True), dtype=torch.uint8, device=DEV)
+        saved = torch.empty(ls.saved_bytes(s, ls.LS_F32), dtype=torch.uint8, device=DEV)
+        bev = torch.empty((3, 64, 200, 200), device=DEV).contiguous(memory_format=torch.channels_last)
+        prob, gfeat, glogits = torch.empty_like(logits), torch.empty_like(feat), torch.empty_like(logits)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        st, gst = ls._bev_strides(bev), ls._bev_strides(gb)
+        ls.check(lib_.ls_forward(P(feat), 0, P(logits), 0, P(Md), P(td), P(fr), C.byref(s), P(scratch), scratch.numel(),
+                                 P(saved), saved.numel(), P(bev), C.byref(st), P(prob), stream), "ls_forward")
+        ls.check(lib_.ls_backward(P(gb), C.byref(gst), None, P(prob), P(feat), 0, 0, C.byref(s), P(scratch),
+                                  scratch.numel(), P(saved), saved.numel(), P(gfeat), P(glogits), stream), "ls_backward")
+        outs.append((bev, prob, gfeat, glogits))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert_close(outs[1][0], _oracle_outputs(shape, c)["bev"], FP32_TOL, "bev")

@@ -74,5 +74,39 @@ def main():
     print(json.dumps(out))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--library" not in sys.argv:
     main()
+
+
+def library_check():
+    """ls_geometry with LS_GEOM_TORCH_CUDA against torch-CUDA's own geometry: mismatch census."""
+    from e2e_parking_carla_b200 import lift_splat as ls
+    from e2e_parking_carla_b200.bev_model import BevModel
+    from e2e_parking_carla_b200.synthetic import make_cfg
+    shape = LiftSplatShape(batch=16, channels=4)
+    intr, extr = make_rig(16, 4, jitter=True, seed=1)
+    dev = torch.device("cuda")
+    model = BevModel(make_cfg(shape), cam_encoder=torch.nn.Identity(), geometry="torch").to(dev)
+    M, t = model.camera_transform(intr.to(dev), extr.to(dev))
+    fr = model.frustum.data
+    ours = ls.geometry(M, t, fr, model._shape(16, 4, 4))
+    ref = tp.camera_geometry(fr, intr.to(dev), extr.to(dev))
+    bad = (ours != ref)
+    out = {"coords": int(bad.numel()), "mismatch": int(bad.sum()),
+           "per_axis": [int(bad[..., i].sum()) for i in range(3)],
+           "per_cam": bad.sum(dim=(2, 3, 4, 5)).flatten().tolist()}
+    idx = bad.nonzero()[:6]
+    ex = []
+    u, v, d = fr[..., 0], fr[..., 1], fr[..., 2]
+    for b, n, dd, r, c, a in idx.tolist():
+        ex.append({"b": b, "n": n, "axis": a, "m": M[b, n, a].tolist(), "t": float(t[b, n, a]),
+                   "u": float(u[dd, r, c]), "v": float(v[dd, r, c]), "d": float(d[dd, r, c]),
+                   "ours": float(ours[b, n, dd, r, c, a]), "ref": float(ref[b, n, dd, r, c, a]),
+                   "ours_hex": ours[b, n, dd, r, c, a].cpu().numpy().tobytes().hex(),
+                   "ref_hex": ref[b, n, dd, r, c, a].cpu().numpy().tobytes().hex()})
+    out["examples"] = ex
+    print(json.dumps(out))
+
+
+if __name__ == "__main__" and "--library" in sys.argv:
+    library_check()
