@@ -49,6 +49,7 @@ struct LsGrid {
   float off[3];    // bev_start_pos - bev_res / 2   (float32 ops, model/bev_model.py:85)
   float res[3];
   float fdim[3];   // (float)dim, exact (dim < 2^24)
+  int zfast;       // Z == 1 and res_z > 0: the z keep-test needs no division (see ls_point_voxel)
 };
 
 struct LsDims {
@@ -98,6 +99,7 @@ static inline LsGrid ls_grid(const LsShape* s) {
     g.res[i] = s->res[i];
   }
   g.fdim[0] = (float)s->X; g.fdim[1] = (float)s->Y; g.fdim[2] = (float)s->Z;
+  g.zfast = (s->Z == 1 && s->res[2] > 0.0f && s->res[2] < 3.0e38f) ? 1 : 0;
   return g;
 }
 
@@ -176,6 +178,25 @@ __device__ __forceinline__ bool ls_point_voxel(const float g[3], const LsGrid& g
     v[i] = __float2int_rz(c[i]);
   }
   return keep;
+}
+
+// The same keep decision and (x, y) voxel for the hot kernel when there is a single z cell
+// (grid.zfast): with a = g_z - off_z and r = res_z > 0,  -1 < RN(a / r) < 1  <=>  -r < a < r.
+// Proof: the floats next to +-r toward zero are at least r * 2^-24 away from it, so their quotient is
+// at most 1 - 2^-24 in magnitude - a representable number, hence rounds to itself or below it, never
+// to 1; |a| >= r gives |a / r| >= 1, which rounds to >= 1.  (NaN fails both forms.)  One IEEE
+// division less per point; the x and y coordinates keep theirs (they need the truncated quotient).
+__device__ __forceinline__ bool ls_point_voxel_xy(const float g[3], const LsGrid& grid, int v[3]) {
+  bool keep = true;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float c = __fdiv_rn(__fsub_rn(g[i], grid.off[i]), grid.res[i]);
+    keep = keep && (c > -1.0f) && (c < grid.fdim[i]);
+    v[i] = __float2int_rz(c);
+  }
+  const float a = __fsub_rn(g[2], grid.off[2]);
+  v[2] = 0;
+  return keep && (a > -grid.res[2]) && (a < grid.res[2]);
 }
 
 template <typename T> __device__ __forceinline__ float ls_to_float(T v);

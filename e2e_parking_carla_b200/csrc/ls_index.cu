@@ -139,7 +139,9 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   for (int k = 0; k < LS_IDX_ILP; ++k) {
     if (kGeomIn) { g[k][0] = u[k]; g[k][1] = v[k]; g[k][2] = d[k]; }
     else ls_point_geom<kPolicy>(cam, cam + 9, u[k], v[k], d[k], g[k]);
-    keep[k] = ls_point_voxel(g[k], grid, c[k], vx[k]) && (i0 + k * blockDim.x < dm.DHW);
+    if (!kExport && grid.zfast) keep[k] = ls_point_voxel_xy(g[k], grid, vx[k]);
+    else keep[k] = ls_point_voxel(g[k], grid, c[k], vx[k]);
+    keep[k] = keep[k] && (i0 + k * blockDim.x < dm.DHW);
     cid[k] = -1;
     tk[k] = 0;
   }

@@ -70,29 +70,94 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 // loop runs over L1-resident keys.  Replaces the (unstable) argsort of model/bev_model.py:96.
 // =====================================================================================
 #define LS_CANON_THREADS 256
+#ifndef LS_CANON_BIG
+#define LS_CANON_BIG 192      // cells with more records than this take the bucketed path
+#endif
+#define LS_CANON_BUCKETS 4096 // by the top 12 of the 24 key bits
+
 __global__ void __launch_bounds__(LS_CANON_THREADS)
-ls_canon_kernel(const int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
+ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
                 LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
   ls_pdl_trigger();
   ls_pdl_wait();
   __shared__ int seg[LS_TILE + 1];
+  __shared__ int any_big;
   const int b = blockIdx.x % dm.B;
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  if (threadIdx.x == 0) any_big = 0;
   for (int i = threadIdx.x; i <= LS_TILE; i += LS_CANON_THREADS) seg[i] = segg[i];
   __syncthreads();
   const int s0 = seg[0], s1 = seg[LS_TILE];
-  const int2* rin = recs + (size_t)b * dm.Npts;
+  int2* rin = recs + (size_t)b * dm.Npts;
   int2* out = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
   for (int i = s0 + threadIdx.x; i < s1; i += LS_CANON_THREADS) {
     const int2 r = rin[i];
     const int cl = (unsigned)r.x >> 24;
     const int a = seg[cl], e = seg[cl + 1];
+    if (e - a > LS_CANON_BIG) { any_big = 1; continue; }      // handled below by the whole CTA
     int pos = a;
 #pragma unroll 4
-    for (int j = a; j < e; ++j) pos += (__ldg(&rin[j].x) < r.x) ? 1 : 0;
+    for (int j = a; j < e; ++j) pos += (rin[j].x < r.x) ? 1 : 0;
     const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
     out[pos] = make_int2((pix << 12) | cl | LS_REC_VALID | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
+  }
+  __syncthreads();
+  if (!any_big) return;
+  // ---- heavy cells (coarse grids, degenerate rigs: up to every point of the sample in one cell) ----
+  // Rank-by-counting is quadratic in the cell's record count; here the cell is first grouped by the top
+  // 12 key bits (shared-memory histogram + scan + scatter, integer atomics only), then every record is
+  // ranked against its own bucket only: k * (k / 4096) compares instead of k^2.  The input run of the
+  // cell (dead after the scatter) is the scratch for the final order.
+  __shared__ int bucket_end[LS_CANON_BUCKETS];      // histogram -> scan -> scatter cursor -> end of each bucket
+  __shared__ int scan_tmp[LS_CANON_THREADS];
+  for (int cl = 0; cl < LS_TILE; ++cl) {
+    const int a = seg[cl], e = seg[cl + 1];
+    if (e - a <= LS_CANON_BIG) continue;             // uniform over the CTA
+    for (int i = threadIdx.x; i < LS_CANON_BUCKETS; i += LS_CANON_THREADS) bucket_end[i] = 0;
+    __syncthreads();
+    for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS)
+      atomicAdd(&bucket_end[(__ldcg(&rin[i].x) & 0xFFFFFF) >> 12], 1);
+    __syncthreads();
+    {
+      // exclusive scan of 4096 counts: 16 per thread, then a block scan of the thread totals
+      constexpr int kPer = LS_CANON_BUCKETS / LS_CANON_THREADS;
+      int loc[kPer], tot = 0;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) { loc[j] = bucket_end[threadIdx.x * kPer + j]; tot += loc[j]; }
+      scan_tmp[threadIdx.x] = tot;
+      __syncthreads();
+      for (int o = 1; o < LS_CANON_THREADS; o <<= 1) {
+        const int v = (int)threadIdx.x >= o ? scan_tmp[threadIdx.x - o] : 0;
+        __syncthreads();
+        scan_tmp[threadIdx.x] += v;
+        __syncthreads();
+      }
+      int run = scan_tmp[threadIdx.x] - tot;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) { bucket_end[threadIdx.x * kPer + j] = run; run += loc[j]; }
+    }
+    __syncthreads();
+    // scatter into bucket order (arbitrary inside a bucket); the cursor ends at the bucket's end
+    for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) {
+      const int2 r = __ldcg(&rin[i]);
+      const int pos = atomicAdd(&bucket_end[(r.x & 0xFFFFFF) >> 12], 1);
+      out[a + pos] = r;
+    }
+    __syncthreads();
+    // rank inside the bucket -> final slot, written in the output format into the (dead) input run
+    for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) {
+      const int2 r = __ldcg(&out[i]);
+      const int bk = (r.x & 0xFFFFFF) >> 12;
+      const int lo = a + (bk ? bucket_end[bk - 1] : 0), hi = a + bucket_end[bk];
+      int pos = lo;
+      for (int j = lo; j < hi; ++j) pos += (__ldcg(&out[j].x) < r.x) ? 1 : 0;
+      const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
+      rin[pos] = make_int2((pix << 12) | cl | LS_REC_VALID | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
+    }
+    __syncthreads();
+    for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) out[i] = __ldcg(&rin[i]);
+    __syncthreads();
   }
 }
 
@@ -385,6 +450,17 @@ template <bool kVec> __device__ __forceinline__ float4 ls_row_load4_cg(const flo
   return make_float4(__ldcg(g), __ldcg(g + 1), __ldcg(g + 2), __ldcg(g + 3));
 }
 
+// eight consecutive bf16 channels (16 B) -> two float4
+__device__ __forceinline__ void ls_load8_bf16(const char* p, float4& a, float4& b) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
+  const float2 v3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
+  a = make_float4(v0.x, v0.y, v1.x, v1.y);
+  b = make_float4(v2.x, v2.y, v3.x, v3.y);
+}
+
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(LS_THREADS, LS_SPLATD_MINB)
 ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
@@ -448,9 +524,14 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
   unsigned row_bytes = (unsigned)(kC * sizeof(T));
   asm volatile("" : "+r"(row_bytes));
-  const char* f0 = reinterpret_cast<const char*>(fbase + 4 * ql);
+  // channels of this lane: fp32 rows are 256 B = two 16-byte pieces per lane, 128 B apart (quads ql and
+  // ql + 8); bf16 rows are 128 B = ONE 16-byte piece per lane (channels 8*ql .. 8*ql+7), which halves
+  // the load instructions and L1 wavefronts of the gather - the bf16 fast path
+  constexpr bool kHalf = sizeof(T) == 2;
+  constexpr int kSecond = kHalf ? 4 : 32;        // channel distance between the lane's two float4 accumulators
+  const char* f0 = reinterpret_cast<const char*>(fbase + (kHalf ? 8 : 4) * ql);
   const unsigned f1off = (unsigned)(32 * sizeof(T));
-  float* lane0 = tile0 + 4 * ql;                  // this lane's first quad of row 0
+  float* lane0 = tile0 + (kHalf ? 8 : 4) * ql;    // this lane's first quad of row 0
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int2* p = rs + idx;
   int2 r[LS_QWIN], rn[LS_QWIN];
@@ -464,8 +545,11 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
     _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
       const char* row = f0 + (unsigned long long)((unsigned)cur[u].x >> 12) * row_bytes;             \
-      fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));                                          \
-      fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));                                  \
+      if (kHalf) ls_load8_bf16(row, fa[u], fb[u]);                                                   \
+      else {                                                                                         \
+        fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));                                        \
+        fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));                                \
+      }                                                                                              \
     }                                                                                                \
     idx += LS_QWIN;                                                                                  \
     p += LS_QWIN;                                                                                    \
@@ -481,7 +565,7 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
       if (cur[u].x & LS_REC_LAST) {                                                                  \
         float* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                       \
         ls_row_store4<kVec>(g, acc0);                                                                \
-        ls_row_store4<kVec>(g + 32, acc1);                                                           \
+        ls_row_store4<kVec>(g + kSecond, acc1);                                                      \
         acc0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
         acc1 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
       }                                                                                              \
@@ -567,7 +651,8 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   if (out == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
   size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
-  LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, recs, seg_start, tile_order, dm, g, recs_sorted);
+  LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, const_cast<int2*>(recs), seg_start, tile_order, dm, g,
+            recs_sorted);
   const dim3 block(LS_THREADS);
   const int2* rs = recs_sorted;
 #define LS_SPLAT(OUT, CC)                                                                                          \

@@ -998,3 +998,44 @@ def test_square_tiles_same_bits_as_strips(lib, tile_x):
     for a, b in zip(*outs):
         assert torch.equal(a, b)
     assert_close(outs[1][0], _oracle_outputs(shape, c)["bev"], FP32_TOL, "bev")
+
+
+@pytest.mark.parametrize("zres", [20.0, 0.3, 7.1, 8.0])
+def test_single_z_cell_keep_test_without_division(lib, zres):
+    """With one z cell the hot kernel decides -1 < RN((z - off) / res) < 1 as -res < z - off < res
+    (no division).  Adversarial z: exactly on both boundaries, one ulp inside / outside, NaN, inf -
+    against the oracle, which divides like the reference (model/bev_model.py:85-90)."""
+    import ctypes as C
+    from oracle import lift_splat_oracle as lo
+    from e2e_parking_carla_b200 import _lib
+    ls = _ls()
+    res = np.array([0.1, 0.1, zres], np.float32)
+    start = np.array([-9.95, -9.95, 0.0], np.float32)
+    dim = np.array([200, 200, 1], np.int64)
+    off = lo.grid_offset(start, res)
+    r = np.float32(zres)
+    edge = []
+    for sgn in (-1.0, 1.0):
+        b = np.float32(sgn) * r
+        for v in (b, np.nextafter(b, np.float32(0)), np.nextafter(b, np.float32(sgn * np.inf)),
+                  np.nextafter(np.nextafter(b, np.float32(0)), np.float32(0))):
+            edge.append(v)
+    edge += [np.float32(0), np.float32(np.nan), np.float32(np.inf), np.float32(-np.inf), np.float32(1e-30), r / 2]
+    rng = np.random.RandomState(3)
+    n = 32 * 16
+    geom = np.empty((1, n, 3), np.float32)
+    geom[0, :, :2] = rng.uniform(-9.9, 9.9, size=(n, 2)).astype(np.float32)
+    a = np.array([edge[i % len(edge)] for i in range(n)], np.float32)
+    a[len(edge) * 8:] = rng.uniform(-1.5, 1.5, size=n - len(edge) * 8).astype(np.float32) * r
+    geom[0, :, 2] = a + off[2]           # z - off reproduces a exactly for these magnitudes? checked below
+    back = (geom[0, :, 2] - off[2]).astype(np.float32)
+    _, keep_o, rank_o = lo.voxel_index(geom.reshape(1, 1, 1, 16, 32, 3), start, res, dim)
+    grid = ls.GridSpec(tuple(float(v) for v in start), tuple(float(v) for v in res), (200, 200, 1))
+    s = ls.make_shape(1, 1, 1, 16, 32, 4, grid)
+    rank = torch.empty(1, n, dtype=torch.int32, device=DEV)
+    g = _dev(geom)
+    ls.check(_lib.load().ls_index_geom(C.c_void_p(g.data_ptr()), C.byref(s), C.c_void_p(rank.data_ptr()), None, None,
+                                       None, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ls_index_geom")
+    assert np.array_equal(rank.cpu().numpy()[0], rank_o[0].astype(np.int32))
+    # the boundary values really are in the input (z - off is exact for them), on both sides of the test
+    assert (np.abs(back) == r).sum() >= 8 and 0 < keep_o.sum() < n
