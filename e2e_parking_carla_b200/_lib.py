@@ -62,6 +62,11 @@ PROTOTYPES = {
     "ls_depth_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ls_scratch_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
     "ls_saved_bytes": (C.c_size_t, [_SH, C.c_int, C.c_int]),
+    "ls_cache_bytes": (C.c_size_t, [_SH]),
+    "ls_forward_cached": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _SH, _P, C.c_size_t, _P, C.c_size_t, _P,
+                                    C.c_size_t, C.c_int, _P, _ST, _P, _P]),
+    "ls_backward_cached": (C.c_int, [_P, _ST, _P, _P, _P, C.c_int, C.c_int, _SH, _P, C.c_size_t, _P, C.c_size_t, _P,
+                                     C.c_size_t, _P, _P, _P]),
     "ls_forward": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _SH, _P, C.c_size_t, _P, C.c_size_t, _P, _ST, _P,
                              _P]),
     "ls_backward": (C.c_int, [_P, _ST, _P, _P, _P, C.c_int, C.c_int, _SH, _P, C.c_size_t, _P, C.c_size_t, _P, _P,

@@ -61,10 +61,15 @@ class BevModel(nn.Module):
     spare_channels : with channels_last, allocate the BEV as the first C channels of a
         ``[B, X, Y, C + spare]`` buffer; ``target_bev.add_target_bev`` then writes the target
         channel (model/parking_model.py:28-46) in place instead of ``torch.cat``-copying the BEV.
+    static_rig : opt-in.  The caller vouches that intrinsics / extrinsics are the same every call (they
+        are constants of the reference's dataset, dataset/carla_dataset.py:392-393): voxel indices, the
+        counting sort and the canonical record order are then computed once per (batch shape, device)
+        and later calls only refresh the depth weights (``ls_forward_cached``).  Call
+        ``invalidate_rig_cache()`` if the rig does change.  Results are bit-identical either way.
     """
 
     def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native",
-                 bev_memory_format=torch.channels_last, spare_channels: int = 0):
+                 bev_memory_format=torch.channels_last, spare_channels: int = 0, static_rig: bool = False):
         super().__init__()
         self.cfg = cfg
         if geometry not in ("native", "torch"):
@@ -74,6 +79,7 @@ class BevModel(nn.Module):
         self.geometry_mode = geometry
         self.bev_memory_format = bev_memory_format
         self.spare_channels = int(spare_channels)
+        self._rig_cache = ls.RigCache() if static_rig else None
         if not getattr(cfg, "use_depth_distribution", 1):
             # the reference crashes in this mode too (depth is None at bev_model.py:64)
             raise ValueError("use_depth_distribution=0 is not supported (nor by the reference)")
@@ -127,6 +133,11 @@ class BevModel(nn.Module):
             return rot.matmul(torch.inverse(intrinsics)).contiguous(), trans.contiguous()
         return ls.camera_transform(intrinsics, extrinsics)
 
+    def invalidate_rig_cache(self):
+        """static_rig=True: the next call recomputes the index structures (the rig changed)."""
+        if self._rig_cache is not None:
+            self._rig_cache.invalidate()
+
     @property
     def geom_policy(self):
         from ._lib import LS_GEOM_TORCH_CPU, LS_GEOM_TORCH_CUDA
@@ -169,7 +180,8 @@ class BevModel(nn.Module):
         feat, depth_logits = self.cam_encoder(images.view(b * n, c, h, w))
         M, t = self.camera_transform(intrinsics, extrinsics)
         bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid,
-                                                self.bev_memory_format, self.spare_channels, self.geom_policy)
+                                                self.bev_memory_format, self.spare_channels, self.geom_policy,
+                                                self._rig_cache)
         return bev_feature, pred_depth
 
     def forward(self, images, intrinsics, extrinsics):

@@ -185,6 +185,29 @@ static LsWs ls_carve(const LsShape* s, int dtype, int feat_layout, int phase, vo
   return w;
 }
 
+// ---- static-rig cache (opt-in) ------------------------------------------------------------
+struct LsCache {
+  int *seg_start, *tile_order, *perm;
+  int2 *recs_sorted, *pix_recs;
+  size_t bytes;
+};
+static LsCache ls_carve_cache(const LsShape* s, void* base) {
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  const size_t pts = (size_t)dm.B * dm.Npts;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) { void* r = p ? (void*)(p + off) : nullptr; off += ls_align(n); return r; };
+  LsCache c;
+  c.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);
+  c.tile_order = (int*)take((size_t)dm.B * g.tiles * 4);
+  c.perm = (int*)take(pts * 4);
+  c.recs_sorted = (int2*)take((size_t)dm.B * ls_sorted_records_capacity(dm, g) * 8);
+  c.pix_recs = (int2*)take(pts * 8);
+  c.bytes = off;
+  return c;
+}
+
 extern "C" {
 
 const char* ls_version(void) { return "ls_b200 0.2 (sm_100a)"; }
@@ -324,7 +347,7 @@ int ls_splat_fwd(const void* feat_nhwc, int dtype, const void* recs, const int32
   if (rc) return rc;
   if (!feat_nhwc || !recs || !seg_start || !tile_order || !recs_scratch || !bev || !st || !ls_dtype_ok(dtype))
     return LS_ERR_BAD_ARG;
-  return ls_launch_splat_fwd(feat_nhwc, dtype, (const int2*)recs, seg_start, tile_order, (int2*)recs_scratch,
+  return ls_launch_splat_fwd(feat_nhwc, dtype, (const int2*)recs, seg_start, tile_order, (int2*)recs_scratch, nullptr,
                              ls_dims(s), ls_grid(s), bev, *st, (cudaStream_t)stream);
 }
 
@@ -401,7 +424,7 @@ int ls_forward(const void* feat, int feat_layout, const void* logits, int dtype,
   if ((rc = fk.join(1))) return rc;
   if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, w.seg_start, w.recs, w.pix_recs, stream))) return rc;
   if ((rc = fk.join(2))) return rc;
-  return ls_launch_splat_fwd(featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, dm, g, bev,
+  return ls_launch_splat_fwd(featT, dtype, w.recs, w.seg_start, w.tile_order, w.recs_sorted, nullptr, dm, g, bev,
                              *bev_strides, stream);
 }
 
@@ -434,6 +457,93 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
   }
   if (rc) return rc;
   // the two layout fix-ups are independent: grad_feat on a side stream, grad_logits on the caller's
+  LsFork fk(stream);
+  if (feat_layout == LS_FEAT_NCHW &&
+      (rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, fk.side(1))))
+    return rc;
+  if ((rc = ls_launch_softmax_bwd(prob, w.gprob_pm, grad_prob_ext, dtype, dm, grad_logits, stream))) return rc;
+  return fk.join(1);
+}
+
+size_t ls_cache_bytes(const LsShape* s) {
+  if (ls_check_splat_shape(s)) return 0;
+  return ls_carve_cache(s, nullptr).bytes;
+}
+
+int ls_forward_cached(const void* feat, int feat_layout, const void* logits, int dtype, const float* M, const float* t,
+                      const float* frustum, const LsShape* s, void* scratch, size_t scratch_bytes, void* saved,
+                      size_t saved_bytes, void* cache, size_t cache_bytes, int rebuild, float* bev,
+                      const LsBevStrides* bev_strides, void* prob, ls_stream_t stream_) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!feat || !logits || !frustum || !scratch || !cache || !bev || !bev_strides || !prob || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  if (rebuild && (!M || !t)) return LS_ERR_BAD_ARG;
+  if (!ls_layout_ok(feat_layout, s)) return LS_ERR_UNSUPPORTED;
+  const bool with_saved = saved != nullptr;
+  LsWs w = ls_carve(s, dtype, feat_layout, 0, scratch, saved, with_saved);
+  LsCache c = ls_carve_cache(s, cache);
+  if (scratch_bytes < w.scratch_bytes || saved_bytes < w.saved_bytes || cache_bytes < c.bytes) return LS_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  if (ls_classify_bev_out(bev, *bev_strides, dm, g) == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
+  const void* featT = feat_layout == LS_FEAT_NHWC ? feat : w.featT;
+  LsFork fk(stream);
+  if ((rc = ls_launch_softmax(logits, dtype, dm, prob, fk.side(1)))) return rc;
+  if (feat_layout == LS_FEAT_NCHW &&
+      (rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, fk.side(2))))
+    return rc;
+  if (rebuild) {
+    // the full index / sort / canonical-order pipeline, written into the cache instead of the scratch
+    if ((rc = ls_launch_zero_counts(w.counts, dm, g, stream))) return rc;
+    if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
+    if ((rc = ls_launch_scan(w.counts, dm, g, c.seg_start, c.tile_order, w.tile_tot, stream))) return rc;
+    if ((rc = fk.join(1))) return rc;
+    if ((rc = ls_launch_place(w.cell, w.within, prob, dtype, dm, g, c.seg_start, w.recs, c.pix_recs, stream))) return rc;
+    if ((rc = fk.join(2))) return rc;
+    return ls_launch_splat_fwd(featT, dtype, w.recs, c.seg_start, c.tile_order, c.recs_sorted, c.perm, dm, g, bev,
+                               *bev_strides, stream);
+  }
+  // cached: only the weights the records carry are new
+  if ((rc = fk.join(1))) return rc;
+  if ((rc = ls_launch_refresh(prob, dtype, c.perm, c.seg_start, dm, g, c.recs_sorted, c.pix_recs, stream))) return rc;
+  if ((rc = fk.join(2))) return rc;
+  return ls_launch_splat_fwd(featT, dtype, nullptr, c.seg_start, c.tile_order, c.recs_sorted, nullptr, dm, g, bev,
+                             *bev_strides, stream);
+}
+
+int ls_backward_cached(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext,
+                       const void* prob, const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch,
+                       size_t scratch_bytes, const void* saved, size_t saved_bytes, const void* cache,
+                       size_t cache_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream_) {
+  int rc = ls_check_splat_shape(s);
+  if (rc) return rc;
+  if (!grad_bev || !grad_strides || !prob || !scratch || !cache || !grad_feat || !grad_logits || !ls_dtype_ok(dtype))
+    return LS_ERR_BAD_ARG;
+  if (!ls_layout_ok(feat_layout, s)) return LS_ERR_UNSUPPORTED;
+  if (feat_layout == LS_FEAT_NHWC ? !feat : !saved) return LS_ERR_BAD_ARG;
+  LsWs wf = ls_carve(s, dtype, feat_layout, 0, nullptr, const_cast<void*>(saved), true);
+  LsWs w = ls_carve(s, dtype, feat_layout, 1, scratch, nullptr, false);
+  LsCache c = ls_carve_cache(s, const_cast<void*>(cache));
+  if (scratch_bytes < w.scratch_bytes || cache_bytes < c.bytes) return LS_ERR_WORKSPACE;
+  if (feat_layout == LS_FEAT_NCHW && saved_bytes < wf.saved_bytes) return LS_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LsDims dm = ls_dims(s);
+  LsGrid g = ls_grid(s);
+  const int mode = ls_classify_grad_in(grad_bev, *grad_strides, dm, g);
+  if (mode == LS_GRAD_BAD) return LS_ERR_UNSUPPORTED;
+  const void* featT = feat_layout == LS_FEAT_NHWC ? feat : wf.featT;
+  void* gfeatT = feat_layout == LS_FEAT_NHWC ? grad_feat : w.gfeatT;
+  if (mode == LS_GRAD_STAGED) {
+    if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, c.seg_start, dm, g, w.gT, stream))) return rc;
+    rc = ls_launch_bwd_gather(w.gT, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, featT, dtype, c.pix_recs, dm, g,
+                              w.gprob_pm, gfeatT, stream);
+  } else {
+    rc = ls_launch_bwd_gather(grad_bev, grad_strides->b, grad_strides->y, mode, featT, dtype, c.pix_recs, dm, g,
+                              w.gprob_pm, gfeatT, stream);
+  }
+  if (rc) return rc;
   LsFork fk(stream);
   if (feat_layout == LS_FEAT_NCHW &&
       (rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, fk.side(1))))

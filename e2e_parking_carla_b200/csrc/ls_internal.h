@@ -35,8 +35,12 @@ int ls_launch_target_bev(const int* pix, int B, int X, int Y, float* out, long l
 // ls_splat.cu
 int ls_debug_fetch_phase_cycles(unsigned long long* out8);   // only with -DLS_PROFILE
 size_t ls_sorted_records_capacity(const LsDims& dm, const LsGrid& g);   // per sample, in 8-byte records
+// recs == NULL: recs_sorted is already canonical (static-rig cache); perm (may be NULL): slot -> point id
 int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, const int* tile_order,
-                        int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s);
+                        int2* recs_sorted, int* perm, const LsDims& dm, const LsGrid& g, float* bev,
+                        const LsBevStrides& st, cudaStream_t s);
+int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* seg_start, const LsDims& dm,
+                      const LsGrid& g, int2* recs_sorted, int2* pix_recs, cudaStream_t s);
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
                             const LsGrid& g, float* gT, cudaStream_t s);
 int ls_launch_bwd_gather(const float* rows_base, long long sample_stride, long long row_stride, int mode /* LsGradIn */,

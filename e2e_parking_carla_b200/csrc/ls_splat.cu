@@ -73,11 +73,12 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 #ifndef LS_CANON_BIG
 #define LS_CANON_BIG 192      // cells with more records than this take the bucketed path
 #endif
-#define LS_CANON_BUCKETS 4096 // by the top 12 of the 24 key bits
+#define LS_CANON_BUCKETS 1024 // by the top 10 of the 24 key bits (4 KB of shared memory: keeps the L1 share of the hot path)
+#define LS_CANON_BSHIFT 14
 
 __global__ void __launch_bounds__(LS_CANON_THREADS)
 ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
-                LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
+                LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted, int* __restrict__ perm) {
   ls_pdl_trigger();
   ls_pdl_wait();
   __shared__ int seg[LS_TILE + 1];
@@ -91,23 +92,31 @@ ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, cons
   const int s0 = seg[0], s1 = seg[LS_TILE];
   int2* rin = recs + (size_t)b * dm.Npts;
   int2* out = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
+  // perm (static-rig cache only): canonical slot -> point id (n*D + d)*HW + rc, the index of the point's
+  // probability inside the sample; lets a later step refresh the weights without redoing the sort
+  int* pm = perm ? perm + (size_t)b * dm.Npts : nullptr;
+  const int dmask = (1 << dm.dbits) - 1;
+  auto point_of = [&](int key, int pix) { const int n = pix / dm.HW; return (n * dm.D + (key & dmask)) * dm.HW + (pix - n * dm.HW); };
+  // (read-only path: the light cells' records are never written by this kernel)
+  const int2* __restrict__ rro = rin;
   for (int i = s0 + threadIdx.x; i < s1; i += LS_CANON_THREADS) {
-    const int2 r = rin[i];
+    const int2 r = __ldg(rro + i);
     const int cl = (unsigned)r.x >> 24;
     const int a = seg[cl], e = seg[cl + 1];
     if (e - a > LS_CANON_BIG) { any_big = 1; continue; }      // handled below by the whole CTA
     int pos = a;
 #pragma unroll 4
-    for (int j = a; j < e; ++j) pos += (rin[j].x < r.x) ? 1 : 0;
+    for (int j = a; j < e; ++j) pos += (__ldg(&rro[j].x) < r.x) ? 1 : 0;
     const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
     out[pos] = make_int2((pix << 12) | cl | LS_REC_VALID | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
+    if (pm) pm[pos] = point_of(r.x, pix);
   }
   __syncthreads();
   if (!any_big) return;
   // ---- heavy cells (coarse grids, degenerate rigs: up to every point of the sample in one cell) ----
   // Rank-by-counting is quadratic in the cell's record count; here the cell is first grouped by the top
-  // 12 key bits (shared-memory histogram + scan + scatter, integer atomics only), then every record is
-  // ranked against its own bucket only: k * (k / 4096) compares instead of k^2.  The input run of the
+  // 10 key bits (shared-memory histogram + scan + scatter, integer atomics only), then every record is
+  // ranked against its own bucket only: k * (k / 1024) compares instead of k^2.  The input run of the
   // cell (dead after the scatter) is the scratch for the final order.
   __shared__ int bucket_end[LS_CANON_BUCKETS];      // histogram -> scan -> scatter cursor -> end of each bucket
   __shared__ int scan_tmp[LS_CANON_THREADS];
@@ -117,7 +126,7 @@ ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, cons
     for (int i = threadIdx.x; i < LS_CANON_BUCKETS; i += LS_CANON_THREADS) bucket_end[i] = 0;
     __syncthreads();
     for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS)
-      atomicAdd(&bucket_end[(__ldcg(&rin[i].x) & 0xFFFFFF) >> 12], 1);
+      atomicAdd(&bucket_end[(__ldcg(&rin[i].x) & 0xFFFFFF) >> LS_CANON_BSHIFT], 1);
     __syncthreads();
     {
       // exclusive scan of 4096 counts: 16 per thread, then a block scan of the thread totals
@@ -141,19 +150,20 @@ ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, cons
     // scatter into bucket order (arbitrary inside a bucket); the cursor ends at the bucket's end
     for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) {
       const int2 r = __ldcg(&rin[i]);
-      const int pos = atomicAdd(&bucket_end[(r.x & 0xFFFFFF) >> 12], 1);
+      const int pos = atomicAdd(&bucket_end[(r.x & 0xFFFFFF) >> LS_CANON_BSHIFT], 1);
       out[a + pos] = r;
     }
     __syncthreads();
     // rank inside the bucket -> final slot, written in the output format into the (dead) input run
     for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) {
       const int2 r = __ldcg(&out[i]);
-      const int bk = (r.x & 0xFFFFFF) >> 12;
+      const int bk = (r.x & 0xFFFFFF) >> LS_CANON_BSHIFT;
       const int lo = a + (bk ? bucket_end[bk - 1] : 0), hi = a + bucket_end[bk];
       int pos = lo;
       for (int j = lo; j < hi; ++j) pos += (__ldcg(&out[j].x) < r.x) ? 1 : 0;
       const int pix = (r.x & 0xFFFFFF) >> dm.dbits;
       rin[pos] = make_int2((pix << 12) | cl | LS_REC_VALID | (pos == e - 1 ? LS_REC_LAST : 0), r.y);
+      if (pm) pm[pos] = point_of(r.x, pix);
     }
     __syncthreads();
     for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) out[i] = __ldcg(&rin[i]);
@@ -635,9 +645,11 @@ static bool ls_attr_needed(unsigned long long* done_mask) {
   return !(prev & bit);
 }
 
+// recs == nullptr: recs_sorted already holds the canonical records (static-rig cache), no re-ordering pass
 template <typename T>
 static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg_start, const int* tile_order,
-                             int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st, cudaStream_t s) {
+                             int2* recs_sorted, int* perm, const LsDims& dm, const LsGrid& g, float* bev,
+                             const LsBevStrides& st, cudaStream_t s) {
   static unsigned long long attr_done = 0;
   if (ls_attr_needed(&attr_done)) {
     const int m = (int)ls_tile_smem_max();
@@ -651,8 +663,9 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   if (out == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
   size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
-  LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, const_cast<int2*>(recs), seg_start, tile_order, dm, g,
-            recs_sorted);
+  if (recs)
+    LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, const_cast<int2*>(recs), seg_start, tile_order, dm, g,
+              recs_sorted, perm);
   const dim3 block(LS_THREADS);
   const int2* rs = recs_sorted;
 #define LS_SPLAT(OUT, CC)                                                                                          \
@@ -685,11 +698,69 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
 }
 
 int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const int* seg_start, const int* tile_order,
-                        int2* recs_sorted, const LsDims& dm, const LsGrid& g, float* bev, const LsBevStrides& st,
-                        cudaStream_t s) {
+                        int2* recs_sorted, int* perm, const LsDims& dm, const LsGrid& g, float* bev,
+                        const LsBevStrides& st, cudaStream_t s) {
   if (dtype == LS_F32)
-    return ls_splat_dispatch<float>(featT, recs, seg_start, tile_order, recs_sorted, dm, g, bev, st, s);
-  return ls_splat_dispatch<__nv_bfloat16>(featT, recs, seg_start, tile_order, recs_sorted, dm, g, bev, st, s);
+    return ls_splat_dispatch<float>(featT, recs, seg_start, tile_order, recs_sorted, perm, dm, g, bev, st, s);
+  return ls_splat_dispatch<__nv_bfloat16>(featT, recs, seg_start, tile_order, recs_sorted, perm, dm, g, bev, st, s);
+}
+
+// =====================================================================================
+// Static-rig cache (opt-in): the camera rig of the reference's data never moves
+// (dataset/carla_dataset.py:392-393), so voxel index, counting sort and canonical order of a
+// batch are the same every step; only the depth probabilities carried by the records change.
+// Refresh = two streaming passes:  recs_sorted[slot].y = prob[perm[slot]]  (canonical records)
+// and  pix_recs[pix][d].y = prob[d][pix]  (pixel-major index of the backward).
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_refresh_records_kernel(const T* __restrict__ prob, const int* __restrict__ perm, const int* __restrict__ seg_start,
+                          LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int b = blockIdx.y;
+  const int kept = __ldg(seg_start + (size_t)b * grid.seg_stride + grid.Vc);
+  const int* pm = perm + (size_t)b * dm.Npts;
+  const T* pb = prob + (size_t)b * dm.Npts;
+  int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kept; i += gridDim.x * blockDim.x)
+    rs[i].y = __float_as_int(ls_to_float(pb[__ldg(pm + i)]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ls_refresh_pixel_index_kernel(const T* __restrict__ prob, LsDims dm, int2* __restrict__ pix_recs) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  extern __shared__ int wstage[];                 // [32][Dp]
+  const int Dp = dm.D | 1;
+  const int bn = blockIdx.y, rc0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int valid = min(32, dm.HW - rc0);
+  if (lane < valid)
+    for (int d = dg; d < dm.D; d += 8)
+      wstage[lane * Dp + d] = __float_as_int(ls_to_float(prob[((size_t)bn * dm.D + d) * dm.HW + rc0 + lane]));
+  __syncthreads();
+  int2* dst = pix_recs + ((size_t)bn * dm.HW + rc0) * dm.D;
+  for (int r = dg; r < valid; r += 8)
+    for (int d = lane; d < dm.D; d += 32) dst[(size_t)r * dm.D + d].y = wstage[r * Dp + d];
+}
+
+int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* seg_start, const LsDims& dm,
+                      const LsGrid& g, int2* recs_sorted, int2* pix_recs, cudaStream_t s) {
+  dim3 ga((dm.Npts + 256 * 8 - 1) / (256 * 8), dm.B);
+  dim3 gb((dm.HW + 31) / 32, dm.B * dm.N);
+  const size_t smem = (size_t)32 * (dm.D | 1) * sizeof(int);
+  if (dtype == LS_F32) {
+    LS_LAUNCH(ls_refresh_records_kernel<float>, ga, dim3(256), 0, s, (const float*)prob, perm, seg_start, dm, g, recs_sorted);
+    if (pix_recs) LS_LAUNCH(ls_refresh_pixel_index_kernel<float>, gb, dim3(256), smem, s, (const float*)prob, dm, pix_recs);
+  } else {
+    LS_LAUNCH(ls_refresh_records_kernel<__nv_bfloat16>, ga, dim3(256), 0, s, (const __nv_bfloat16*)prob, perm, seg_start,
+              dm, g, recs_sorted);
+    if (pix_recs)
+      LS_LAUNCH(ls_refresh_pixel_index_kernel<__nv_bfloat16>, gb, dim3(256), smem, s, (const __nv_bfloat16*)prob, dm, pix_recs);
+  }
+  return LS_OK;
 }
 
 // =====================================================================================

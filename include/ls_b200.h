@@ -223,6 +223,30 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
                 const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch, size_t scratch_bytes,
                 const void* saved, size_t saved_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream);
 
+/* ---- static-rig cache (opt-in) ---------------------------------------------------------------
+ * The reference's camera rig never moves (intrinsics / extrinsics are constants of the dataset,
+ * dataset/carla_dataset.py:392-393), so voxel indices, the counting sort and the canonical record order
+ * of a batch are identical every step; only the depth probabilities the records carry change.
+ * `cache` (>= ls_cache_bytes(), device, owned by the caller, kept across steps) holds the CSR offsets,
+ * the tile order, the canonical records, their slot -> point permutation and the pixel-major index.
+ *   rebuild != 0  same work as ls_forward, results kept in the cache (first step, or the rig changed);
+ *   rebuild == 0  softmax + a streaming refresh of the record weights + the splat: no index kernel, no
+ *                 histogram, no scan, no placement, no re-ordering.  M / t are not read.
+ * The caller vouches that M, t, frustum and the shape are those of the rebuild step.  When a cache is
+ * in use the backward state in `saved` only carries the NHWC feature copy (NULL for channels-last
+ * features).  Results are bit-identical to ls_forward / ls_backward. */
+size_t ls_cache_bytes(const LsShape* s);
+int ls_forward_cached(const void* feat, int feat_layout, const void* logits, int dtype, const float* M,
+                      const float* t, const float* frustum, const LsShape* s, void* scratch,
+                      size_t scratch_bytes, void* saved, size_t saved_bytes, void* cache, size_t cache_bytes,
+                      int rebuild, float* bev, const LsBevStrides* bev_strides, void* prob,
+                      ls_stream_t stream);
+int ls_backward_cached(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext,
+                       const void* prob, const void* feat, int feat_layout, int dtype, const LsShape* s,
+                       void* scratch, size_t scratch_bytes, const void* saved, size_t saved_bytes,
+                       const void* cache, size_t cache_bytes, void* grad_feat, void* grad_logits,
+                       ls_stream_t stream);
+
 /* ---- consumer of bev: ParkingModel.add_target_bev (model/parking_model.py:28-46) ----------
  * Writes the target channel: ones on [px-4, px+4) x [py-4, py+4) (python slice semantics) around
  * target_pix i32[B,2] = the (noised) target pixel, zeros elsewhere, into `out` with element
