@@ -781,6 +781,9 @@ int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* s
 #ifndef LS_GATHER_REVERSE
 #define LS_GATHER_REVERSE 1
 #endif
+#ifndef LS_GATHER_SKIP_DEAD
+#define LS_GATHER_SKIP_DEAD 1
+#endif
 #ifndef LS_TCHUNK
 #define LS_TCHUNK 32   // channels per CTA of the gradient transposer (16, 32 or 64): 8 x 16 B in flight per thread
 #endif
@@ -1059,6 +1062,15 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
     for (int w = 0; w < wpp; ++w) {
       int2 recn = rec;
       if (w + 1 < wpp) recn = __ldg(pr + 16 * (w + 1));
+#if LS_GATHER_SKIP_DEAD
+      // a ray leaves the grid at some depth and stays out: whole windows of dropped points (about one in
+      // seven at the default rig) need no rows, no FMAs, no butterfly - their probability gradient is 0
+      if (!__any_sync(hmask, (unsigned)rec.x < rows.nrows)) {
+        gprob_pm[pix * dm.D + 16 * w + hl] = 0.0f;
+        rec = recn;
+        continue;
+      }
+#endif
       float dot[16];
 #pragma unroll
       for (int h = 0; h < 16 / LS_GOCC_ROWS; ++h) {

@@ -312,7 +312,7 @@ def synthetic_batch(cfg, batch, device, seed=0, cams=4):
     intr, extr = make_rig(batch, cams, jitter=True, seed=seed + 1)
     tokens = torch.randint(0, 201, (batch, 12), generator=g)
     ctrl = torch.cat([torch.full((batch, 1), 201), tokens, torch.full((batch, 1), 202), torch.full((batch, 1), 203)], 1)
-    shape = LiftSplatShape(batch=batch, cams=cams)
+    shape = LiftSplatShape(batch=batch, cams=cams, final_dim=list(cfg.final_dim), bev_down_sample=cfg.bev_down_sample)
     data = {
         "image": torch.randn(batch, cams, 3, h, w, generator=g),
         "depth": make_depth_labels(shape, seed=seed),
