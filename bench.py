@@ -413,6 +413,30 @@ class Stepper:
         comp.wait_stream(e["d2h"])
         comp.wait_stream(e["h2d"])
 
+    def link_floor_ms(self, iters: int = 5):
+        """Time to move exactly the step's bytes host->device and device->host (two copy streams, full
+        duplex, no kernel in between), synchronised per iteration: what the PCIe link and the host's
+        memory system allow for this step at this rank count - the floor of the e2e number."""
+        h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = {"bev": self.bev, "prob": self.prob, "gfeat": self.gfeat, "glogits": self.glogits}
+
+        def once():
+            with torch.cuda.stream(h2d):
+                for k, v in self.host.items():
+                    self.dev[k].copy_(v, non_blocking=True)
+            with torch.cuda.stream(d2h):
+                for k, v in outs.items():
+                    self.out_host[k].copy_(v, non_blocking=True)
+            h2d.synchronize()
+            d2h.synchronize()
+
+        once()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            once()
+        return (time.perf_counter() - t0) / iters * 1e3
+
     def e2e_bytes(self):
         h2d = sum(v.numel() * v.element_size() for v in self.host.values())
         d2h = sum(v.numel() * v.element_size() for v in self.out_host.values())
@@ -678,10 +702,13 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    barrier()
+    floor_ms = st.link_floor_ms()          # all ranks at once: they share the host's PCIe / memory fabric
+    barrier()
+    t = torch.tensor([ms, ms_e2e, floor_ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, floor_ms = float(t[0]), float(t[1]), float(t[2])
     ms_step = ms / args.steps
     value = shape.batch * world / (ms_step * 1e-3)
     e2e_value = shape.batch * world / (ms_e2e / e2e_steps * 1e-3)
@@ -759,6 +786,9 @@ def main():
                 "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / e2e_steps,
+                        "link_floor_ms": floor_ms,
+                        "link_floor_what": "the same bytes copied both ways with no kernels, all ranks concurrently, "
+                                           "max over ranks: what PCIe + the host memory system allow at this rank count",
                         "what": "pinned host buffers -> device -> ls_camera_transform/ls_forward/ls_backward -> "
                                 "pinned host buffers (all inputs incl. upstream grads, all outputs), sync per step; "
                                 "sample groups %s; forward inputs sent first, BEV returned while the upstream "

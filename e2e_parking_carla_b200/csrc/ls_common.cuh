@@ -230,6 +230,29 @@ template <> __device__ __forceinline__ void ls_store4<__nv_bfloat16>(__nv_bfloat
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
+// ---- packed float32 pairs (Blackwell FFMA2 / FMUL2: two fused multiply-adds per issue slot) ----
+#ifndef LS_FFMA2
+#define LS_FFMA2 0   // measured slower on a B200 (splat +3 us, gather +4 us: the pack/unpack moves and register-pair constraints cost more than the saved issue slots)
+#endif
+__device__ __forceinline__ unsigned long long ls_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ls_unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ls_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ls_mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // Shared-memory tile [cell][channel] with row stride (cc + 4) floats; the channel quad of a
 // cell is XOR-swizzled with bits of the cell index so that BOTH the row-wise float4 accesses
 // (one cell, 16 quads) and the column-wise scalar walks (fixed channel, consecutive cells)

@@ -543,6 +543,30 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   const unsigned f1off = (unsigned)(32 * sizeof(T));
   float* lane0 = tile0 + (kHalf ? 8 : 4) * ql;    // this lane's first quad of row 0
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#if LS_FFMA2
+  // the 8 channel sums of this lane live in four packed float32 pairs: 4 FFMA2 per record instead of 8 FFMA
+  unsigned long long a01 = ls_pack2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+#define LS_ACC8(WT__, A, B)                                                      \
+  {                                                                              \
+    const unsigned long long w2__ = ls_pack2(WT__, WT__);                        \
+    a01 = ls_fma2(w2__, ls_pack2(A.x, A.y), a01);                                \
+    a23 = ls_fma2(w2__, ls_pack2(A.z, A.w), a23);                                \
+    a45 = ls_fma2(w2__, ls_pack2(B.x, B.y), a45);                                \
+    a67 = ls_fma2(w2__, ls_pack2(B.z, B.w), a67);                                \
+  }
+#define LS_ACC_GET() { ls_unpack2(a01, acc0.x, acc0.y); ls_unpack2(a23, acc0.z, acc0.w); ls_unpack2(a45, acc1.x, acc1.y); ls_unpack2(a67, acc1.z, acc1.w); }
+#define LS_ACC_ZERO() { a01 = ls_pack2(0.f, 0.f); a23 = a01; a45 = a01; a67 = a01; }
+#else
+#define LS_ACC8(WT__, A, B)                                                                          \
+  {                                                                                                  \
+    acc0.x = fmaf(WT__, A.x, acc0.x); acc0.y = fmaf(WT__, A.y, acc0.y);                              \
+    acc0.z = fmaf(WT__, A.z, acc0.z); acc0.w = fmaf(WT__, A.w, acc0.w);                              \
+    acc1.x = fmaf(WT__, B.x, acc1.x); acc1.y = fmaf(WT__, B.y, acc1.y);                              \
+    acc1.z = fmaf(WT__, B.z, acc1.z); acc1.w = fmaf(WT__, B.w, acc1.w);                              \
+  }
+#define LS_ACC_GET() {}
+#define LS_ACC_ZERO() { acc0 = make_float4(0.f, 0.f, 0.f, 0.f); acc1 = make_float4(0.f, 0.f, 0.f, 0.f); }
+#endif
   const int2* p = rs + idx;
   int2 r[LS_QWIN], rn[LS_QWIN];
 #pragma unroll
@@ -567,17 +591,14 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
       if (cur[u].x & LS_REC_VALID) {                                                                 \
         const float wt = __int_as_float(cur[u].y);                                                   \
-        acc0.x = fmaf(wt, fa[u].x, acc0.x); acc0.y = fmaf(wt, fa[u].y, acc0.y);                      \
-        acc0.z = fmaf(wt, fa[u].z, acc0.z); acc0.w = fmaf(wt, fa[u].w, acc0.w);                      \
-        acc1.x = fmaf(wt, fb[u].x, acc1.x); acc1.y = fmaf(wt, fb[u].y, acc1.y);                      \
-        acc1.z = fmaf(wt, fb[u].z, acc1.z); acc1.w = fmaf(wt, fb[u].w, acc1.w);                      \
+        LS_ACC8(wt, fa[u], fb[u]);                                                                   \
       }                                                                                              \
       if (cur[u].x & LS_REC_LAST) {                                                                  \
         float* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                       \
+        LS_ACC_GET();                                                                                \
         ls_row_store4<kVec>(g, acc0);                                                                \
         ls_row_store4<kVec>(g + kSecond, acc1);                                                      \
-        acc0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
-        acc1 = make_float4(0.f, 0.f, 0.f, 0.f);                                                      \
+        LS_ACC_ZERO();                                                                               \
       }                                                                                              \
     }                                                                                                \
   }
@@ -588,6 +609,9 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     if (idx >= end) break;
   }
 #undef LS_SPLATD_WINDOW
+#undef LS_ACC8
+#undef LS_ACC_GET
+#undef LS_ACC_ZERO
 }
 
 int ls_debug_fetch_phase_cycles(unsigned long long* out8) {
@@ -1057,6 +1081,10 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
     const size_t pix = (size_t)bn * dm.HW + (size_t)row * dm.fw + col;
     const float4 f = on ? ls_load4<T>(featT + pix * dm.Cp + 4 * hl) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 gf = make_float4(0.f, 0.f, 0.f, 0.f);
+#if LS_FFMA2
+    const unsigned long long fxy = ls_pack2(f.x, f.y), fzw = ls_pack2(f.z, f.w);
+    unsigned long long gfxy = ls_pack2(0.f, 0.f), gfzw = gfxy;
+#endif
     const int2* pr = pix_recs + pix * dm.D + hl;
     int2 rec = __ldg(pr);
     for (int w = 0; w < wpp; ++w) {
@@ -1083,6 +1111,17 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
           const float wgt = __int_as_float(__shfl_sync(hmask, rec.y, LS_GOCC_ROWS * h + u, 16));
+#if LS_FFMA2
+          // packed pairs: (x,y) and (z,w) of the row take one FFMA2 each for the feature gradient and
+          // one FMUL2 + one FFMA2 for the dot product (6 issue slots per row instead of 8)
+          const unsigned long long gxy = ls_pack2(g[u].x, g[u].y), gzw = ls_pack2(g[u].z, g[u].w);
+          const unsigned long long w2 = ls_pack2(wgt, wgt);
+          float d0, d1;
+          ls_unpack2(ls_fma2(fzw, gzw, ls_mul2(fxy, gxy)), d0, d1);
+          dot[LS_GOCC_ROWS * h + u] = d0 + d1;
+          gfxy = ls_fma2(w2, gxy, gfxy);
+          gfzw = ls_fma2(w2, gzw, gfzw);
+#else
           float dv = f.x * g[u].x;
           dv = fmaf(f.y, g[u].y, dv);
           dv = fmaf(f.z, g[u].z, dv);
@@ -1090,11 +1129,16 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
           dot[LS_GOCC_ROWS * h + u] = dv;
           gf.x = fmaf(wgt, g[u].x, gf.x); gf.y = fmaf(wgt, g[u].y, gf.y);
           gf.z = fmaf(wgt, g[u].z, gf.z); gf.w = fmaf(wgt, g[u].w, gf.w);
+#endif
         }
       }
       gprob_pm[pix * dm.D + 16 * w + hl] = ls_half_butterfly(dot, hl, hmask);
       rec = recn;
     }
+#if LS_FFMA2
+    ls_unpack2(gfxy, gf.x, gf.y);
+    ls_unpack2(gfzw, gf.z, gf.w);
+#endif
     if (on) ls_store4<T>(gfeatT + pix * dm.Cp + 4 * hl, gf);
   }
 }

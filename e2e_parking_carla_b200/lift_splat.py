@@ -290,7 +290,11 @@ class LiftSplatFunction(torch.autograd.Function):
     ``torch.channels_last`` is the splat's native layout (a cell's channels are one row): the
     tile leaves as one bulk store, and a channels_last gradient is gathered in place."""
 
+    # autocast: the function consumes whatever dtype the (autocast) encoder produced - bf16 feature maps
+    # and logits go straight to the bf16 kernels, the BEV tensor is float32 either way as in the
+    # reference (model/bev_model.py:76) - and runs with autocast switched off inside
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, feat, logits, M, t, frustum, shape: LsShape, bev_format=torch.contiguous_format,
                 spare_channels: int = 0, rig_cache: Optional[RigCache] = None):
         _need_cuda(feat, logits, M, t, frustum)
@@ -337,6 +341,7 @@ class LiftSplatFunction(torch.autograd.Function):
         return bev, prob
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_bev, grad_prob):
         prob, feat_nhwc = ctx.saved_tensors
         shape, code, layout, saved = ctx.shape, ctx.code, ctx.layout, ctx.saved_blob
@@ -383,6 +388,8 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
                          (tuple(feat.shape), tuple(depth_logits.shape), B, N))
     if tuple(frustum.shape) != (D, fh, fw, 3):
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
+    if feat.dtype != depth_logits.dtype:          # e.g. one head left in float32 under autocast: compute in float32
+        feat, depth_logits = feat.float(), depth_logits.float()
     shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy,
                        pick_tile_x(Cc, bev_format == torch.channels_last))
     return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format, spare_channels, rig_cache)

@@ -1102,3 +1102,36 @@ def test_every_point_in_one_cell(lib):
     for k in a:
         assert relerr(a[k], b[k]) <= 1e-5, k
     assert torch.equal(a["bev"], _run(shape, c["feat"], c["logits"], c["M"], c["t"])["bev"])
+
+
+def test_autocast_and_mixed_dtypes(lib):
+    """Under torch.autocast the encoder emits bf16 feature maps / logits: they go to the bf16 kernels
+    unchanged, the BEV stays float32 (model/bev_model.py:76), gradients come back in bf16 and reach
+    float32 parameters.  Mixed head dtypes are computed in float32."""
+    from e2e_parking_carla_b200 import BevModel
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.f = torch.nn.Conv2d(3, 64, 8, stride=8)
+            self.d = torch.nn.Conv2d(3, 48, 8, stride=8)
+
+        def forward(self, x):
+            return self.f(x).relu(), self.d(x).relu()
+
+    shape = LiftSplatShape(batch=1, channels=64)
+    model = BevModel(make_cfg(shape), cam_encoder=Enc()).to(DEV)
+    intr, extr = make_rig(1, 4, jitter=True, seed=8)
+    images = torch.randn(1, 4, 3, 256, 256, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        bev, depth = model(images, intr.to(DEV), extr.to(DEV))
+    assert bev.dtype == torch.float32 and depth.dtype == torch.bfloat16
+    (bev.sum() + depth.float().square().sum()).backward()
+    assert model.cam_encoder.f.weight.grad.dtype == torch.float32 and model.cam_encoder.f.weight.grad.abs().sum() > 0
+    ref, _ = model(images, intr.to(DEV), extr.to(DEV))            # float32 run of the same weights
+    assert relerr(bev, ref) <= BF16_TOL
+    ls = _ls()
+    f, z = model.cam_encoder(images.view(4, 3, 256, 256))
+    M, t = model.camera_transform(intr.to(DEV), extr.to(DEV))
+    mixed, prob = ls.lift_splat(f.bfloat16(), z, M, t, model.frustum, model._grid)
+    assert prob.dtype == torch.float32 and relerr(mixed, ref) <= BF16_TOL
