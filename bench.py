@@ -67,14 +67,14 @@ def workload(args) -> LiftSplatShape:
     raise SystemExit("unknown workload")
 
 
-def algorithmic_bytes(shape: LiftSplatShape, s_in: int):
+def algorithmic_bytes(shape: LiftSplatShape, s_in: int, s_out: int = 4):
     """per-sample algorithmic HBM bytes (softmax upstream + prob write)."""
     n, hw = shape.cams, shape.fh * shape.fw
     c, d = shape.channels, shape.depth_bins
     x = int(round((shape.bev_x_bound[1] - shape.bev_x_bound[0]) / shape.bev_x_bound[2]))
     y = int(round((shape.bev_y_bound[1] - shape.bev_y_bound[0]) / shape.bev_y_bound[2]))
     io = n * hw * (c + d) * s_in
-    bev = c * x * y * 4
+    bev = c * x * y * s_out
     return {"fwd": io + bev, "bwd": bev + 2 * io,
             # per kernel (DESIGN.md "Kernels"): what each one must move at minimum
             "splat_fwd": io + bev, "bwd_transpose": bev, "bwd_gather": 2 * io}
@@ -226,7 +226,8 @@ class Stepper:
     """Pre-allocated device buffers + direct C-ABI calls (what LiftSplatFunction does,
     minus the autograd bookkeeping) so the timed region is the library, not Python."""
 
-    def __init__(self, shape: LiftSplatShape, dtype, device, seed=0, bev_format="channels_last", feat_format="nchw"):
+    def __init__(self, shape: LiftSplatShape, dtype, device, seed=0, bev_format="channels_last", feat_format="nchw",
+                 bev_dtype=torch.float32):
         from e2e_parking_carla_b200 import _lib, lift_splat as ls
         from e2e_parking_carla_b200.bev_model import BevModel
         from e2e_parking_carla_b200.synthetic import make_cfg
@@ -235,8 +236,9 @@ class Stepper:
         self.grid = model._grid
         self.frustum = model.frustum.data.to(device)
         self.tile_x = ls.pick_tile_x(shape.channels, bev_format == "channels_last")
+        self.bev_code = ls.LS_BF16 if bev_dtype == torch.bfloat16 else ls.LS_F32
         self.s = ls.make_shape(shape.batch, shape.cams, shape.depth_bins, shape.fh, shape.fw, shape.channels,
-                               self.grid, 0, self.tile_x)
+                               self.grid, 0, self.tile_x, self.bev_code)
         self.code = ls.LS_F32 if dtype == torch.float32 else ls.LS_BF16
         intr, extr = make_rig(shape.batch, shape.cams, jitter=True, seed=1 + seed)
         feat, logits = make_encoder_outputs(shape, seed=seed)
@@ -247,7 +249,7 @@ class Stepper:
         ffmt = torch.channels_last if feat_format == "channels_last" else torch.contiguous_format
         self.layout = ls.LS_FEAT_NHWC if feat_format == "channels_last" else ls.LS_FEAT_NCHW
         feat = feat.contiguous(memory_format=ffmt)
-        gb = gb.contiguous(memory_format=bfmt)
+        gb = gb.contiguous(memory_format=bfmt).to(bev_dtype)
         self.host = {"feat": feat.to(dtype).pin_memory(), "logits": logits.to(dtype).pin_memory(),
                      "intr": intr.pin_memory(), "extr": extr.pin_memory(), "gbev": gb.pin_memory(),
                      "gprob": gp.to(dtype).pin_memory()}
@@ -255,7 +257,7 @@ class Stepper:
         B, Cc, X, Y = shape.batch, shape.channels, self.grid.dim[0], self.grid.dim[1]
         self.M = torch.empty(B, shape.cams, 3, 3, device=device)
         self.t = torch.empty(B, shape.cams, 3, device=device)
-        self.bev = torch.empty((B, Cc, X, Y), device=device, memory_format=bfmt)
+        self.bev = torch.empty((B, Cc, X, Y), device=device, memory_format=bfmt, dtype=bev_dtype)
         self.prob = torch.empty_like(self.dev["logits"])
         self.gfeat = torch.empty_like(self.dev["feat"])          # same memory format as feat
         self.glogits = torch.empty_like(self.dev["logits"])
@@ -356,8 +358,8 @@ class Stepper:
             sizes = _e2e_sizes(sh.batch, chunks)
             starts = [sum(sizes[:i]) for i in range(len(sizes))]
             groups = [(lo, lo + sz) for lo, sz in zip(starts, sizes)]
-            shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid, 0, self.tile_x)
-                      for lo, hi in groups]
+            shapes = [ls.make_shape(hi - lo, n, sh.depth_bins, sh.fh, sh.fw, sh.channels, self.grid, 0, self.tile_x,
+                                    self.bev_code) for lo, hi in groups]
             self._e2e = {"chunks": chunks, "groups": groups, "shapes": shapes, "h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(),
                          "scratch": [torch.empty(ls.scratch_bytes(sc, self.code, True), dtype=torch.uint8,
                                                  device=self.device) for sc in shapes],
@@ -582,6 +584,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--bev-format", default="channels_last", choices=["channels_last", "nchw"],
                     help="memory format of the BEV output and of the gradient arriving on it")
+    ap.add_argument("--bev-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32: the reference's contract (BEV always float32); bf16: opt-in bf16 BEV tensor + gradient "
+                         "(128-byte rows; channels_last only)")
     ap.add_argument("--feat-format", default="nchw", choices=["channels_last", "nchw"],
                     help="memory format of the encoder's feature maps (and of their gradient)")
     ap.add_argument("--cpu-batch", type=int, default=0,
@@ -647,8 +652,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from e2e_parking_carla_b200 import _lib
     lib = _lib.load()
-    st = Stepper(shape, dtype, device, seed=rank, bev_format=args.bev_format, feat_format=args.feat_format)
-    config["bev_format"], config["feat_format"] = args.bev_format, args.feat_format
+    st = Stepper(shape, dtype, device, seed=rank, bev_format=args.bev_format, feat_format=args.feat_format,
+                 bev_dtype=torch.bfloat16 if args.bev_dtype == "bf16" else torch.float32)
+    config["bev_format"], config["feat_format"], config["bev_dtype"] = args.bev_format, args.feat_format, args.bev_dtype
 
     def barrier():
         if dist is not None:
@@ -760,7 +766,7 @@ def main():
     unbind_cpus(all_cpus)
     if rank == 0:
         peak, peak_src = measured_peak()
-        ab = algorithmic_bytes(shape, s_in)
+        ab = algorithmic_bytes(shape, s_in, 2 if args.bev_dtype == "bf16" else 4)
         # dominant kernel group of the step and its own algorithmic traffic
         cand = {"splat_fwd": stages["splat_fwd"], "splat_bwd(transpose+gather)": stages["splat_bwd(transpose+gather)"]}
         dom = max(cand, key=cand.get)

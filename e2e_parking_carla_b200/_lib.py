@@ -21,7 +21,8 @@ class LsShape(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("fh", C.c_int32),
                 ("fw", C.c_int32), ("C", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32),
                 ("Z", C.c_int32), ("start", C.c_float * 3), ("res", C.c_float * 3),
-                ("geom_policy", C.c_int32), ("tile_x", C.c_int32)]
+                ("geom_policy", C.c_int32), ("tile_x", C.c_int32),
+                ("bev_dtype", C.c_int32)]
 
 
 class LsBevStrides(C.Structure):

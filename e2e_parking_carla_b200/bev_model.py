@@ -61,6 +61,10 @@ class BevModel(nn.Module):
     spare_channels : with channels_last, allocate the BEV as the first C channels of a
         ``[B, X, Y, C + spare]`` buffer; ``target_bev.add_target_bev`` then writes the target
         channel (model/parking_model.py:28-46) in place instead of ``torch.cat``-copying the BEV.
+    bev_dtype : ``torch.float32`` (default) is the reference's contract: the BEV tensor is float32 whatever
+        the encoder's dtype (model/bev_model.py:76).  ``torch.bfloat16`` is an opt-in for autocast
+        training - the consumer convolution runs in bf16 anyway: 128-byte cell rows, half the output
+        and gradient-row traffic (needs channels_last, 64 channels, no spare channel).  Sums stay float32.
     static_rig : opt-in.  The caller vouches that intrinsics / extrinsics are the same every call (they
         are constants of the reference's dataset, dataset/carla_dataset.py:392-393): voxel indices, the
         counting sort and the canonical record order are then computed once per (batch shape, device)
@@ -69,7 +73,8 @@ class BevModel(nn.Module):
     """
 
     def __init__(self, cfg, cam_encoder: Optional[nn.Module] = None, geometry: str = "native",
-                 bev_memory_format=torch.channels_last, spare_channels: int = 0, static_rig: bool = False):
+                 bev_memory_format=torch.channels_last, spare_channels: int = 0, static_rig: bool = False,
+                 bev_dtype=torch.float32):
         super().__init__()
         self.cfg = cfg
         if geometry not in ("native", "torch"):
@@ -80,6 +85,7 @@ class BevModel(nn.Module):
         self.bev_memory_format = bev_memory_format
         self.spare_channels = int(spare_channels)
         self._rig_cache = ls.RigCache() if static_rig else None
+        self.bev_dtype = bev_dtype
         if not getattr(cfg, "use_depth_distribution", 1):
             # the reference crashes in this mode too (depth is None at bev_model.py:64)
             raise ValueError("use_depth_distribution=0 is not supported (nor by the reference)")
@@ -181,7 +187,7 @@ class BevModel(nn.Module):
         M, t = self.camera_transform(intrinsics, extrinsics)
         bev_feature, pred_depth = ls.lift_splat(feat, depth_logits, M, t, self.frustum, self._grid,
                                                 self.bev_memory_format, self.spare_channels, self.geom_policy,
-                                                self._rig_cache)
+                                                self._rig_cache, self.bev_dtype)
         return bev_feature, pred_depth
 
     def forward(self, images, intrinsics, extrinsics):

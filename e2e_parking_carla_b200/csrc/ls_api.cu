@@ -101,6 +101,7 @@ static int ls_check_shape(const LsShape* s) {
   if (s->X <= 0 || s->Y <= 0 || s->Z <= 0) return LS_ERR_BAD_ARG;
   if (s->geom_policy != LS_GEOM_TORCH_CPU && s->geom_policy != LS_GEOM_TORCH_CUDA) return LS_ERR_BAD_ARG;
   if (s->tile_x < 0 || s->tile_x > LS_TILE || (s->tile_x & (s->tile_x - 1))) return LS_ERR_BAD_ARG;
+  if (s->bev_dtype != LS_F32 && s->bev_dtype != LS_BF16) return LS_ERR_BAD_ARG;
   if ((long long)s->X * s->Y * s->Z >= (1LL << 28)) return LS_ERR_UNSUPPORTED;
   if ((long long)s->B * s->N * s->D * s->fh * s->fw >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
   return LS_OK;

@@ -60,6 +60,7 @@ struct LsDims {
   int Npts;    // N*D*fh*fw points per sample
   int dbits;   // ceil(log2(D)): sort key = cell_in_tile<<24 | (pix << dbits | d)
   int policy;  // LsGeomPolicy
+  int bev_bf16; // LsShape.bev_dtype == LS_BF16: BEV tensor and its gradient are bf16 (opt-in)
 };
 
 static inline LsDims ls_dims(const LsShape* s) {
@@ -72,6 +73,7 @@ static inline LsDims ls_dims(const LsShape* s) {
   d.dbits = 0;
   while ((1 << d.dbits) < s->D) ++d.dbits;
   d.policy = s->geom_policy;
+  d.bev_bf16 = s->bev_dtype == LS_BF16;
   return d;
 }
 

@@ -43,7 +43,7 @@ int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* s
                       const LsGrid& g, int2* recs_sorted, int2* pix_recs, cudaStream_t s);
 int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int* seg_start, const LsDims& dm,
                             const LsGrid& g, float* gT, cudaStream_t s);
-int ls_launch_bwd_gather(const float* rows_base, long long sample_stride, long long row_stride, int mode /* LsGradIn */,
+int ls_launch_bwd_gather(const void* rows_base, long long sample_stride, long long row_stride, int mode /* LsGradIn */,
                          const void* featT, int dtype, const int2* pix_recs, const LsDims& dm, const LsGrid& g,
                          float* gprob_pm, void* gfeatT, cudaStream_t s);
 int ls_classify_bev_out(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g);   // LsBevOut

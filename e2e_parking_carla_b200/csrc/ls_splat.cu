@@ -455,9 +455,13 @@ template <bool kVec> __device__ __forceinline__ void ls_row_store4(float* g, flo
   if (kVec) { __stcs(reinterpret_cast<float4*>(g), v); }
   else { __stcs(g, v.x); __stcs(g + 1, v.y); __stcs(g + 2, v.z); __stcs(g + 3, v.w); }
 }
-template <bool kVec> __device__ __forceinline__ float4 ls_row_load4_cg(const float* g) {
-  if (kVec) return __ldcg(reinterpret_cast<const float4*>(g));
-  return make_float4(__ldcg(g), __ldcg(g + 1), __ldcg(g + 2), __ldcg(g + 3));
+// bf16 BEV rows (opt-in, always 8-byte aligned): four channels = one 8-byte store
+template <bool kVec> __device__ __forceinline__ void ls_row_store4(__nv_bfloat16* g, float4 v) {
+  __nv_bfloat162 a = __float22bfloat162_rn(make_float2(v.x, v.y)), b = __float22bfloat162_rn(make_float2(v.z, v.w));
+  uint2 raw;
+  raw.x = *reinterpret_cast<unsigned*>(&a);
+  raw.y = *reinterpret_cast<unsigned*>(&b);
+  __stcs(reinterpret_cast<uint2*>(g), raw);
 }
 
 // eight consecutive bf16 channels (16 B) -> two float4
@@ -471,11 +475,11 @@ __device__ __forceinline__ void ls_load8_bf16(const char* p, float4& a, float4& 
   b = make_float4(v2.x, v2.y, v3.x, v3.y);
 }
 
-template <typename T, bool kVec>
+template <typename T, bool kVec, typename TO>
 __global__ void __launch_bounds__(LS_THREADS, LS_SPLATD_MINB)
 ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
                            const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm,
-                           LsGrid grid, float* __restrict__ bev, LsBevStrides st) {
+                           LsGrid grid, TO* __restrict__ bev, LsBevStrides st) {
   constexpr int kC = 64;
   __shared__ int seg[LS_TILE + 1];
   const int b = blockIdx.x % dm.B;
@@ -485,8 +489,8 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
   const int tx0 = (tile_id / grid.tiles_y) << grid.tx_shift, ty0 = (tile_id % grid.tiles_y) << grid.ty_shift;
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
-  float* tile0 = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * st.y;
-  // row of cell-in-tile cl (floats from tile0): tile row cl / ty, column cl % ty
+  TO* tile0 = bev + (size_t)b * st.b + (size_t)tx0 * st.x + (size_t)ty0 * st.y;
+  // row of cell-in-tile cl (elements from tile0): tile row cl / ty, column cl % ty
   const unsigned ty_shift = (unsigned)grid.ty_shift, ty_mask = (unsigned)grid.ty - 1u;
   const unsigned sxu = (unsigned)st.x, syu = (unsigned)st.y;      // < 2^32 floats (checked by the classifier)
   auto row_off = [&](unsigned cl) -> size_t { return (size_t)((cl >> ty_shift) * sxu) + (size_t)((cl & ty_mask) * syu); };
@@ -541,7 +545,7 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   constexpr int kSecond = kHalf ? 4 : 32;        // channel distance between the lane's two float4 accumulators
   const char* f0 = reinterpret_cast<const char*>(fbase + (kHalf ? 8 : 4) * ql);
   const unsigned f1off = (unsigned)(32 * sizeof(T));
-  float* lane0 = tile0 + (kHalf ? 8 : 4) * ql;    // this lane's first quad of row 0
+  TO* lane0 = tile0 + (kHalf ? 8 : 4) * ql;       // this lane's first quad of row 0
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #if LS_FFMA2
   // the 8 channel sums of this lane live in four packed float32 pairs: 4 FFMA2 per record instead of 8 FFMA
@@ -594,7 +598,7 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
         LS_ACC8(wt, fa[u], fb[u]);                                                                   \
       }                                                                                              \
       if (cur[u].x & LS_REC_LAST) {                                                                  \
-        float* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                       \
+        TO* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                          \
         LS_ACC_GET();                                                                                \
         ls_row_store4<kVec>(g, acc0);                                                                \
         ls_row_store4<kVec>(g + kSecond, acc1);                                                      \
@@ -649,6 +653,11 @@ static bool ls_bev_vec4(const float* p, const LsBevStrides& st, const LsGrid& g)
 
 // How the splat writes a BEV tensor with these strides (include/ls_b200.h LsBevStrides).
 int ls_classify_bev_out(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g) {
+  if (dm.bev_bf16) {          // strides in bf16 elements: rows must be 16-byte aligned
+    const bool ok = st.c == 1 && dm.C == 64 && st.y >= 64 && st.y % 8 == 0 && st.x % 8 == 0 && st.b % 8 == 0 &&
+                    (uintptr_t)p % 16 == 0 && st.x < (1LL << 32) && st.y < (1LL << 32);
+    return ok ? LS_OUT_NHWC_DIRECT_VEC : LS_OUT_BAD;
+  }
   if (st.y == 1 && (st.c != 1 || dm.C == 1)) return ls_bev_vec4(p, st, g) ? LS_OUT_NCHW_VEC4 : LS_OUT_NCHW_SCALAR;
   if (st.c == 1) {
     const bool vec = (uintptr_t)p % 16 == 0 && st.b % 4 == 0 && st.x % 4 == 0 && st.y % 4 == 0;
@@ -701,10 +710,13 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   const bool direct = out == LS_OUT_NHWC_DIRECT_VEC || out == LS_OUT_NHWC_DIRECT_SCALAR ||
                       (out == LS_OUT_NHWC_BULK && !(want_bulk && g.tx == 1));
   if (!direct && g.tx != 1) return LS_ERR_UNSUPPORTED;      // the tile kernels know 1 x 128 strips only
-  if (direct && out != LS_OUT_NHWC_DIRECT_SCALAR) {
-    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+  if (dm.bev_bf16) {          // opt-in bf16 BEV: the classifier only lets dense, aligned 64-channel rows through
+    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true, __nv_bfloat16>), grid, block, 0, s, (const T*)featT, seg_start, tile_order,
+              rs, dm, g, reinterpret_cast<__nv_bfloat16*>(bev), st);
+  } else if (direct && out != LS_OUT_NHWC_DIRECT_SCALAR) {
+    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true, float>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
   } else if (direct) {
-    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, false>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, false, float>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
   } else if (out == LS_OUT_NHWC_BULK) {
     smem = (size_t)LS_TILE * 64 * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
     LS_SPLAT(LS_OUT_NHWC_BULK, 64);
@@ -942,11 +954,13 @@ int ls_launch_bwd_transpose(const float* gbev, const LsBevStrides& st, const int
 // then serialised the window into pairs: 2x slower).
 __device__ float4 ls_zero_row[4 * LS_CCHUNK / 4];
 
-template <int MODE>
+// TG: element type of the gradient rows (float; __nv_bfloat16 for the opt-in bf16 BEV, direct-vector mode only)
+template <int MODE, typename TG>
 __device__ __forceinline__ float4 ls_grad_row4(const char* __restrict__ base, const char* __restrict__ zero,
                                                unsigned rank, unsigned row_bytes, unsigned nrows) {
   if (MODE == LS_GRAD_STAGED) return __ldg(reinterpret_cast<const float4*>(base + (size_t)rank * row_bytes));
   const char* p = rank < nrows ? base + (size_t)rank * row_bytes : zero;
+  if (sizeof(TG) == 2) return ls_load4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p));
   if (MODE == LS_GRAD_DIRECT_VEC) return __ldg(reinterpret_cast<const float4*>(p));
   const float* f = reinterpret_cast<const float*>(p);
   return make_float4(__ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3));
@@ -983,8 +997,8 @@ __device__ __forceinline__ float ls_half_butterfly(float (&dot)[16], int hl, uns
 
 // Where a sample's gradient rows live: base + b * sample_stride floats, rows row_bytes apart.
 struct LsRows {
-  const float* base;
-  long long sample_stride;
+  const void* base;
+  long long sample_stride;     // elements
   unsigned row_bytes;
   unsigned nrows;       // X*Y
 };
@@ -1005,7 +1019,7 @@ ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __res
 #pragma unroll
   for (int q = 0; q < NCH; ++q) on[q] = (q * LS_CCHUNK + 4 * hl) < dm.Cp;
   // lanes beyond the channel count read valid bytes (lane 0's) and never store
-  const char* gb = reinterpret_cast<const char*>(rows.base + (size_t)b * rows.sample_stride);
+  const char* gb = reinterpret_cast<const char*>(reinterpret_cast<const float*>(rows.base) + (size_t)b * rows.sample_stride);
   const char* zrow = reinterpret_cast<const char*>(ls_zero_row);
 
   for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
@@ -1031,7 +1045,7 @@ ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __res
         float4 g[16];
         const char* gq = gb + (on[q] ? (q * LS_CCHUNK + 4 * hl) * 4 : 0);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) g[u] = ls_grad_row4<MODE>(gq, zrow, (unsigned)r[u].x, rows.row_bytes, rows.nrows);
+        for (int u = 0; u < 16; ++u) g[u] = ls_grad_row4<MODE, float>(gq, zrow, (unsigned)r[u].x, rows.row_bytes, rows.nrows);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const float w = __int_as_float(r[u].y);
@@ -1062,7 +1076,7 @@ ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __res
 // records of a depth window are loaded one per lane (a single coalesced 128-byte load per
 // half-warp, prefetched a window ahead, broadcast with 16-wide shuffles) and the rows are
 // gathered eight at a time - under 86 registers, three CTAs (24 warps) per SM.
-template <typename T, int MODE>
+template <typename T, int MODE, typename TG>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GOCC_MINB)
 ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
                          LsDims dm, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
@@ -1074,7 +1088,8 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
   const unsigned hmask = ls_half_mask();
   const bool on = 4 * hl < dm.Cp;
   // lanes beyond the channel count read valid bytes (lane 0's) and never store
-  const char* gb = reinterpret_cast<const char*>(rows.base + (size_t)b * rows.sample_stride + (on ? 4 * hl : 0));
+  const char* gb = reinterpret_cast<const char*>(reinterpret_cast<const TG*>(rows.base) + (size_t)b * rows.sample_stride +
+                                                 (on ? 4 * hl : 0));
   const char* zrow = reinterpret_cast<const char*>(ls_zero_row);
   const int wpp = dm.D >> 4;                                                  // windows per pixel
   for (int row = hw; row < dm.fh; row += LS_HALFWARPS) {
@@ -1106,7 +1121,7 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
           const unsigned rank = (unsigned)__shfl_sync(hmask, rec.x, LS_GOCC_ROWS * h + u, 16);
-          g[u] = ls_grad_row4<MODE>(gb, zrow, rank, rows.row_bytes, rows.nrows);
+          g[u] = ls_grad_row4<MODE, TG>(gb, zrow, rank, rows.row_bytes, rows.nrows);
         }
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
@@ -1145,6 +1160,12 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 
 // How the backward reads a gradient with these strides (include/ls_b200.h LsBevStrides).
 int ls_classify_grad_in(const float* p, const LsBevStrides& st, const LsDims& dm, const LsGrid& g) {
+  if (dm.bev_bf16) {      // bf16 gradient rows: in place only, through the register-lean gather
+    const bool ok = st.c == 1 && dm.C == 64 && dm.D % 16 == 0 && st.x == (long long)g.Y * st.y && st.y >= 64 &&
+                    st.y % 4 == 0 && st.b % 4 == 0 && (uintptr_t)p % 8 == 0 &&
+                    (unsigned long long)g.XY * (unsigned long long)st.y * 2ULL < (1ULL << 32);
+    return ok ? LS_GRAD_DIRECT_VEC : LS_GRAD_BAD;
+  }
   if (st.y == 1 && (st.c != 1 || dm.C == 1)) return LS_GRAD_STAGED;
   if (st.c == 1 && dm.C == dm.Cp && st.x == (long long)g.Y * st.y && st.y >= dm.C &&
       (unsigned long long)g.XY * (unsigned long long)st.y * 4ULL < (1ULL << 32)) {
@@ -1159,9 +1180,15 @@ static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2*
                               float* gprob_pm, void* gfeatT, cudaStream_t s) {
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
+  if (dm.bev_bf16) {
+    if (MODE != LS_GRAD_DIRECT_VEC) return LS_ERR_UNSUPPORTED;
+    LS_LAUNCH((ls_bwd_gather_occ_kernel<T, LS_GRAD_DIRECT_VEC, __nv_bfloat16>), grid, dim3(LS_GATHER_THREADS), 0, s, rows,
+              (const T*)featT, pix_recs, dm, gprob_pm, (T*)gfeatT);
+    return LS_OK;
+  }
   if (LS_GATHER_OCC && dm.D % 16 == 0 && nch == 1) {
-    LS_LAUNCH((ls_bwd_gather_occ_kernel<T, MODE>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT, pix_recs,
-              dm, gprob_pm, (T*)gfeatT);
+    LS_LAUNCH((ls_bwd_gather_occ_kernel<T, MODE, float>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT,
+              pix_recs, dm, gprob_pm, (T*)gfeatT);
     return LS_OK;
   }
 #define LS_GATHER(NCH)                                                                                        \
@@ -1179,13 +1206,13 @@ static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2*
 }
 
 // rows: staged (gT, mode LS_GRAD_STAGED) or the channels-last gradient itself (direct modes)
-int ls_launch_bwd_gather(const float* rows_base, long long sample_stride, long long row_stride, int mode,
+int ls_launch_bwd_gather(const void* rows_base, long long sample_stride, long long row_stride, int mode,
                          const void* featT, int dtype, const int2* pix_recs, const LsDims& dm, const LsGrid& g,
                          float* gprob_pm, void* gfeatT, cudaStream_t s) {
   LsRows rows;
   rows.base = rows_base;
   rows.sample_stride = sample_stride;
-  rows.row_bytes = (unsigned)(row_stride * 4);
+  rows.row_bytes = (unsigned)(row_stride * (dm.bev_bf16 && mode != LS_GRAD_STAGED ? 2 : 4));
   rows.nrows = (unsigned)g.XY;
 #define LS_GD(TT, MODE) return ls_gather_dispatch<TT, MODE>(rows, featT, pix_recs, dm, gprob_pm, gfeatT, s)
   if (dtype == LS_F32) {

@@ -44,10 +44,11 @@ def pick_tile_x(channels: int, bev_channels_last: bool) -> int:
 
 
 def make_shape(B: int, N: int, D: int, fh: int, fw: int, Cc: int, grid: GridSpec, geom_policy: int = 0,
-               tile_x: int = 1) -> LsShape:
+               tile_x: int = 1, bev_dtype: int = LS_F32) -> LsShape:
     s = LsShape()
     s.geom_policy = geom_policy
     s.tile_x = tile_x
+    s.bev_dtype = bev_dtype
     s.B, s.N, s.D, s.fh, s.fw, s.C = B, N, D, fh, fw, Cc
     s.X, s.Y, s.Z = grid.dim
     for i in range(3):
@@ -86,8 +87,11 @@ def _bev_strides(t: torch.Tensor) -> LsBevStrides:
     return LsBevStrides(t.stride(0), t.stride(1), t.stride(2), t.stride(3))
 
 
-def _grad_layout_ok(g: torch.Tensor) -> bool:
+def _grad_layout_ok(g: torch.Tensor, depth_bins: int = 16) -> bool:
     """Can ls_backward read this gradient in place?  (mirrors ls_classify_grad_in)"""
+    if g.dtype == torch.bfloat16:
+        return (g.stride(1) == 1 and g.shape[1] == 64 and depth_bins % 16 == 0 and g.stride(2) == g.shape[3] * g.stride(3)
+                and g.stride(3) >= 64 and g.stride(3) % 4 == 0 and g.stride(0) % 4 == 0 and g.data_ptr() % 8 == 0)
     if g.stride(3) == 1 and (g.stride(1) != 1 or g.shape[1] == 1):
         return True
     return (g.stride(1) == 1 and g.shape[1] % 4 == 0 and g.stride(2) == g.shape[3] * g.stride(3)
@@ -267,7 +271,7 @@ class RigCache:
 
     def prepare(self, shape: LsShape, code: int, device: torch.device) -> torch.Tensor:
         key = (shape.B, shape.N, shape.D, shape.fh, shape.fw, shape.C, shape.X, shape.Y, tuple(shape.start),
-               tuple(shape.res), shape.geom_policy, shape.tile_x, code, device.index)
+               tuple(shape.res), shape.geom_policy, shape.tile_x, shape.bev_dtype, code, device.index)
         if key != self.key or self.blob is None:
             n = _lib.load().ls_cache_bytes(C.byref(shape))
             if n == 0:
@@ -311,7 +315,10 @@ class LiftSplatFunction(torch.autograd.Function):
             raise ValueError("spare BEV channels need the channels_last layout")
         # spare_channels: the BEV is the first C channels of a channels-last [B,X,Y,C+spare] buffer, so
         # that add_target_bev (model/parking_model.py:28-46) fills in its channel without a torch.cat copy
-        bev = torch.empty((shape.B, shape.C + spare_channels, shape.X, shape.Y), dtype=torch.float32, device=dev,
+        bev_dt = torch.bfloat16 if shape.bev_dtype == LS_BF16 else torch.float32
+        if shape.bev_dtype == LS_BF16 and (bev_format != torch.channels_last or shape.C != 64 or spare_channels):
+            raise ValueError("a bf16 BEV tensor needs the dense channels_last layout and 64 channels")
+        bev = torch.empty((shape.B, shape.C + spare_channels, shape.X, shape.Y), dtype=bev_dt, device=dev,
                           memory_format=bev_format)
         if spare_channels:
             bev = bev[:, :shape.C]
@@ -350,9 +357,13 @@ class LiftSplatFunction(torch.autograd.Function):
         dev = prob.device
         if grad_bev is None:
             grad_bev = torch.zeros(shape.B, shape.C, shape.X, shape.Y, dtype=torch.float32, device=dev)
-        grad_bev = grad_bev.to(torch.float32)
-        if not _grad_layout_ok(grad_bev):
-            grad_bev = grad_bev.contiguous()
+        if shape.bev_dtype == LS_BF16 and not (grad_bev.dtype == torch.bfloat16 and _grad_layout_ok(grad_bev, shape.D)):
+            shape = LsShape.from_buffer_copy(shape)      # this gradient cannot be read as bf16 rows: float32 path
+            shape.bev_dtype = LS_F32
+        if shape.bev_dtype == LS_F32:
+            grad_bev = grad_bev.to(torch.float32)
+            if not _grad_layout_ok(grad_bev):
+                grad_bev = grad_bev.contiguous()
         if grad_prob is not None:
             grad_prob = grad_prob.to(prob.dtype).contiguous()
         fmt = torch.channels_last if layout == LS_FEAT_NHWC else torch.contiguous_format
@@ -376,7 +387,8 @@ class LiftSplatFunction(torch.autograd.Function):
 
 def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, t: torch.Tensor,
                frustum: torch.Tensor, grid: GridSpec, bev_format=torch.contiguous_format, spare_channels: int = 0,
-               geom_policy: int = 0, rig_cache: Optional[RigCache] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+               geom_policy: int = 0, rig_cache: Optional[RigCache] = None, bev_dtype=torch.float32
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
     """feat [B*N,C,fh,fw], depth_logits [B*N,D,fh,fw] (CamEncoder outputs,
     model/cam_encoder.py:102-111), M [B,N,3,3], t [B,N,3], frustum [D,fh,fw,3] ->
     (bev f32[B,C,X,Y] in ``bev_format``, depth_prob [B*N,D,fh,fw])."""
@@ -390,8 +402,10 @@ def lift_splat(feat: torch.Tensor, depth_logits: torch.Tensor, M: torch.Tensor, 
         raise ValueError("frustum %s does not match depth/feature maps" % (tuple(frustum.shape),))
     if feat.dtype != depth_logits.dtype:          # e.g. one head left in float32 under autocast: compute in float32
         feat, depth_logits = feat.float(), depth_logits.float()
-    shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy,
-                       pick_tile_x(Cc, bev_format == torch.channels_last))
+    if bev_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("bev_dtype must be torch.float32 or torch.bfloat16")
+    shape = make_shape(B, N, D, fh, fw, Cc, grid, geom_policy, pick_tile_x(Cc, bev_format == torch.channels_last),
+                       LS_BF16 if bev_dtype == torch.bfloat16 else LS_F32)
     return LiftSplatFunction.apply(feat, depth_logits, M, t, frustum, shape, bev_format, spare_channels, rig_cache)
 
 

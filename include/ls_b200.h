@@ -53,6 +53,12 @@ typedef struct LsShape {
                         * 1 x 128 strips (required for NCHW BEV tensors), 8 = 8 x 16 (what the
                         * channels-last 64-channel splat wants); a power of two <= 128.  Use the
                         * same value for every call of one forward/backward pair.            */
+  int32_t bev_dtype;   /* LsDtype of the BEV tensor and of the gradient arriving on it.  LS_F32 (0) is the
+                        * reference's contract (model/bev_model.py:76: always float32).  LS_BF16 is an opt-in
+                        * for autocast training (the consumer convolution runs in bf16 anyway): 128-byte
+                        * rows, half the output and gradient-row traffic; needs a dense channels-last
+                        * tensor with C == 64 (and D % 16 == 0 for the backward); the `float*` BEV
+                        * arguments then point at bf16 data.  Sums are still taken in float32.      */
 } LsShape;
 
 /* model/bev_model.py:54 is a broadcast batched 3x3 matmul; its float32 rounding depends on the

@@ -1135,3 +1135,39 @@ def test_autocast_and_mixed_dtypes(lib):
     M, t = model.camera_transform(intr.to(DEV), extr.to(DEV))
     mixed, prob = ls.lift_splat(f.bfloat16(), z, M, t, model.frustum, model._grid)
     assert prob.dtype == torch.float32 and relerr(mixed, ref) <= BF16_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_bf16_bev_opt_in(lib, dtype):
+    """BevModel(bev_dtype=torch.bfloat16): bf16 BEV tensor and bf16 gradient rows (128 bytes per cell),
+    sums in float32.  Forward = the float32-BEV result rounded once to bf16; gradients within the bf16
+    tolerance of the float64 oracle evaluated on the bf16-rounded upstream gradient; a gradient that
+    cannot be read in place (NCHW float32) falls back to the float32 path with the same result."""
+    ls = _ls()
+    shape = LiftSplatShape(batch=2, channels=64)
+    c = _oracle_case(shape, rig_seed=53, in_seed=25)
+    fr, grid = _dev(frustum_of(shape)), _grid_spec(shape)
+    Md, td = _dev(c["M"]), _dev(c["t"])
+
+    def run(bev_dtype, gb):
+        f = c["feat"].to(DEV, dtype).requires_grad_(True)
+        z = c["logits"].to(DEV, dtype).requires_grad_(True)
+        bev, prob = ls.lift_splat(f, z, Md, td, fr, grid, torch.channels_last, bev_dtype=bev_dtype)
+        torch.autograd.backward([bev, prob], [gb, c["gp"].to(DEV, dtype)])
+        return bev.detach(), f.grad, z.grad
+
+    gb16 = c["gb"].to(DEV).contiguous(memory_format=torch.channels_last).bfloat16()
+    b16, gf16, gl16 = run(torch.bfloat16, gb16)
+    assert b16.dtype == torch.bfloat16 and b16.is_contiguous(memory_format=torch.channels_last)
+    b32, gf32, gl32 = run(torch.float32, gb16.float())           # same upstream values, float32 tensors
+    assert torch.equal(b16, b32.bfloat16())                      # one rounding on the store
+    assert torch.equal(gf16, gf32) and torch.equal(gl16, gl32)   # the rows carry the same values either way
+    ref = _oracle_outputs(shape, c, dtype)
+    assert_close(b16.float(), ref["bev"], BF16_TOL, "bev")
+    assert_close(gf16.float(), ref["grad_feat"], BF16_TOL, "grad_feat")
+    # fallback: an NCHW float32 gradient on a bf16-BEV forward
+    f = c["feat"].to(DEV, dtype).requires_grad_(True)
+    z = c["logits"].to(DEV, dtype).requires_grad_(True)
+    bev, prob = ls.lift_splat(f, z, Md, td, fr, grid, torch.channels_last, bev_dtype=torch.bfloat16)
+    (bev.float() * gb16.float().contiguous()).sum().backward()
+    assert relerr(f.grad, gf32) < (1e-5 if dtype == torch.float32 else 2e-2)
