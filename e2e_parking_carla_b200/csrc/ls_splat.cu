@@ -475,13 +475,15 @@ __device__ __forceinline__ void ls_load8_bf16(const char* p, float4& a, float4& 
   b = make_float4(v2.x, v2.y, v3.x, v3.y);
 }
 
-template <typename T, bool kVec, typename TO>
+// kStrip: 1 x 128 tiles (the default): a cell's row offset is cl * y-stride, no shift/mask/second multiply
+template <typename T, bool kVec, typename TO, bool kStrip>
 __global__ void __launch_bounds__(LS_THREADS, LS_SPLATD_MINB)
 ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ seg_start,
                            const int* __restrict__ tile_order, const int2* __restrict__ recs_sorted, LsDims dm,
                            LsGrid grid, TO* __restrict__ bev, LsBevStrides st) {
   constexpr int kC = 64;
   __shared__ int seg[LS_TILE + 1];
+  __shared__ int cuts[LS_QWARPS + 1];
   const int b = blockIdx.x % dm.B;
   const int tid = threadIdx.x;
   ls_pdl_trigger();
@@ -493,13 +495,17 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   // row of cell-in-tile cl (elements from tile0): tile row cl / ty, column cl % ty
   const unsigned ty_shift = (unsigned)grid.ty_shift, ty_mask = (unsigned)grid.ty - 1u;
   const unsigned sxu = (unsigned)st.x, syu = (unsigned)st.y;      // < 2^32 floats (checked by the classifier)
-  auto row_off = [&](unsigned cl) -> size_t { return (size_t)((cl >> ty_shift) * sxu) + (size_t)((cl & ty_mask) * syu); };
+  auto row_off = [&](unsigned cl) -> size_t {
+    if (kStrip) return (size_t)(cl * syu);
+    return (size_t)((cl >> ty_shift) * sxu) + (size_t)((cl & ty_mask) * syu);
+  };
   {
     // this thread's cell: empty cells inside the grid get a zero row (the BEV tensor is never memset)
     const int a = __ldg(segg + tid), e = __ldg(segg + tid + 1);
     seg[tid] = a;
     if (tid == LS_TILE - 1) seg[LS_TILE] = e;
-    const bool in_grid = (tx0 + (int)((unsigned)tid >> ty_shift)) < grid.X && (ty0 + (int)((unsigned)tid & ty_mask)) < grid.Y;
+    const bool in_grid = kStrip ? (ty0 + tid < grid.Y)
+                                : (tx0 + (int)((unsigned)tid >> ty_shift)) < grid.X && (ty0 + (int)((unsigned)tid & ty_mask)) < grid.Y;
     unsigned m = __ballot_sync(0xffffffffu, in_grid && a == e);
     const int lane = tid & 31, wbase = tid & ~31;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,19 +526,23 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   // down to cell boundaries, so every cell is summed by ONE quarter-warp, front to back, in
   // canonical order: the bits of a cell do not depend on the tiling or on where the cuts fall.
   const int ql = tid & 7, qw = tid >> 3, n = s1 - s0;
-  auto cut = [&](int q) -> int {
-    if (q >= LS_QWARPS) return s1;
-    const int target = s0 + (int)(((long long)q * n) / LS_QWARPS);
-    int lo = 0, hi = LS_TILE;                    // largest cell with seg[cell] <= target
+  if (tid <= LS_QWARPS) {                        // 17 threads find the 17 cuts, everyone else just reads them
+    int c = s1;
+    if (tid < LS_QWARPS) {
+      const int target = s0 + (int)(((long long)tid * n) / LS_QWARPS);
+      int lo = 0, hi = LS_TILE;                  // largest cell with seg[cell] <= target
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (seg[mid] <= target) lo = mid; else hi = mid - 1;
+      for (int it = 0; it < 8; ++it) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (seg[mid] <= target) lo = mid; else hi = mid - 1;
+      }
+      c = seg[lo];
     }
-    return seg[lo];
-  };
-  int idx = cut(qw);
-  const int end = cut(qw + 1);
+    cuts[tid] = c;
+  }
+  __syncthreads();
+  int idx = cuts[qw];
+  const int end = cuts[qw + 1];
   if (idx >= end) return;
   const T* fbase = featT + (size_t)b * dm.N * dm.HW * kC;
   const int2* rs = recs_sorted + (size_t)b * ls_sorted_capacity(dm.Npts);
@@ -710,13 +720,21 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   const bool direct = out == LS_OUT_NHWC_DIRECT_VEC || out == LS_OUT_NHWC_DIRECT_SCALAR ||
                       (out == LS_OUT_NHWC_BULK && !(want_bulk && g.tx == 1));
   if (!direct && g.tx != 1) return LS_ERR_UNSUPPORTED;      // the tile kernels know 1 x 128 strips only
+#define LS_DIRECT(VEC, TOUT, PTR)                                                                                      \
+  do {                                                                                                                 \
+    if (g.tx == 1)                                                                                                     \
+      LS_LAUNCH((ls_splat_fwd_direct_kernel<T, VEC, TOUT, true>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, \
+                rs, dm, g, PTR, st);                                                                                   \
+    else                                                                                                               \
+      LS_LAUNCH((ls_splat_fwd_direct_kernel<T, VEC, TOUT, false>), grid, block, 0, s, (const T*)featT, seg_start,       \
+                tile_order, rs, dm, g, PTR, st);                                                                       \
+  } while (0)
   if (dm.bev_bf16) {          // opt-in bf16 BEV: the classifier only lets dense, aligned 64-channel rows through
-    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true, __nv_bfloat16>), grid, block, 0, s, (const T*)featT, seg_start, tile_order,
-              rs, dm, g, reinterpret_cast<__nv_bfloat16*>(bev), st);
+    LS_DIRECT(true, __nv_bfloat16, reinterpret_cast<__nv_bfloat16*>(bev));
   } else if (direct && out != LS_OUT_NHWC_DIRECT_SCALAR) {
-    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, true, float>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+    LS_DIRECT(true, float, bev);
   } else if (direct) {
-    LS_LAUNCH((ls_splat_fwd_direct_kernel<T, false, float>), grid, block, 0, s, (const T*)featT, seg_start, tile_order, rs, dm, g, bev, st);
+    LS_DIRECT(false, float, bev);
   } else if (out == LS_OUT_NHWC_BULK) {
     smem = (size_t)LS_TILE * 64 * sizeof(float) + (LS_QWARPS + 4) * sizeof(int);
     LS_SPLAT(LS_OUT_NHWC_BULK, 64);
@@ -730,6 +748,7 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
     LS_SPLAT(LS_OUT_NCHW_SCALAR, 0);
   }
 #undef LS_SPLAT
+#undef LS_DIRECT
   return LS_OK;
 }
 
