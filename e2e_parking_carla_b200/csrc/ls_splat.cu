@@ -71,7 +71,7 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 // =====================================================================================
 #define LS_CANON_THREADS 256
 #ifndef LS_CANON_BIG
-#define LS_CANON_BIG 192      // cells with more records than this take the bucketed path
+#define LS_CANON_BIG 512      // cells with more records than this take the bucketed path (its ~50 barriers cost more than 512^2/256 compares per thread)
 #endif
 #define LS_CANON_BUCKETS 1024 // by the top 10 of the 24 key bits (4 KB of shared memory: keeps the L1 share of the hot path)
 #define LS_CANON_BSHIFT 14
