@@ -73,6 +73,24 @@ def test_abi_argument_checking(lib):
     odd = ls.LsBevStrides(64 * 200 * 200, 2, 200 * 128, 128)
     assert lib.ls_forward(dummy16, 0, dummy16, 0, dummy16, dummy16, dummy16, C.byref(s), dummy16, 1 << 40, None, 0,
                           dummy16, C.byref(odd), dummy16, None) == -2
+    # round-2 entry points: same conventions
+    assert lib.ls_cache_bytes(C.byref(s)) > 0 and lib.ls_cache_bytes(C.byref(bad)) == 0
+    assert lib.ls_forward_cached(None, 0, None, 0, None, None, None, C.byref(s), None, 0, None, 0, None, 0, 1, None,
+                                 None, None, None) == -1
+    assert lib.ls_forward_cached(dummy16, 0, dummy16, 0, dummy16, dummy16, dummy16, C.byref(s), dummy16, 1 << 40, None, 0,
+                                 dummy16, 16, 1, dummy16, C.byref(ls.LsBevStrides(2560000, 40000, 200, 1)), dummy16,
+                                 None) == -3                       # cache blob too small
+    assert lib.ls_depth_loss_ws_bytes(4, 32, 32) == 4 * 32 * 2 * 4 and lib.ls_depth_loss_ws_bytes(0, 32, 32) == 0
+    assert lib.ls_depth_loss_fwd(None, 0, None, 4, 48, 32, 32, 8, 0.25, 0.25, None, None, 0, None, None) == -1
+    assert lib.ls_depth_loss_fwd(dummy16, 0, dummy16, 4, 48, 32, 32, 8, 0.25, 0.25, dummy16, dummy16, 8, dummy16,
+                                 None) == -3                       # workspace too small
+    assert lib.ls_depth_loss_bwd(dummy16, 3, dummy16, dummy16, None, 4, 48, 32, 32, dummy16, None) == -1   # dtype
+    assert lib.ls_target_bev(None, 2, 200, 200, None, 0, 0, 0, None) == -1
+    assert lib.ls_index_geom(None, C.byref(s), None, None, None, None, None) == -1
+    odd_policy = ls.make_shape(1, 4, 48, 32, 32, 64, grid, geom_policy=7)
+    assert lib.ls_scratch_bytes(C.byref(odd_policy), ls.LS_F32, 1) == 0
+    assert lib.ls_scratch_bytes(C.byref(ls.make_shape(1, 4, 48, 32, 32, 64, grid, tile_x=3)), ls.LS_F32, 1) == 0
+    assert lib.ls_scratch_bytes(C.byref(ls.make_shape(1, 4, 48, 32, 32, 64, grid, tile_x=8)), ls.LS_F32, 1) > 0
     # unknown dtype code
     dummy = C.c_void_p(16)
     assert lib.ls_softmax(dummy, 7, C.byref(s), dummy, None) == -1
