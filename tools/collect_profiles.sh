@@ -7,6 +7,7 @@ python bench.py --steps 20 --warmup 5 --dtype bf16 --no-train --no-gpu-reference
 python bench.py --steps 10 --warmup 3 --workload stress --no-train --no-gpu-reference --no-cpu-baseline > $O/stress.out 2>> $O/bench.err && last $O/stress.out $O/r02_bench_stress.json
 python bench.py --steps 10 --warmup 3 --workload stress --dtype bf16 --no-train --no-gpu-reference --no-cpu-baseline > $O/stressb.out 2>> $O/bench.err && last $O/stressb.out $O/r02_bench_stress_bf16.json
 python bench.py --steps 20 --warmup 5 --bev-format nchw --no-train --no-gpu-reference --no-cpu-baseline > $O/nchw.out 2>> $O/bench.err && last $O/nchw.out $O/r02_bench_nchw.json
+python bench.py --steps 20 --warmup 5 --dtype bf16 --bev-dtype bf16 --no-train --no-gpu-reference --no-cpu-baseline > $O/bevbf16.out 2>> $O/bench.err && last $O/bevbf16.out $O/r02_bench_bf16_bev.json
 python bench.py --steps 20 --warmup 5 --feat-format channels_last --no-train --no-gpu-reference --no-cpu-baseline > $O/featcl.out 2>> $O/bench.err && last $O/featcl.out $O/r02_bench_featcl.json
 LS_SPLAT_OUT=bulk python bench.py --steps 20 --warmup 5 --no-train --no-gpu-reference --no-cpu-baseline > $O/bulk.out 2>> $O/bench.err && last $O/bulk.out $O/r02_bench_bulk_tma.json
 python bench.py --impl reference --steps 3 --warmup 1 > $O/ref.out 2>> $O/bench.err && last $O/ref.out $O/r02_bench_reference.json

@@ -54,8 +54,8 @@ Round 1: 0.3144 ms/step, step roofline 0.205, dominant stage 0.28 with 450 MB of
 {table}
 
 Sum of `ls_*` kernels per step (ncu, serialised, cold caches): {tot:.1f} us.  In situ (CUPTI, graph replay, `r02_timeline.txt`): span
-246.1 us per step, idle 2.5 us; index 26.8, place 26.8, canon 21.0, splat 59.9, gather 69.6, softmax backward 17.0, camera 3.9,
-zero 3.8, scan 6.1; softmax 8.1 / NHWC staging 11.4 / 8.3 run on side streams.  Backward = gather + softmax backward = 86.6 us
+244.9 us per step, idle 2.3 us; index 26.7, place 26.9, canon 20.9, splat 58.8, gather 69.8, softmax backward 17.0, camera 3.9,
+zero 3.8, scan 6.2; softmax 8.1 / NHWC staging 11.7 / 8.4 run on side streams.  Backward = gather + softmax backward = 86.8 us
 (round 1: 137 us with the transposer).
 
 ## All bench lines of this build
@@ -66,6 +66,7 @@ zero 3.8, scan 6.1; softmax 8.1 / NHWC staging 11.4 / 8.3 run on side streams.  
 '''
 for f, desc in (("r02_bench_featcl.json", "+ channels-last features (LS_FEAT_NHWC: no staging copies)"),
                 ("r02_bench_bf16.json", "bf16 features / logits"),
+                ("r02_bench_bf16_bev.json", "bf16 features / logits + opt-in bf16 BEV and gradient (`--bev-dtype bf16`)"),
                 ("r02_bench_nchw.json", "NCHW BEV + gradient (the reference's strides; staged backward)"),
                 ("r02_bench_bulk_tma.json", "`LS_SPLAT_OUT=bulk`: one bulk (TMA) store per tile instead of direct rows"),
                 ("r02_bench_stress.json", "stress: B=32, 6 cams, D=96, 400x400 (configs[3]); round 1: 2.01 ms"),
@@ -122,7 +123,7 @@ lift-splat ops in the same stack {agr["stream"]["wall_ms"]["p50"]:.1f} / {agr["s
   registers, 640 B of shared memory).  The kernel sits at 63 % of the L1 data-pipe wavefront peak and 53 % issue-active; L2->SM
   9.4 TB/s.  It is NOT L2-read bound: square tiles that cut L2 reads in principle (3.6 records per pixel and tile instead of
   1.15) were 8-11 us slower, fewer or more rows in flight per quarter-warp did not help, packed FFMA2 was slower.
-* **The integer pipeline is now a third of the step** (zero 3.8 + index 26.8 + scan 6.1 + place 26.8 + canon 21.0 = 84.5 us):
+* **The integer pipeline is now a third of the step** (zero 3.8 + index 26.7 + scan 6.2 + place 26.9 + canon 20.9 = 84.5 us):
   the index kernel is ~150 exact float32 instructions per point with two IEEE divisions (the third, for z, is proven away),
   placement is bound by its scattered 8-byte stores, canon by k^2 key compares.  The opt-in static-rig cache replaces all five by
   two streaming refresh kernels (17.5 + 10.4 us under ncu): 0.195 ms per step.
