@@ -580,6 +580,7 @@ def main():
                          "(configs[4])")
     ap.add_argument("--train-batch", type=int, default=12, help="per-GPU batch of the training step (config/training.yaml:12)")
     ap.add_argument("--no-channels-last", action="store_true", help="train/agent: keep the conv stacks and the BEV NCHW")
+    ap.add_argument("--no-compat", action="store_true", help="skip the nchw_compat key of the default line")
     ap.add_argument("--no-train", action="store_true", help="skip the short `train` measurement appended to the default line")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--bev-format", default="channels_last", choices=["channels_last", "nchw"],
@@ -749,6 +750,31 @@ def main():
                           "weights refreshed; the headline `value` recomputes them every step"}
         del gc
     stages = st.stage_times(min(args.steps, 20)) if rank == 0 else None
+    # the same step with the reference's own NCHW strides for the BEV tensor and its gradient (transposing
+    # write-out, gradient staged as cell rows): the strict-layout compat path, reported next to `value`
+    compat = None
+    if rank == 0 and args.bev_format == "channels_last" and args.bev_dtype == "fp32" and not args.no_compat:
+        st2 = Stepper(shape, dtype, device, seed=rank, bev_format="nchw", feat_format=args.feat_format)
+        for _ in range(args.warmup):
+            st2.step()
+        g2 = st2.capture()
+        for _ in range(3):
+            g2.replay()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(args.steps):
+            g2.replay()
+        c1.record()
+        torch.cuda.synchronize()
+        ms_n = c0.elapsed_time(c1) / args.steps
+        close = float((st2.bev - st.bev).abs().max()) <= 1e-6 * float(st.bev.abs().max())
+        compat = {"ms_per_step": ms_n, "value": shape.batch / (ms_n * 1e-3), "unit": UNIT,
+                  "gradients_bit_identical": bool(torch.equal(st2.gfeat, st.gfeat) and torch.equal(st2.glogits, st.glogits)),
+                  "bev_equal_to_last_bit": close,
+                  "what": "BEV tensor and upstream gradient with the reference's NCHW strides (model/bev_model.py:76,105) "
+                          "instead of channels_last: same values, transposing write-out + staged gradient"}
+        del g2, st2
     graph_launches = st.graph_launches if use_graph else 0
     del st
     if use_graph:
@@ -808,6 +834,8 @@ def main():
                 "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": step_gbs / peak},
                 "stage_ms": stages, "clocks": clocks}
+        if compat is not None:
+            line["nchw_compat"] = compat
         if cached is not None:
             line["static_rig_cache"] = cached
         if train is not None:
