@@ -786,7 +786,7 @@ def main():
         # the timed region, on every rank (python bench.py --workload train runs it longer, on its own)
         from harness import run as hr
         try:
-            train = hr.train_benchmark(args.train_batch, 8, 3, rank, world, device, "b200", e2e_steps=4)
+            train = hr.train_benchmark(args.train_batch, 12, 3, rank, world, device, "b200", e2e_steps=4)
         except Exception as exc:          # never lose the hot-path line to the harness
             train = {"error": repr(exc)[:300]}
     unbind_cpus(all_cpus)
