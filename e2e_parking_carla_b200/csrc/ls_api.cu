@@ -141,6 +141,7 @@ struct LsWs {
   void* featT;
   int* seg_start;
   int2* pix_recs;
+  int* bwd_flags;      // per-image arrival / departure counters of the overlapped backward epilogue (zeroed by the forward, self-resetting)
   size_t scratch_bytes, saved_bytes;
 };
 static inline size_t ls_align(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -181,6 +182,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int feat_layout, int phase, vo
     w.seg_start = (int*)take((size_t)dm.B * g.seg_stride * 4);
     w.pix_recs = (int2*)take(pts * 8);
     if (feat_layout == LS_FEAT_NCHW) w.featT = take(feat);
+    w.bwd_flags = (int*)take((size_t)ls_bwd_flag_ints(dm) * 4);
   }
   w.saved_bytes = off;
   return w;
@@ -188,7 +190,7 @@ static LsWs ls_carve(const LsShape* s, int dtype, int feat_layout, int phase, vo
 
 // ---- static-rig cache (opt-in) ------------------------------------------------------------
 struct LsCache {
-  int *seg_start, *tile_order, *perm;
+  int *seg_start, *tile_order, *perm, *bwd_flags;
   int2 *recs_sorted, *pix_recs;
   size_t bytes;
 };
@@ -205,6 +207,7 @@ static LsCache ls_carve_cache(const LsShape* s, void* base) {
   c.perm = (int*)take(pts * 4);
   c.recs_sorted = (int2*)take((size_t)dm.B * ls_sorted_records_capacity(dm, g) * 8);
   c.pix_recs = (int2*)take(pts * 8);
+  c.bwd_flags = (int*)take((size_t)ls_bwd_flag_ints(dm) * 4);
   c.bytes = off;
   return c;
 }
@@ -367,10 +370,10 @@ int ls_splat_bwd(const float* grad_bev, const LsBevStrides* gst, const void* fea
     if (!gT_ws || !seg_start) return LS_ERR_BAD_ARG;
     if ((rc = ls_launch_bwd_transpose(grad_bev, *gst, seg_start, dm, g, gT_ws, (cudaStream_t)stream))) return rc;
     return ls_launch_bwd_gather(gT_ws, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, feat_nhwc, dtype,
-                                (const int2*)pix_recs, dm, g, grad_prob_pm, grad_feat_nhwc, (cudaStream_t)stream);
+                                (const int2*)pix_recs, dm, g, grad_prob_pm, grad_feat_nhwc, nullptr, (cudaStream_t)stream);
   }
   return ls_launch_bwd_gather(grad_bev, gst->b, gst->y, mode, feat_nhwc, dtype, (const int2*)pix_recs, dm, g,
-                              grad_prob_pm, grad_feat_nhwc, (cudaStream_t)stream);
+                              grad_prob_pm, grad_feat_nhwc, nullptr, (cudaStream_t)stream);
 }
 
 int ls_target_bev(const int32_t* target_pix, int32_t B, int32_t X, int32_t Y, float* out, int64_t stride_b,
@@ -419,7 +422,7 @@ int ls_forward(const void* feat, int feat_layout, const void* logits, int dtype,
       (rc = ls_launch_to_nhwc(feat, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, w.featT, fk.side(2))))
     return rc;
   // caller's stream: index -> scan, then (after softmax) placement, then (after staging) the splat
-  if ((rc = ls_launch_zero_counts(w.counts, dm, g, stream))) return rc;
+  if ((rc = ls_launch_zero_counts(w.counts, dm, g, w.bwd_flags, ls_bwd_flag_ints(dm), stream))) return rc;
   if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
   if ((rc = ls_launch_scan(w.counts, dm, g, w.seg_start, w.tile_order, w.tile_tot, stream))) return rc;
   if ((rc = fk.join(1))) return rc;
@@ -448,15 +451,21 @@ int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const v
   if (mode == LS_GRAD_BAD) return LS_ERR_UNSUPPORTED;
   const void* featT = feat_layout == LS_FEAT_NHWC ? feat : wf.featT;
   void* gfeatT = feat_layout == LS_FEAT_NHWC ? grad_feat : w.gfeatT;
+  // common shapes: the epilogue (softmax backward + grad_feat layout) is ONE pixel-stationary launch; with
+  // LS_OVERLAP_BWD=1 it overlaps the gather's tail, synchronised per image through the counters in the saved blob
+  int* ready = ls_gather_can_overlap(dm) ? wf.bwd_flags : nullptr;
   if (mode == LS_GRAD_STAGED) {
     if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, wf.seg_start, dm, g, w.gT, stream))) return rc;
     rc = ls_launch_bwd_gather(w.gT, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, featT, dtype, wf.pix_recs, dm, g,
-                              w.gprob_pm, gfeatT, stream);
+                              w.gprob_pm, gfeatT, ready, stream);
   } else {
     rc = ls_launch_bwd_gather(grad_bev, grad_strides->b, grad_strides->y, mode, featT, dtype, wf.pix_recs, dm, g,
-                              w.gprob_pm, gfeatT, stream);
+                              w.gprob_pm, gfeatT, ready, stream);
   }
   if (rc) return rc;
+  if (ready || ls_epilogue_supports(dm))
+    return ls_launch_bwd_epilogue(prob, w.gprob_pm, grad_prob_ext, feat_layout == LS_FEAT_NCHW ? w.gfeatT : nullptr, dtype,
+                                  dm, grad_logits, grad_feat, ready, ls_gather_ready_target(dm), stream);
   // the two layout fix-ups are independent: grad_feat on a side stream, grad_logits on the caller's
   LsFork fk(stream);
   if (feat_layout == LS_FEAT_NCHW &&
@@ -497,7 +506,7 @@ int ls_forward_cached(const void* feat, int feat_layout, const void* logits, int
     return rc;
   if (rebuild) {
     // the full index / sort / canonical-order pipeline, written into the cache instead of the scratch
-    if ((rc = ls_launch_zero_counts(w.counts, dm, g, stream))) return rc;
+    if ((rc = ls_launch_zero_counts(w.counts, dm, g, c.bwd_flags, ls_bwd_flag_ints(dm), stream))) return rc;
     if ((rc = ls_launch_index(M, t, frustum, dm, g, nullptr, w.cell, w.within, w.counts, stream))) return rc;
     if ((rc = ls_launch_scan(w.counts, dm, g, c.seg_start, c.tile_order, w.tile_tot, stream))) return rc;
     if ((rc = fk.join(1))) return rc;
@@ -508,7 +517,9 @@ int ls_forward_cached(const void* feat, int feat_layout, const void* logits, int
   }
   // cached: only the weights the records carry are new
   if ((rc = fk.join(1))) return rc;
-  if ((rc = ls_launch_refresh(prob, dtype, c.perm, c.seg_start, dm, g, c.recs_sorted, c.pix_recs, stream))) return rc;
+  if ((rc = ls_launch_refresh(prob, dtype, c.perm, c.seg_start, dm, g, c.recs_sorted, c.pix_recs, c.bwd_flags,
+                              ls_bwd_flag_ints(dm), stream)))
+    return rc;
   if ((rc = fk.join(2))) return rc;
   return ls_launch_splat_fwd(featT, dtype, nullptr, c.seg_start, c.tile_order, c.recs_sorted, nullptr, dm, g, bev,
                              *bev_strides, stream);
@@ -536,15 +547,19 @@ int ls_backward_cached(const float* grad_bev, const LsBevStrides* grad_strides, 
   if (mode == LS_GRAD_BAD) return LS_ERR_UNSUPPORTED;
   const void* featT = feat_layout == LS_FEAT_NHWC ? feat : wf.featT;
   void* gfeatT = feat_layout == LS_FEAT_NHWC ? grad_feat : w.gfeatT;
+  int* ready = ls_gather_can_overlap(dm) ? c.bwd_flags : nullptr;
   if (mode == LS_GRAD_STAGED) {
     if ((rc = ls_launch_bwd_transpose(grad_bev, *grad_strides, c.seg_start, dm, g, w.gT, stream))) return rc;
     rc = ls_launch_bwd_gather(w.gT, (long long)(g.XY + 1) * dm.Cp, dm.Cp, mode, featT, dtype, c.pix_recs, dm, g,
-                              w.gprob_pm, gfeatT, stream);
+                              w.gprob_pm, gfeatT, ready, stream);
   } else {
     rc = ls_launch_bwd_gather(grad_bev, grad_strides->b, grad_strides->y, mode, featT, dtype, c.pix_recs, dm, g,
-                              w.gprob_pm, gfeatT, stream);
+                              w.gprob_pm, gfeatT, ready, stream);
   }
   if (rc) return rc;
+  if (ready || ls_epilogue_supports(dm))
+    return ls_launch_bwd_epilogue(prob, w.gprob_pm, grad_prob_ext, feat_layout == LS_FEAT_NCHW ? w.gfeatT : nullptr, dtype,
+                                  dm, grad_logits, grad_feat, ready, ls_gather_ready_target(dm), stream);
   LsFork fk(stream);
   if (feat_layout == LS_FEAT_NCHW &&
       (rc = ls_launch_from_nhwc(w.gfeatT, dtype, dm.B * dm.N, dm.C, dm.Cp, dm.HW, grad_feat, fk.side(1))))

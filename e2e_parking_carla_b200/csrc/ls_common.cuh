@@ -34,6 +34,9 @@ static_assert(LS_TX == 1 && LS_TY == 128, "the tile kernels of the NCHW path ass
 #define LS_GATHER_MINB 2
 #endif
 #define LS_HALFWARPS (LS_GATHER_THREADS / 16)
+#ifndef LS_GATHER_REVERSE
+#define LS_GATHER_REVERSE 1          // the gradient gather (and its overlapped epilogue) walk the images last to first
+#endif
 #define LS_SEG_PAD 4                 // seg_start row stride = Vc + LS_SEG_PAD (16 B aligned rows)
 
 // Everything a kernel needs to know about the BEV grid, derived once on the host.

@@ -45,8 +45,11 @@ __device__ __forceinline__ void ls_gauss_jordan_cols(double (&col)[n], int base)
 __global__ void __launch_bounds__(32)
 ls_camera_transform_kernel(const float* __restrict__ intr, const float* __restrict__ extr, int BN,
                            float* __restrict__ M, float* __restrict__ t) {
-  ls_pdl_trigger();
   ls_pdl_wait();
+  // 64 warps of dependent fp64 arithmetic leave the GPU empty: once everything before this kernel is
+  // complete (the wait above), the next launch may start - ls_forward's first kernel zeroes the
+  // histogram without needing M, t and only joins this kernel's completion at its end
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x, lane = threadIdx.x;
   double e[4], k[3];
 #pragma unroll
@@ -181,17 +184,24 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
 
 // zero the per-cell histogram (B * Vc ints, a multiple of 128): one 16-byte store per thread and trip
 __global__ void __launch_bounds__(256)
-ls_zero_counts_kernel(int4* __restrict__ p, int n16) {
+ls_zero_counts_kernel(int4* __restrict__ p, int n16, int* __restrict__ extra, int n_extra) {
   ls_pdl_trigger();
-  ls_pdl_wait();
+  // The histogram is private scratch of this call and nothing written here is read by the predecessor,
+  // so the zeroing does not wait for it.  A predecessor lets this kernel start early only after ITS
+  // dependency wait (ls_camera_transform_kernel) or at its completion, i.e. when all earlier users of
+  // the scratch blob are done.  The dependency wait comes last: this grid completes after the
+  // predecessor, which keeps the stream order transitive for the kernels that wait on this one.
   const int4 z = make_int4(0, 0, 0, 0);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) p[i] = z;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_extra; i += gridDim.x * blockDim.x) extra[i] = 0;
+  ls_pdl_wait();
 }
 
-int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, cudaStream_t s) {
+int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, int* extra, int n_extra, cudaStream_t s) {
   const int n16 = (int)(((size_t)dm.B * g.Vc) / 4);      // Vc is a multiple of LS_TILE
   const int blocks = (n16 + 1023) / 1024;
-  LS_LAUNCH(ls_zero_counts_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, s, reinterpret_cast<int4*>(counts), n16);
+  LS_LAUNCH(ls_zero_counts_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, s, reinterpret_cast<int4*>(counts), n16,
+            extra, extra ? n_extra : 0);
   return LS_OK;
 }
 
@@ -417,45 +427,46 @@ ls_place_kernel(const int* __restrict__ cell, const int* __restrict__ within, co
   const int b = blockIdx.z, n = blockIdx.y, rc0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, dg = threadIdx.x >> 5;
   const int rc = rc0 + lane;
-  const int* seg = seg_start + (size_t)b * grid.seg_stride;
+  // block-uniform 64-bit bases; everything per thread is a 32-bit offset inside the camera / the sample
+  // (B*Npts < 2^31 is checked by the API), loads are unconditional on clamped addresses: no branch per load
+  const size_t cam0 = (size_t)b * dm.Npts + (size_t)n * dm.DHW;
+  const int* __restrict__ cellp = cell + cam0;
+  const int* __restrict__ withp = within + cam0;
+  const T* __restrict__ probp = prob + cam0;
+  const int* __restrict__ seg = seg_start + (size_t)b * grid.seg_stride;
+  int2* __restrict__ rb = recs + (size_t)b * dm.Npts;
   if (rc < dm.HW) {
-    const int pix = n * dm.HW + rc;
-    // K = ceil(D/8) depth bins per thread, unrolled: the three streams and the dependent
+    const int pixd = (n * dm.HW + rc) << dm.dbits;
+    // K = ceil(D/groups) depth bins per thread, unrolled: the three streams and the dependent
     // seg_start lookups of all bins are in flight together
     int c[K], tk[K], wb[K], sg[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int d = dg + LS_PLACE_GROUPS * k;
-      c[k] = -1; tk[k] = 0; wb[k] = 0;
-      if (d < dm.D) {
-        const size_t idx = (size_t)b * dm.Npts + (size_t)(n * dm.D + d) * dm.HW + rc;
-        c[k] = cell[idx];
-        tk[k] = within[idx];
-        wb[k] = __float_as_int(ls_to_float(prob[idx]));
-      }
+      const int off = (d < dm.D ? d : 0) * dm.HW + rc;
+      c[k] = cellp[off];
+      tk[k] = withp[off];
+      wb[k] = __float_as_int(ls_to_float(probp[off]));
+      if (d >= dm.D) c[k] = -1;
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) sg[k] = (c[k] >= 0) ? __ldg(seg + c[k]) : 0;
+    for (int k = 0; k < K; ++k) sg[k] = __ldg(seg + (c[k] >= 0 ? c[k] : 0));
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int d = dg + LS_PLACE_GROUPS * k;
-      if (d < dm.D) {
-        if (c[k] >= 0) {
-          const int key = ((c[k] & (LS_TILE - 1)) << 24) | (pix << dm.dbits) | d;
-          recs[(size_t)b * dm.Npts + sg[k] + tk[k]] = make_int2(key, wb[k]);
-        }
-        // row of the cell in rank order (gx*Y + gy: a row of a channels-last gradient, or of the
-        // staged cell-major copy of an NCHW one); X*Y for a dropped point
-        if (pix_recs) stage[lane * Dp + d] = make_int2(c[k] >= 0 ? ls_rank_of_cell_fast(c[k], grid) : grid.XY, wb[k]);
-      }
+      if (c[k] >= 0) rb[sg[k] + tk[k]] = make_int2(((c[k] & (LS_TILE - 1)) << 24) | pixd | d, wb[k]);
+      // row of the cell in rank order (gx*Y + gy: a row of a channels-last gradient, or of the
+      // staged cell-major copy of an NCHW one); X*Y for a dropped point
+      if (pix_recs && d < dm.D)
+        stage[lane * Dp + d] = make_int2(c[k] >= 0 ? ls_rank_of_cell_fast(c[k], grid) : grid.XY, wb[k]);
     }
   }
   if (!pix_recs) return;
   __syncthreads();
   const int valid = min(32, dm.HW - rc0);
-  int2* dst = pix_recs + ((size_t)(b * dm.N + n) * dm.HW + rc0) * dm.D;
+  int2* __restrict__ dst = pix_recs + ((size_t)(b * dm.N + n) * dm.HW + rc0) * dm.D;
   for (int r = dg; r < valid; r += LS_PLACE_GROUPS)
-    for (int d = lane; d < dm.D; d += 32) dst[(size_t)r * dm.D + d] = stage[r * Dp + d];
+    for (int d = lane; d < dm.D; d += 32) dst[r * dm.D + d] = stage[r * Dp + d];
 }
 
 template <typename T>

@@ -76,16 +76,14 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 #define LS_CANON_BUCKETS 1024 // by the top 10 of the 24 key bits (4 KB of shared memory: keeps the L1 share of the hot path)
 #define LS_CANON_BSHIFT 14
 
-__global__ void __launch_bounds__(LS_CANON_THREADS)
-ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
-                LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted, int* __restrict__ perm) {
-  ls_pdl_trigger();
-  ls_pdl_wait();
+// one tile of sample b by a whole CTA of LS_CANON_THREADS threads (CTA-uniform control flow)
+__device__ __forceinline__ void ls_canon_tile(int2* __restrict__ recs, const int* __restrict__ seg_start, int b, int tile_id,
+                                              const LsDims& dm, const LsGrid& grid, int2* __restrict__ recs_sorted,
+                                              int* __restrict__ perm) {
   __shared__ int seg[LS_TILE + 1];
   __shared__ int any_big;
-  const int b = blockIdx.x % dm.B;
-  const int tile_id = tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B];
   const int* segg = seg_start + (size_t)b * grid.seg_stride + (size_t)tile_id * LS_TILE;
+  __syncthreads();                       // (called in a loop: the previous tile's readers of seg / any_big are done)
   if (threadIdx.x == 0) any_big = 0;
   for (int i = threadIdx.x; i <= LS_TILE; i += LS_CANON_THREADS) seg[i] = segg[i];
   __syncthreads();
@@ -169,6 +167,15 @@ ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, cons
     for (int i = a + threadIdx.x; i < e; i += LS_CANON_THREADS) out[i] = __ldcg(&rin[i]);
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(LS_CANON_THREADS)
+ls_canon_kernel(int2* __restrict__ recs, const int* __restrict__ seg_start, const int* __restrict__ tile_order,
+                LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted, int* __restrict__ perm) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int b = blockIdx.x % dm.B;
+  ls_canon_tile(recs, seg_start, b, tile_order[(size_t)b * grid.tiles + blockIdx.x / dm.B], dm, grid, recs_sorted, perm);
 }
 
 // =====================================================================================
@@ -449,6 +456,9 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
 #ifndef LS_SPLATD_MINB
 #define LS_SPLATD_MINB 6
 #endif
+#ifndef LS_SPLAT_FASTLOOP
+#define LS_SPLAT_FASTLOOP 0   // unmasked record prefetch for full windows: 72 -> 80 registers, splat +3 us (measured); off
+#endif
 // 16 bytes of a row: one vector access when rows are 16-byte aligned (row pitch a multiple of 4
 // floats), four scalar ones otherwise (a 64-channel slice of a 65-channel tensor: 260-byte pitch)
 template <bool kVec> __device__ __forceinline__ void ls_row_store4(float* g, float4 v) {
@@ -556,6 +566,10 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   const char* f0 = reinterpret_cast<const char*>(fbase + (kHalf ? 8 : 4) * ql);
   const unsigned f1off = (unsigned)(32 * sizeof(T));
   TO* lane0 = tile0 + (kHalf ? 8 : 4) * ql;       // this lane's first quad of row 0
+  // strips: a finished cell's row address is ONE 32x32+64 multiply-add (cell * row pitch in bytes + base)
+  unsigned pitch_bytes = syu * (unsigned)sizeof(TO);
+  asm volatile("" : "+r"(pitch_bytes));
+  const char* lane0b = reinterpret_cast<const char*>(lane0);
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #if LS_FFMA2
   // the 8 channel sums of this lane live in four packed float32 pairs: 4 FFMA2 per record instead of 8 FFMA
@@ -588,7 +602,7 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     r[u] = p[u];
     if (idx + u >= end) r[u] = make_int2(0, 0);
   }
-#define LS_SPLATD_WINDOW(cur, nxt)                                                                   \
+#define LS_SPLATD_WINDOW(cur, nxt, MASKED)                                                           \
   {                                                                                                  \
     float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
     _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
@@ -601,14 +615,17 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     }                                                                                                \
     idx += LS_QWIN;                                                                                  \
     p += LS_QWIN;                                                                                    \
-    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) nxt[u] = (idx + u < end) ? p[u] : make_int2(0, 0); \
+    _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u)                                              \
+        nxt[u] = (!(MASKED) || idx + u < end) ? p[u] : make_int2(0, 0);                              \
     _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
       if (cur[u].x & LS_REC_VALID) {                                                                 \
         const float wt = __int_as_float(cur[u].y);                                                   \
         LS_ACC8(wt, fa[u], fb[u]);                                                                   \
       }                                                                                              \
       if (cur[u].x & LS_REC_LAST) {                                                                  \
-        TO* g = lane0 + row_off((unsigned)cur[u].x & 255u);                                          \
+        const unsigned cl__ = (unsigned)cur[u].x & 255u;                                             \
+        TO* g = kStrip ? reinterpret_cast<TO*>(const_cast<char*>(lane0b) + (unsigned long long)cl__ * pitch_bytes) \
+                       : lane0 + row_off(cl__);                                                      \
         LS_ACC_GET();                                                                                \
         ls_row_store4<kVec>(g, acc0);                                                                \
         ls_row_store4<kVec>(g + kSecond, acc1);                                                      \
@@ -616,10 +633,16 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
       }                                                                                              \
     }                                                                                                \
   }
+  // full windows first: while the window after the next still lies inside the piece, the record prefetch
+  // needs no bounds test (4 of ~27 instructions per record); the masked form finishes the piece
+  while (LS_SPLAT_FASTLOOP && idx + 3 * LS_QWIN <= end) {
+    LS_SPLATD_WINDOW(r, rn, 0);
+    LS_SPLATD_WINDOW(rn, r, 0);
+  }
   for (;;) {
-    LS_SPLATD_WINDOW(r, rn);
+    LS_SPLATD_WINDOW(r, rn, 1);
     if (idx >= end) break;
-    LS_SPLATD_WINDOW(rn, r);
+    LS_SPLATD_WINDOW(rn, r, 1);
     if (idx >= end) break;
   }
 #undef LS_SPLATD_WINDOW
@@ -706,6 +729,11 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
   if (out == LS_OUT_BAD) return LS_ERR_UNSUPPORTED;
   size_t smem = ls_tile_smem_bytes(dm);
   dim3 grid(g.tiles * dm.B);
+  // dense channels-last rows: direct row stores (no shared-memory tile, L1 kept for the feature
+  // rows) unless LS_SPLAT_OUT=bulk asks for the one-bulk-store-per-tile (TMA) variant
+  static const bool want_bulk = getenv("LS_SPLAT_OUT") && !strcmp(getenv("LS_SPLAT_OUT"), "bulk");
+  const bool direct = out == LS_OUT_NHWC_DIRECT_VEC || out == LS_OUT_NHWC_DIRECT_SCALAR ||
+                      (out == LS_OUT_NHWC_BULK && !(want_bulk && g.tx == 1));
   if (recs)
     LS_LAUNCH(ls_canon_kernel, grid, dim3(LS_CANON_THREADS), 0, s, const_cast<int2*>(recs), seg_start, tile_order, dm, g,
               recs_sorted, perm);
@@ -714,11 +742,6 @@ static int ls_splat_dispatch(const void* featT, const int2* recs, const int* seg
 #define LS_SPLAT(OUT, CC)                                                                                          \
   LS_LAUNCH((ls_splat_fwd_kernel<T, OUT, CC>), grid, block, smem, s, (const T*)featT, seg_start, tile_order, rs, dm, g, \
             bev, st)
-  // dense channels-last rows: direct row stores (no shared-memory tile, L1 kept for the feature
-  // rows) unless LS_SPLAT_OUT=bulk asks for the one-bulk-store-per-tile (TMA) variant
-  static const bool want_bulk = getenv("LS_SPLAT_OUT") && !strcmp(getenv("LS_SPLAT_OUT"), "bulk");
-  const bool direct = out == LS_OUT_NHWC_DIRECT_VEC || out == LS_OUT_NHWC_DIRECT_SCALAR ||
-                      (out == LS_OUT_NHWC_BULK && !(want_bulk && g.tx == 1));
   if (!direct && g.tx != 1) return LS_ERR_UNSUPPORTED;      // the tile kernels know 1 x 128 strips only
 #define LS_DIRECT(VEC, TOUT, PTR)                                                                                      \
   do {                                                                                                                 \
@@ -770,10 +793,12 @@ int ls_launch_splat_fwd(const void* featT, int dtype, const int2* recs, const in
 template <typename T>
 __global__ void __launch_bounds__(256)
 ls_refresh_records_kernel(const T* __restrict__ prob, const int* __restrict__ perm, const int* __restrict__ seg_start,
-                          LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted) {
+                          LsDims dm, LsGrid grid, int2* __restrict__ recs_sorted, int* __restrict__ zero_ints, int n_zero) {
   ls_pdl_trigger();
   ls_pdl_wait();
   const int b = blockIdx.y;
+  if (b == 0)      // the backward's per-image arrival counters start from zero
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_ints[i] = 0;
   const int kept = __ldg(seg_start + (size_t)b * grid.seg_stride + grid.Vc);
   const int* pm = perm + (size_t)b * dm.Npts;
   const T* pb = prob + (size_t)b * dm.Npts;
@@ -802,16 +827,18 @@ ls_refresh_pixel_index_kernel(const T* __restrict__ prob, LsDims dm, int2* __res
 }
 
 int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* seg_start, const LsDims& dm,
-                      const LsGrid& g, int2* recs_sorted, int2* pix_recs, cudaStream_t s) {
+                      const LsGrid& g, int2* recs_sorted, int2* pix_recs, int* zero_ints, int n_zero, cudaStream_t s) {
+  if (!zero_ints) n_zero = 0;
   dim3 ga((dm.Npts + 256 * 8 - 1) / (256 * 8), dm.B);
   dim3 gb((dm.HW + 31) / 32, dm.B * dm.N);
   const size_t smem = (size_t)32 * (dm.D | 1) * sizeof(int);
   if (dtype == LS_F32) {
-    LS_LAUNCH(ls_refresh_records_kernel<float>, ga, dim3(256), 0, s, (const float*)prob, perm, seg_start, dm, g, recs_sorted);
+    LS_LAUNCH(ls_refresh_records_kernel<float>, ga, dim3(256), 0, s, (const float*)prob, perm, seg_start, dm, g, recs_sorted,
+              zero_ints, n_zero);
     if (pix_recs) LS_LAUNCH(ls_refresh_pixel_index_kernel<float>, gb, dim3(256), smem, s, (const float*)prob, dm, pix_recs);
   } else {
     LS_LAUNCH(ls_refresh_records_kernel<__nv_bfloat16>, ga, dim3(256), 0, s, (const __nv_bfloat16*)prob, perm, seg_start,
-              dm, g, recs_sorted);
+              dm, g, recs_sorted, zero_ints, n_zero);
     if (pix_recs)
       LS_LAUNCH(ls_refresh_pixel_index_kernel<__nv_bfloat16>, gb, dim3(256), smem, s, (const __nv_bfloat16*)prob, dm, pix_recs);
   }
@@ -1095,12 +1122,18 @@ ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __res
 // records of a depth window are loaded one per lane (a single coalesced 128-byte load per
 // half-warp, prefetched a window ahead, broadcast with 16-wide shuffles) and the rows are
 // gathered eight at a time - under 86 registers, three CTAs (24 warps) per SM.
+// ready != NULL: the backward's epilogue (ls_bwd_epilogue_kernel: softmax backward + layout fix-up of
+// grad_feat) is the next launch in the stream and runs OVERLAPPED with this kernel's tail.  Every CTA
+// lets the dependent launch be scheduled as soon as it has passed its own dependency wait; the
+// epilogue's CTAs then take the SM slots this grid's last wave leaves free and wait, per image, on
+// ready[image]: each warp adds 1 (release) when its rows are written, fw * warps-per-CTA arrivals = image done.
 template <typename T, int MODE, typename TG>
 __global__ void __launch_bounds__(LS_GATHER_THREADS, LS_GOCC_MINB)
 ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* __restrict__ pix_recs,
-                         LsDims dm, float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+                         LsDims dm, float* __restrict__ gprob_pm, T* __restrict__ gfeatT, int* __restrict__ ready) {
   ls_pdl_trigger();
   ls_pdl_wait();
+  if (ready) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int b = bn / dm.N;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
@@ -1175,6 +1208,24 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 #endif
     if (on) ls_store4<T>(gfeatT + pix * dm.Cp + 4 * hl, gf);
   }
+  if (ready) {
+    // this warp's rows of image bn are written: one release-add per warp (the warp barrier orders the
+    // other lanes' stores before lane 0's release)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ready + bn) : "memory");
+  }
+}
+
+// arrivals that complete an image in ready[] (ls_bwd_gather_occ_kernel)
+int ls_gather_ready_target(const LsDims& dm) { return dm.fw * (LS_GATHER_THREADS / 32); }
+// Opt-in (LS_OVERLAP_BWD=1): measured on a B200 at the default sizes, the overlap hides ~10 us of the
+// epilogue but the gather's tail slows down by the same amount (its last wave is not idle capacity) -
+// 239.4 vs 239.9 us per step; off by default, kept with a test.
+bool ls_gather_can_overlap(const LsDims& dm) {
+  const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
+  static const bool on = getenv("LS_OVERLAP_BWD") != nullptr;
+  return on && LS_GATHER_OCC && dm.D % 16 == 0 && ls_epilogue_supports(dm) && nch == 1 && ls_pdl_enabled();
 }
 
 // How the backward reads a gradient with these strides (include/ls_b200.h LsBevStrides).
@@ -1196,18 +1247,19 @@ int ls_classify_grad_in(const float* p, const LsBevStrides& st, const LsDims& dm
 
 template <typename T, int MODE>
 static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2* pix_recs, const LsDims& dm,
-                              float* gprob_pm, void* gfeatT, cudaStream_t s) {
+                              float* gprob_pm, void* gfeatT, int* ready, cudaStream_t s) {
   const int nch = (dm.Cp + LS_CCHUNK - 1) / LS_CCHUNK;
   dim3 grid(dm.fw, dm.B * dm.N);
+  if (ready && !ls_gather_can_overlap(dm)) return LS_ERR_UNSUPPORTED;
   if (dm.bev_bf16) {
     if (MODE != LS_GRAD_DIRECT_VEC) return LS_ERR_UNSUPPORTED;
     LS_LAUNCH((ls_bwd_gather_occ_kernel<T, LS_GRAD_DIRECT_VEC, __nv_bfloat16>), grid, dim3(LS_GATHER_THREADS), 0, s, rows,
-              (const T*)featT, pix_recs, dm, gprob_pm, (T*)gfeatT);
+              (const T*)featT, pix_recs, dm, gprob_pm, (T*)gfeatT, ready);
     return LS_OK;
   }
   if (LS_GATHER_OCC && dm.D % 16 == 0 && nch == 1) {
     LS_LAUNCH((ls_bwd_gather_occ_kernel<T, MODE, float>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT,
-              pix_recs, dm, gprob_pm, (T*)gfeatT);
+              pix_recs, dm, gprob_pm, (T*)gfeatT, ready);
     return LS_OK;
   }
 #define LS_GATHER(NCH)                                                                                        \
@@ -1227,13 +1279,13 @@ static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2*
 // rows: staged (gT, mode LS_GRAD_STAGED) or the channels-last gradient itself (direct modes)
 int ls_launch_bwd_gather(const void* rows_base, long long sample_stride, long long row_stride, int mode,
                          const void* featT, int dtype, const int2* pix_recs, const LsDims& dm, const LsGrid& g,
-                         float* gprob_pm, void* gfeatT, cudaStream_t s) {
+                         float* gprob_pm, void* gfeatT, int* ready, cudaStream_t s) {
   LsRows rows;
   rows.base = rows_base;
   rows.sample_stride = sample_stride;
   rows.row_bytes = (unsigned)(row_stride * (dm.bev_bf16 && mode != LS_GRAD_STAGED ? 2 : 4));
   rows.nrows = (unsigned)g.XY;
-#define LS_GD(TT, MODE) return ls_gather_dispatch<TT, MODE>(rows, featT, pix_recs, dm, gprob_pm, gfeatT, s)
+#define LS_GD(TT, MODE) return ls_gather_dispatch<TT, MODE>(rows, featT, pix_recs, dm, gprob_pm, gfeatT, ready, s)
   if (dtype == LS_F32) {
     if (mode == LS_GRAD_STAGED) LS_GD(float, LS_GRAD_STAGED);
     if (mode == LS_GRAD_DIRECT_VEC) LS_GD(float, LS_GRAD_DIRECT_VEC);

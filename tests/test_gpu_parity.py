@@ -505,12 +505,18 @@ def test_plain_stream_order_matches(lib):
     digests = []
     # ... and LS_SPLAT_OUT=bulk: the shared-memory-tile splat that leaves as one bulk (TMA) store per tile
     # instead of the default direct row stores
-    for extra in ({}, {"LS_NO_PDL": "1", "LS_NO_SIDE_STREAMS": "1"}, {"LS_SPLAT_OUT": "bulk"}):
+    # ... LS_OVERLAP_BWD=1: the backward's epilogue launched as the gather's programmatic dependent, waiting per
+    # image on the gather's arrival counters instead of on the whole grid; LS_SOFTMAX_BWD_STAGED=1: the
+    # shared-memory-staged softmax backward instead of the thread-per-pixel one (same summation order)
+    for extra in ({}, {"LS_NO_PDL": "1", "LS_NO_SIDE_STREAMS": "1"}, {"LS_SPLAT_OUT": "bulk"}, {"LS_OVERLAP_BWD": "1"},
+                  {"LS_SOFTMAX_BWD_STAGED": "1"}):
         env = dict(os.environ, **extra)
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
     assert digests[0] == digests[1]
+    assert digests[0] == digests[3], "overlapped epilogue"
+    assert digests[0] == digests[4], "staged softmax backward / layout kernels"
     # the bulk (shared-memory tile) variant cuts its pieces inside cells: same gradients, BEV equal up to
     # the last bit - checked on values in test_bulk_store_variant_matches, here it only has to run
     assert len(digests[2]) > 10
@@ -726,6 +732,32 @@ def test_many_depth_bins_serial_softmax(lib, dtype):
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
     out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype)
     _check_all(out, _oracle_outputs(shape, c), tol, 1e-6 if dtype == torch.float32 else None)
+
+
+@pytest.mark.parametrize("d_bound, bins", [([0.5, 8.5, 0.25], 32), ([0.5, 16.5, 0.25], 64)])
+@pytest.mark.parametrize("feat_format", [torch.contiguous_format, torch.channels_last])
+def test_pixel_stationary_epilogue_depth_counts(lib, d_bound, bins, feat_format):
+    """The thread-per-pixel backward epilogue (softmax backward + NHWC->NCHW of grad_feat in one launch) has
+    instantiations for 32, 48 and 64 depth bins; 48 is what every default-shape test runs, this covers the other
+    two, for NCHW features (both parts) and channels-last features (softmax part only), with and without an
+    upstream gradient on prob."""
+    shape = LiftSplatShape(batch=2, cams=3, channels=64, d_bound=d_bound)
+    assert shape.depth_bins == bins
+    c = _oracle_case(shape, rig_seed=53, in_seed=23)
+    ref = _oracle_outputs(shape, c)
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], bev_format=torch.channels_last,
+               feat_format=feat_format)
+    _check_all(out, ref, FP32_TOL, 1e-6)
+    # no upstream gradient on prob (grad_prob_ext == NULL): the epilogue's gext branch is off
+    ls = _ls()
+    feat = c["feat"].to(DEV).contiguous(memory_format=feat_format).requires_grad_(True)
+    logits = c["logits"].to(DEV).requires_grad_(True)
+    bev, _ = ls.lift_splat(feat, logits, _dev(c["M"]), _dev(c["t"]), _dev(frustum_of(shape)), _grid_spec(shape),
+                           torch.channels_last)
+    bev.backward(c["gb"].to(DEV).contiguous(memory_format=torch.channels_last))
+    ref0 = _oracle_outputs(shape, dict(c, gp=torch.zeros_like(c["gp"])))
+    assert_close(logits.grad, ref0["grad_logits"], FP32_TOL, "grad_logits without upstream prob gradient")
+    assert_close(feat.grad, ref0["grad_feat"], FP32_TOL, "grad_feat without upstream prob gradient")
 
 
 def test_full_size_values_on_sampled_batch_indices(lib):
