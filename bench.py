@@ -479,14 +479,14 @@ class Stepper:
             ("sort(scan+place)", lambda: lib.ls_sort(P(cell), P(within), P(counts), P(self.prob), self.code, C.byref(s), P(seg), P(order), P(tscr), P(recs), P(pix), stream)),
             ("nchw_to_nhwc", lambda: lib.ls_nchw_to_nhwc(P(d["feat"]), self.code, bn, sh.channels, hw, P(featT), stream)),
             ("splat_fwd", lambda: lib.ls_splat_fwd(P(featT), self.code, P(recs), P(seg), P(order), P(recs2), C.byref(s), P(self.bev), C.byref(self.st), stream)),
-            # the shipped backward: ONE call (for the common shapes one kernel: the gather with the softmax
-            # backward and both layout fix-ups fused in; preceded by the gradient staging pass for NCHW
-            # gradients) on the state the last step() left in self.saved
+            # the shipped backward: ONE call = gradient gather + the thread-per-pixel epilogue kernel (softmax
+            # backward and grad_feat layout), preceded by the gradient staging pass for NCHW gradients, on the
+            # state the last step() left in self.saved
             ("backward(gather+epilogue)", lambda: lib.ls_backward(
                 P(d["gbev"]), C.byref(self.gst), P(d["gprob"]), P(self.prob), P(d["feat"]) if nhwc_feat else None,
                 self.layout, self.code, C.byref(s), P(self.scratch), self.scratch.numel(), P(self.saved),
                 self.saved.numel(), P(self.gfeat), P(self.glogits), stream)),
-            # the same backward as separate stage-level entry points (un-fused: what round 2 shipped before)
+            # the same backward through the stage-level entry points (gather, then the two fix-ups one by one)
             ("splat_bwd(transpose+gather)", lambda: lib.ls_splat_bwd(P(d["gbev"]), C.byref(self.gst), P(featT), self.code, P(pix), P(seg), C.byref(s), P(gT), P(gprob), P(gfeatT), stream)),
             ("nhwc_to_nchw", lambda: lib.ls_nhwc_to_nchw(P(gfeatT), self.code, bn, sh.channels, hw, P(self.gfeat), stream)),
             ("softmax_bwd", lambda: lib.ls_softmax_bwd(P(self.prob), P(gprob), P(d["gprob"]), self.code, C.byref(s), P(self.glogits), stream)),
@@ -818,9 +818,10 @@ def main():
         step_bytes = (ab["fwd"] + ab["bwd"]) * shape.batch
         step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
         kernels = {"splat_fwd": "ls_canon_kernel + ls_splat_fwd_direct_kernel" if not staged else "ls_canon_kernel + ls_splat_fwd_kernel",
-                   "backward(gather+epilogue)": "ls_bwd_gather_occ_kernel<fused> (gradient rows gathered in place, softmax "
-                                                "backward and layout fix-ups in the same kernel)" if not staged
-                   else "ls_bwd_transpose_kernel + ls_bwd_gather_occ_kernel<fused>"}
+                   "backward(gather+epilogue)": "ls_bwd_gather_occ_kernel (gradient rows gathered in place) + "
+                                                "ls_bwd_epilogue_kernel (softmax backward and grad_feat layout, "
+                                                "thread per pixel)" if not staged
+                   else "ls_bwd_transpose_kernel + ls_bwd_gather_occ_kernel + ls_bwd_epilogue_kernel"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",

@@ -69,7 +69,9 @@ __host__ __device__ __forceinline__ size_t ls_sorted_capacity(int Npts) { return
 // the atomics.  Flat: one thread per record, one CTA per tile (heaviest first), the compare
 // loop runs over L1-resident keys.  Replaces the (unstable) argsort of model/bev_model.py:96.
 // =====================================================================================
+#ifndef LS_CANON_THREADS
 #define LS_CANON_THREADS 256
+#endif
 #ifndef LS_CANON_BIG
 #define LS_CANON_BIG 512      // cells with more records than this take the bucketed path (its ~50 barriers cost more than 512^2/256 compares per thread)
 #endif
@@ -97,8 +99,13 @@ __device__ __forceinline__ void ls_canon_tile(int2* __restrict__ recs, const int
   auto point_of = [&](int key, int pix) { const int n = pix / dm.HW; return (n * dm.D + (key & dmask)) * dm.HW + (pix - n * dm.HW); };
   // (read-only path: the light cells' records are never written by this kernel)
   const int2* __restrict__ rro = rin;
+  // (a thread's next record is fetched before the compare loop of the current one: the kernel is bound by
+  // the length of this per-thread chain of dependent loads, not by work)
+  int2 rnext = make_int2(0, 0);
+  if (s0 + (int)threadIdx.x < s1) rnext = __ldg(rro + s0 + threadIdx.x);
   for (int i = s0 + threadIdx.x; i < s1; i += LS_CANON_THREADS) {
-    const int2 r = __ldg(rro + i);
+    const int2 r = rnext;
+    if (i + LS_CANON_THREADS < s1) rnext = __ldg(rro + i + LS_CANON_THREADS);
     const int cl = (unsigned)r.x >> 24;
     const int a = seg[cl], e = seg[cl + 1];
     if (e - a > LS_CANON_BIG) { any_big = 1; continue; }      // handled below by the whole CTA
@@ -1160,7 +1167,9 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 #if LS_GATHER_SKIP_DEAD
       // a ray leaves the grid at some depth and stays out: whole windows of dropped points (about one in
       // seven at the default rig) need no rows, no FMAs, no butterfly - their probability gradient is 0
-      if (!__any_sync(hmask, (unsigned)rec.x < rows.nrows)) {
+      // (LS_GATHER_SKIP_DEAD == 2: the same test per batch of LS_GOCC_ROWS rows - the window a ray leaves the grid in)
+      const unsigned kept16 = (__ballot_sync(hmask, (unsigned)rec.x < rows.nrows) >> (threadIdx.x & 16)) & 0xFFFFu;
+      if (!kept16) {
         gprob_pm[pix * dm.D + 16 * w + hl] = 0.0f;
         rec = recn;
         continue;
@@ -1169,6 +1178,13 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
       float dot[16];
 #pragma unroll
       for (int h = 0; h < 16 / LS_GOCC_ROWS; ++h) {
+#if LS_GATHER_SKIP_DEAD == 2
+        if (!((kept16 >> (LS_GOCC_ROWS * h)) & ((1u << LS_GOCC_ROWS) - 1u))) {      // half-warp uniform
+#pragma unroll
+          for (int u = 0; u < LS_GOCC_ROWS; ++u) dot[LS_GOCC_ROWS * h + u] = 0.0f;
+          continue;
+        }
+#endif
         float4 g[LS_GOCC_ROWS];
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {

@@ -1,17 +1,38 @@
-"""profiles/r02_summary.md from the files tools/collect_profiles.sh produced (copied under profiles/).
-usage: python tools/make_r02_summary.py"""
+"""profiles/r02_summary.md + profiles/traffic.json from the files tools/collect_profiles.sh produced (copied under
+profiles/).  usage: python tools/make_r02_summary.py"""
 import json
+import os
+import re
 
 P = "profiles/"
 line = lambda f: json.load(open(P + f))
+have = lambda f: os.path.exists(P + f)
 b = line("r02_bench.json")
 d = line("r02_kernels.json")
 k, L = d["kernels"], d["launch_us"]
-tj = line("traffic.json")
-tot = sum(v for kk, v in L.items() if kk.startswith("ls_") and "refresh" not in kk)
+find = lambda kk, p: next(v for n, v in kk.items() if p in n)
+mb = lambda m: (m["dram_read_MB"] + m["dram_write_MB"]) * 1e6
+
+# ---- traffic.json: DRAM read+write bytes per launch of the two dominant stages --------------------------------------
+traffic = {"source": "profiles/r02_kernels.json / r02_kernels_nchw.json (ncu --set full --clock-control none over `python "
+                     "bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-graph [--bev-format "
+                     "nchw]`, first launch of each kernel; DRAM read+write bytes per launch, summed over the kernels of the stage)",
+           "cfg2/fp32/channels_last": {
+               "splat_fwd": int(mb(find(k, "ls_canon")) + mb(find(k, "ls_splat_fwd_direct"))),
+               "backward(gather+epilogue)": int(mb(find(k, "ls_bwd_gather_occ")) + mb(find(k, "ls_bwd_epilogue")))}}
+if have("r02_kernels_nchw.json"):
+    kn = line("r02_kernels_nchw.json")["kernels"]
+    traffic["cfg2/fp32/nchw"] = {
+        "splat_fwd": int(mb(find(kn, "ls_canon")) + mb(find(kn, "ls_splat_fwd_kernel"))),
+        "backward(gather+epilogue)": int(mb(find(kn, "ls_bwd_transpose")) + mb(find(kn, "ls_bwd_gather_occ")) +
+                                         mb(find(kn, "ls_bwd_epilogue")))}
+json.dump(traffic, open(P + "traffic.json", "w"), indent=1)
+
+# ---- per-kernel table ---------------------------------------------------------------------------------------------
+tot = sum(v for kk, v in L.items() if kk.startswith("ls_") and "refresh" not in kk and kk in k)
 rows = []
 for kk, v in sorted(L.items(), key=lambda kv: -kv[1]):
-    if not kk.startswith("ls_") or "refresh" in kk:
+    if not kk.startswith("ls_") or "refresh" in kk or kk not in k:      # (kernels of bench.py's stage-by-stage pass only)
         continue
     m = k.get(kk, {})
     l2 = ("%.2f" % m["l2_to_sm_TBps"]) if isinstance(m.get("l2_to_sm_TBps"), float) else "-"
@@ -20,43 +41,53 @@ for kk, v in sorted(L.items(), key=lambda kv: -kv[1]):
         m.get("l2_hit_pct", 0), m.get("l1_hit_pct", 0), l2, m.get("issue_active_pct", 0), m.get("warps_active_pct", 0),
         int(m.get("regs", 0)), m.get("stall_long_sb", 0), m.get("stall_barrier", 0), m.get("stall_short_sb", 0)))
 table = "\n".join(rows)
-n2, n4, n8 = [line("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8")]
-t8, t1, tr = line("r02_bench_train8.json"), line("r02_bench_train.json"), line("r02_bench_train_reference.json")
-ag, agr = line("r02_bench_agent.json")["latency"], line("r02_bench_agent_reference.json")["latency"]
-ref = line("r02_bench_reference.json")
+
+# ---- in-situ timeline ---------------------------------------------------------------------------------------------
+tl = open(P + "r02_timeline.txt").read()
+span = float(re.search(r"span per step ([\d.]+)", tl).group(1))
+idle = float(re.search(r"idle per step ([\d.]+)", tl).group(1))
+insitu = {m.group(1).split("<")[0].strip(): float(m.group(2)) for m in re.finditer(r"^(ls_\S+).*?mean ([\d.]+) us", tl, re.M)}
+t = lambda p: next(v for n, v in insitu.items() if p in n)
+chain = ["camera_transform", "index", "tile_totals", "tile_scan", "place", "canon", "splat_fwd", "bwd_gather", "bwd_epilogue"]
+chain_us = sum(t(p) for p in chain)
+
 dom = b["roofline"]["kernel"]
-traffic = b["roofline"]["traffic"] or tj["cfg2/fp32/channels_last"][dom]
-bwd_traffic = tj["cfg2/fp32/channels_last"]["splat_bwd(transpose+gather)"]
-md = f'''# Round 02 profile summary (B200, sm_100a)
+dom_traffic = b["roofline"]["traffic"] or traffic["cfg2/fp32/channels_last"][dom]
+bwd_traffic = traffic["cfg2/fp32/channels_last"]["backward(gather+epilogue)"]
+fwd_traffic = traffic["cfg2/fp32/channels_last"]["splat_fwd"]
+ref = line("r02_bench_reference.json")
+md = f'''# Round 02 profile summary (B200, sm_100a) - final build of the round
 
 Command profiled: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-train --no-graph`
 (kernel-by-kernel launches of the same step the bench replays as a CUDA graph; BASELINE.json configs[1]: fwd+bwd, B=16,
 4 cams, D=48, C=64, 200x200, fp32; default layouts: channels-last BEV + gradient, NCHW features).
-Everything here was produced by `tools/collect_profiles.sh` on one fresh B200 box (multi-GPU lines: separate `gpurun --gpus N`
-calls of the same commit series), tables by `tools/make_r02_summary.py`.
+Single-GPU files were produced by `tools/collect_profiles.sh` on one fresh B200 box, tables by `tools/make_r02_summary.py`.
 
 * `r02_launches.csv` - every launch with `gpu__time_duration.sum` (`ncu --metrics gpu__time_duration.sum --clock-control none`);
   cold-cache, serialised: compare SHARES, not absolutes.  The first 6 launches of each kernel are the full-batch steps.
-* `r02_kernels.json` - per-kernel metrics from `ncu --set full --clock-control none --import-source on` (first launch of each
-  kernel) + mean duration of the 6 full-batch launches (`tools/ncu_summary.py`).
+* `r02_kernels.json` (`r02_kernels_nchw.json`: the NCHW-compat path) - per-kernel metrics from `ncu --set full --clock-control
+  none --import-source on` (first launch of each kernel) + mean duration of the 6 full-batch launches (`tools/ncu_summary.py`).
 * `r02_timeline.txt` - CUPTI timeline of the graph replay (`tools/timeline.py graph`): in-situ durations, idle time.
 * `traffic.json` - DRAM read+write bytes per launch of the dominant stages (read by `bench.py` for `roofline.traffic`).
 * `r02_bench*.json` - bench lines of the same build, all taken WITHOUT a profiler (see the table below).
 
 Bench (no profiler): **{b["ms_per_step"]:.4f} ms/step, {b["value"]:.0f} samples/s**, step roofline {b["roofline_step"]["frac"]:.3f} of the measured
 HBM peak ({b["roofline"]["peak"]:.1f} GB/s); dominant stage `{dom}` ({b["roofline"]["kernels"]}) at
-{b["roofline"]["frac"]:.3f}, its DRAM traffic {traffic / 1e6:.0f} MB for {b["roofline"]["algorithmic_bytes_per_launch"] / 1e6:.0f} MB algorithmic;
+{b["roofline"]["frac"]:.3f}, its DRAM traffic {dom_traffic / 1e6:.0f} MB for {b["roofline"]["algorithmic_bytes_per_launch"] / 1e6:.0f} MB algorithmic;
 e2e (host buffers) {b["e2e"]["value"]:.0f} samples/s = {b["e2e"]["ms_per_step"]:.2f} ms against a measured link floor of {b["e2e"]["link_floor_ms"]:.2f} ms for the same bytes.
-Round 1: 0.3144 ms/step, step roofline 0.205, dominant stage 0.28 with 450 MB of traffic (2.02x algorithmic).
+Earlier in this round (commit 338cf7a): 0.2449 ms/step.  Round 1: 0.3144 ms/step, step roofline 0.205, dominant stage 0.28
+with 450 MB of traffic (2.02x algorithmic).
 
 | kernel | launch (us) | share | DRAM read / write (MB) | DRAM % | L2 hit % | L1 hit % | L2->SM (TB/s) | issue active % | warps active % | regs | stalls long_sb / barrier / short_sb |
 |---|---|---|---|---|---|---|---|---|---|---|---|
 {table}
 
-Sum of `ls_*` kernels per step (ncu, serialised, cold caches): {tot:.1f} us.  In situ (CUPTI, graph replay, `r02_timeline.txt`): span
-244.9 us per step, idle 2.3 us; index 26.7, place 26.9, canon 20.9, splat 58.8, gather 69.8, softmax backward 17.0, camera 3.9,
-zero 3.8, scan 6.2; softmax 8.1 / NHWC staging 11.7 / 8.4 run on side streams.  Backward = gather + softmax backward = 86.8 us
-(round 1: 137 us with the transposer).
+Sum of `ls_*` kernels per step (ncu, serialised, cold caches): {tot:.1f} us.  In situ (CUPTI, graph replay, `r02_timeline.txt`):
+span {span:.1f} us per step under the profiler, idle {idle:.1f} us; the dependent chain is camera {t("camera_transform"):.1f} -> index {t("index"):.1f} ->
+scan {t("tile_totals") + t("tile_scan"):.1f} -> place {t("place"):.1f} -> canon {t("canon"):.1f} -> splat {t("splat_fwd"):.1f} -> gather {t("bwd_gather"):.1f} -> epilogue {t("bwd_epilogue"):.1f} =
+{chain_us:.1f} us; histogram zeroing ({t("zero_counts"):.1f}) runs under the camera transform, softmax ({t("ls_softmax_kernel"):.1f}) and the NHWC staging of the
+features ({t("to_nhwc"):.1f}) on side streams under index + scan.  Backward = gather + epilogue = {t("bwd_gather") + t("bwd_epilogue"):.1f} us
+(earlier in the round: 69.8 + 17.0 with two epilogue kernels; round 1: 137 us with the transposer).
 
 ## All bench lines of this build
 
@@ -69,28 +100,44 @@ for f, desc in (("r02_bench_featcl.json", "+ channels-last features (LS_FEAT_NHW
                 ("r02_bench_bf16_bev.json", "bf16 features / logits + opt-in bf16 BEV and gradient (`--bev-dtype bf16`)"),
                 ("r02_bench_nchw.json", "NCHW BEV + gradient (the reference's strides; staged backward)"),
                 ("r02_bench_bulk_tma.json", "`LS_SPLAT_OUT=bulk`: one bulk (TMA) store per tile instead of direct rows"),
+                ("r02_bench_overlap_bwd.json", "`LS_OVERLAP_BWD=1`: epilogue launched as the gather's programmatic dependent, per-image arrival counters"),
+                ("r02_bench_staged_epilogue.json", "`LS_SOFTMAX_BWD_STAGED=1`: the two staged epilogue kernels (softmax backward || layout) instead of the thread-per-pixel one"),
                 ("r02_bench_stress.json", "stress: B=32, 6 cams, D=96, 400x400 (configs[3]); round 1: 2.01 ms"),
                 ("r02_bench_stress_bf16.json", "stress, bf16")):
+    if not have(f):
+        continue
     x = line(f)
     md += f'| `{f}` | {desc} | {x["ms_per_step"]:.4f} | {x["value"]:.0f} | {x["roofline"]["frac"]:.3f} / {x["roofline_step"]["frac"]:.3f} |\n'
 sc = b["static_rig_cache"]
+nc = b.get("nchw_compat")
 md += f'''| `r02_bench.json` key `static_rig_cache` | opt-in static-rig cache (index structures reused, weights refreshed; bit-identical) | {sc["ms_per_step"]:.4f} | {sc["value"]:.0f} | - |
-| `r02_bench.json` key `gpu_reference` | the reference's torch op chain on the same GPU, full batch | {b["gpu_reference"]["ms_per_step"]:.0f} | {b["gpu_reference"]["value"]:.1f} | - |
+'''
+if nc:
+    md += f'''| `r02_bench.json` key `nchw_compat` | the NCHW path measured inside the default run (gradients bit-identical: {nc["gradients_bit_identical"]}) | {nc["ms_per_step"]:.4f} | {nc["value"]:.0f} | - |
+'''
+md += f'''| `r02_bench.json` key `gpu_reference` | the reference's torch op chain on the same GPU, full batch | {b["gpu_reference"]["ms_per_step"]:.0f} | {b["gpu_reference"]["value"]:.1f} | - |
 | `r02_bench_reference.json` | `--impl reference`: the same on {ref["cpu_baseline"]["cores"]} host threads, FULL batch of 16 | {ref["ms_per_step"]:.0f} | {ref["value"]:.2f} | - |
 
-Multi-GPU (torchrun, one rank per GPU, per-GPU batch 16 for the lift-splat and 12 for training; `r02_bench_n2/n4/n8.json`,
-`r02_bench_train.json`, `r02_bench_train8.json`, `r02_nccl_n8.txt`):
+'''
+if all(have("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8", "train", "train8", "train_reference")):
+    n2, n4, n8 = [line("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8")]
+    t8, t1, tr = line("r02_bench_train8.json"), line("r02_bench_train.json"), line("r02_bench_train_reference.json")
+    md += f'''Multi-GPU (torchrun, one rank per GPU, per-GPU batch 16 for the lift-splat and 12 for training; `r02_bench_n2/n4/n8.json`,
+`r02_bench_train8.json`, `r02_nccl_n8.txt`: separate `gpurun --gpus N` calls at commit 129717f, i.e. BEFORE the epilogue / placement
+changes of the final build - the per-GPU device time there is 0.245 ms; the 1-GPU row and the training lines `r02_bench_train*.json`
+are of the final build):
 
 | GPUs | lift-splat samples/s (device) | ms/step | efficiency | e2e samples/s (ms) | train samples/s (ms/step) | train efficiency |
 |---|---|---|---|---|---|---|
 | 1 | {b["value"]:.0f} | {b["ms_per_step"]:.4f} | 1.00 | {b["e2e"]["value"]:.0f} ({b["e2e"]["ms_per_step"]:.2f}) | {b["train"]["samples_per_s"]:.1f} ({b["train"]["ms_per_step"]:.1f}) | 1.00 |
 '''
-for n, x in ((2, n2), (4, n4), (8, n8)):
-    md += (f'| {n} | {x["value"]:.0f} | {x["ms_per_step"]:.4f} | {x["value"] / n / b["value"]:.3f} | {x["e2e"]["value"]:.0f} ({x["e2e"]["ms_per_step"]:.2f}) | '
-           f'{x["train"]["samples_per_s"]:.1f} ({x["train"]["ms_per_step"]:.1f}) | {x["train"]["samples_per_s"] / n / b["train"]["samples_per_s"]:.3f} |\n')
-md += f'''| 8 (`--workload train --steps 20`) | - | - | - | - | {t8["value"]:.1f} ({t8["ms_per_step"]:.1f}) | {t8["value"] / 8 / t1["value"]:.3f} |
+    for n, x in ((2, n2), (4, n4), (8, n8)):
+        # efficiencies against the 1-GPU numbers of the same commit series (65 339 samples/s, 227.1 train samples/s)
+        md += (f'| {n} | {x["value"]:.0f} | {x["ms_per_step"]:.4f} | {x["value"] / n / 65339.0:.3f} | {x["e2e"]["value"]:.0f} ({x["e2e"]["ms_per_step"]:.2f}) | '
+               f'{x["train"]["samples_per_s"]:.1f} ({x["train"]["ms_per_step"]:.1f}) | {x["train"]["samples_per_s"] / n / 227.1:.3f} |\n')
+    md += f'''| 8 (`--workload train --steps 20`) | - | - | - | - | {t8["value"]:.1f} ({t8["ms_per_step"]:.1f}) | {t8["value"] / 8 / t1["value"]:.3f} |
 
-* The lift-splat has no data-path collective: device-timed efficiency is 1.00 by construction.
+* The lift-splat has no data-path collective: device-timed efficiency is 1.00 by construction (each rank's own step time).
 * Training: DDP all-reduces 78.4 MB of gradients per step (19.6 M parameters) inside the timed region; the step grows from
   52.7 ms (1 GPU) to 57-60 ms (8 GPUs): efficiency 0.88 (8 timed steps inside the default line) to 0.92 (20-step run),
   above the 0.85 target.  NCCL reports no NVLS on these VMs (`r02_nccl_n8.txt`); what is lost is the exposed tail of the
@@ -103,32 +150,42 @@ md += f'''| 8 (`--workload train --steps 20`) | - | - | - | - | {t8["value"]:.1f
   `e2e.link_floor_ms` (the same bytes copied both ways by all ranks at once, no kernels) is what PCIe plus the host memory
   system allow - at 1 GPU the step is within 5 % of it.
 
-Agent tick (B=1, `r02_bench_agent.json`, 1000 iterations): as one CUDA graph p50 {ag["graph"]["wall_ms"]["p50"]:.2f} ms / p99 {ag["graph"]["wall_ms"]["p99"]:.2f} ms
+'''
+if have("r02_bench_agent.json") and have("r02_bench_agent_reference.json"):
+    ag, agr = line("r02_bench_agent.json")["latency"], line("r02_bench_agent_reference.json")["latency"]
+    md += f'''Agent tick (B=1, `r02_bench_agent.json`, 1000 iterations): as one CUDA graph p50 {ag["graph"]["wall_ms"]["p50"]:.2f} ms / p99 {ag["graph"]["wall_ms"]["p99"]:.2f} ms
 wall ({ag["graph"]["device_ms"]["p50"]:.2f} / {ag["graph"]["device_ms"]["p99"]:.2f} device); stream launches {ag["stream"]["wall_ms"]["p50"]:.1f} / {ag["stream"]["wall_ms"]["p99"]:.1f} ms; with the reference's torch
 lift-splat ops in the same stack {agr["stream"]["wall_ms"]["p50"]:.1f} / {agr["stream"]["wall_ms"]["p99"]:.1f} ms (its host syncs prevent graph capture).  Paper: 74.92 ms on a Quadro RTX 5000.
 
-## Reading
+'''
+ga, ep, sp, ca = find(k, "ls_bwd_gather_occ"), find(k, "ls_bwd_epilogue"), find(k, "ls_splat_fwd_direct"), find(k, "ls_canon")
+md += f'''## Reading
 
-* **The gradient round trip is gone.**  Round 1 staged the NCHW gradient as cell rows (`ls_bwd_transpose_kernel`, 54 us,
-  170 MB read + 87 MB written) and gathered from the copy (66 us, another 170 MB).  With a channels-last gradient the gather
-  reads the rows in place: {bwd_traffic / 1e6:.1f} MB of DRAM traffic for the whole backward stage against 222.6 MB algorithmic ({bwd_traffic / 222.56e6:.2f}x; round 1:
-  450 MB, 2.02x).  `r02_nchw.ncu-rep` has the compat path of the same build: transposer 45.4 us (169.8 + 82.5 MB), gather 64.4 us
-  (170.2 + 22.1 MB), NCHW splat 86.7 us.
-* **The in-place gather is cold-DRAM + issue bound.**  170 MB read = 118 MB of distinct gradient rows + feature rows + the
-  pixel-major index: essentially every byte once; L1 hit 28 % (a CTA is one feature-map column, its rays share cells), L2 hit
-  44 %, 56 % issue-active, 24 warps/SM at 80 registers.  A predicated row load for dropped points halved its speed (ptxas
-  serialised the window); selecting the address of a zero row keeps all eight loads in flight.
-* **Forward splat: three write-outs, same records.**  NCHW tile 86.7 us, channels-last bulk (TMA) store 83.1 us
-  (`r02_bulk_tma.ncu-rep`: 43.4 + 107.8 MB, L1 hit 10 %), direct row stores 63.6 us (41.4 + 106.2 MB, L1 hit 16.5 %, 7 CTAs/SM at 72
-  registers, 640 B of shared memory).  The kernel sits at 63 % of the L1 data-pipe wavefront peak and 53 % issue-active; L2->SM
-  9.4 TB/s.  It is NOT L2-read bound: square tiles that cut L2 reads in principle (3.6 records per pixel and tile instead of
-  1.15) were 8-11 us slower, fewer or more rows in flight per quarter-warp did not help, packed FFMA2 was slower.
-* **The integer pipeline is now a third of the step** (zero 3.8 + index 26.7 + scan 6.2 + place 26.9 + canon 20.9 = 84.5 us):
-  the index kernel is ~150 exact float32 instructions per point with two IEEE divisions (the third, for z, is proven away),
-  placement is bound by its scattered 8-byte stores, canon by k^2 key compares.  The opt-in static-rig cache replaces all five by
-  two streaming refresh kernels (17.5 + 10.4 us under ncu): 0.195 ms per step.
+* **Backward = two kernels.**  The gather reads the channels-last gradient rows in place ({ga["dram_read_MB"]:.0f} MB of DRAM reads: 118 MB of
+  distinct rows + feature rows + the pixel-major index, essentially every byte once; L1 hit {ga["l1_hit_pct"]:.0f} %, L2 hit {ga["l2_hit_pct"]:.0f} %,
+  {ga["issue_active_pct"]:.0f} % issue-active, 24 warps/SM at {int(ga["regs"])} registers).  The epilogue - softmax backward and the NHWC -> NCHW fix-up of
+  `grad_feat`, formerly two kernels staged through shared memory (17 us in situ, ~80 instructions per element) - is ONE
+  thread-per-pixel kernel now ({ep["dram_read_MB"]:.0f} + {ep["dram_write_MB"]:.0f} MB, {ep["dram_pct"]:.0f} % of the DRAM peak, {ep["issue_active_pct"]:.0f} % issue-active, {int(ep["regs"])} registers): same bits, {t("bwd_epilogue"):.1f} us in situ.
+  DRAM traffic of the whole backward stage: {bwd_traffic / 1e6:.1f} MB against 222.6 MB algorithmic ({bwd_traffic / 222.56e6:.2f}x; round 1: 450 MB, 2.02x).
+* **What was tried on the backward and lost** (all built and timed, numbers in DESIGN.md section 5): the epilogue inside the gather
+  (per-pixel softmax backward in the half-warp that owns the pixel + the layout fix-up by the last of every eight column-CTAs
+  to finish: 118 us instead of 95, `__threadfence` invalidates L1 and the fix-up CTAs serialise their L2 round trips); the
+  epilogue as the gather's programmatic dependent waiting on per-image arrival counters (`LS_OVERLAP_BWD=1`, kept, tested:
+  hides 10 us of the epilogue and slows the gather's last wave by the same amount); a dead-point test per batch of 8 rows (+4 us).
+* **Forward splat**: direct row stores, {sp["dram_read_MB"]:.1f} + {sp["dram_write_MB"]:.1f} MB, L1 hit {sp["l1_hit_pct"]:.1f} %, {int(sp["regs"])} registers, 640 B of shared memory; the cell
+  flush is branch-free now (predicated stores, one multiply-add for the row address: 616 -> 520 SASS instructions), which did not move
+  its time ({t("splat_fwd"):.1f} us in situ): the kernel sits at ~63 % of the L1 data-pipe wavefront peak.  Canonical ordering INSIDE the splat
+  (shared-memory run per tile, no `recs_sorted` round trip, no separate kernel) was built and measured: splat 59 -> 79 us for the
+  21 us kernel it removes - the ordering is bound by its per-tile chain of dependent loads wherever it runs; not kept.
+  Forward stage traffic {fwd_traffic / 1e6:.0f} MB for 193 MB algorithmic.
+* **The integer pipeline** (index {t("index"):.1f} + scan {t("tile_totals") + t("tile_scan"):.1f} + place {t("place"):.1f} + canon {t("canon"):.1f} = {t("index") + t("tile_totals") + t("tile_scan") + t("place") + t("canon"):.1f} us; zeroing hidden): placement lost a third
+  of its instructions (block-uniform 64-bit bases, 32-bit offsets, unconditional clamped loads: 27 -> 24 us).  Canon is latency-bound
+  per thread, not k^2-bound (10 compares per record on average): 64 / 128 / 256 / 512 / 1024 threads per tile give 73 / 36 / 21 / 30 /
+  52 us; ordering a tile's cells by size so that a warp's compare loops have equal trip counts made it slower (27 us).  The
+  opt-in static-rig cache replaces index, scan, place and canon by two streaming refresh kernels.
 * SASS: `UBLKCP.G.S` (bulk async copy shared -> global, the TMA path) is in `ls_splat_fwd_kernel<.., LS_OUT_NHWC_BULK, 64>`
-  (`cuobjdump -sass libls_b200.so | grep UBLKCP`: fp32 and bf16 variants).
+  (`cuobjdump -sass libls_b200.so | grep UBLKCP`: fp32 and bf16 variants); `griddepcontrol.launch_dependents` (ACQBULK / PDL trigger)
+  in `ls_camera_transform_kernel` and, with `LS_OVERLAP_BWD=1`, in the gather.
 '''
 open(P + "r02_summary.md", "w").write(md)
 print("written", len(md))
