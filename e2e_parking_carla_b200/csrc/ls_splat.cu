@@ -1265,6 +1265,7 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
   }
 }
 
+
 // arrivals that complete an image in ready[] (ls_bwd_gather_occ_kernel)
 int ls_gather_ready_target(const LsDims& dm) { return dm.fw * (LS_GATHER_THREADS / 32); }
 // Opt-in (LS_OVERLAP_BWD=1): measured on a B200 at the default sizes, the overlap hides ~10 us of the
