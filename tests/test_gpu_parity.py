@@ -760,6 +760,19 @@ def test_pixel_stationary_epilogue_depth_counts(lib, d_bound, bins, feat_format)
     assert_close(feat.grad, ref0["grad_feat"], FP32_TOL, "grad_feat without upstream prob gradient")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pixel_stationary_epilogue_ragged_feature_map(lib, dtype):
+    """D = 48 (the thread-per-pixel epilogue) on a 25 x 33 feature map - 825 pixels per image, neither a multiple of the
+    epilogue's 128-thread CTAs nor of a warp - with 6 channels padded to 8 (the layout part drops the padding)."""
+    shape = LiftSplatShape(batch=2, cams=3, channels=6, final_dim=[200, 264])
+    assert (shape.fh, shape.fw, shape.depth_bins) == (25, 33, 48)
+    c = _oracle_case(shape, rig_seed=59, in_seed=29)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    out = _run(shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"], dtype=dtype,
+               bev_format=torch.channels_last)
+    _check_all(out, _oracle_outputs(shape, c, dtype), tol, 1e-6 if dtype == torch.float32 else None)
+
+
 def test_full_size_values_on_sampled_batch_indices(lib):
     """BASELINE.json configs[1] at its full size (B=16, C=64): the BEV features and gradients of
     three batch indices against the oracle's values (the rest of the batch is covered by the
