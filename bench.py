@@ -627,7 +627,8 @@ def main():
     config = {"workload": wl_name, "per_gpu_batch": shape.batch, "global_batch": shape.batch * world,
               "rig": "CARLA 4-camera rig with per-sample jitter (SURVEY.md 8d rig B)",
               "parallelism": "dp%d (per-sample path, no collective)" % world,
-              "l2": "no flush: one step streams ~0.6 GB (BEV + grad BEV + cell-major gradient) through the 126 MB L2"}
+              "l2": "no flush: one step streams ~0.45 GB (the BEV tensor written, its gradient read, the index "
+                    "structures) through the 126 MB L2"}
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
