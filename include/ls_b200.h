@@ -224,7 +224,12 @@ int ls_forward(const void* feat, int feat_layout, const void* logits, int dtype,
 
 /* grad_bev f32 (strided), grad_prob_ext (`dtype`, may be NULL), prob = forward's output, feat =
  * forward's input (read only when feat_layout == LS_FEAT_NHWC: no copy of it was saved).
- * Outputs grad_feat [B*N,C,fh,fw] in `feat_layout`, grad_logits [B*N,D,fh,fw] of `dtype`. */
+ * Outputs grad_feat [B*N,C,fh,fw] in `feat_layout`, grad_logits [B*N,D,fh,fw] of `dtype`.
+ * = [ls_bwd_transpose for NCHW gradients ->] the gradient gather of ls_splat_bwd -> ONE epilogue kernel
+ * (the softmax backward of ls_softmax_bwd + the NHWC -> NCHW fix-up of grad_feat, a thread per pixel;
+ * D = 32, 48, 64 - other depth counts run ls_softmax_bwd and ls_nhwc_to_nchw side by side); the same
+ * bits either way.  `saved` also carries a few per-image counters (zeroed by ls_forward, left zero by
+ * ls_backward) that the opt-in overlapped epilogue (environment LS_OVERLAP_BWD=1) synchronises on. */
 int ls_backward(const float* grad_bev, const LsBevStrides* grad_strides, const void* grad_prob_ext, const void* prob,
                 const void* feat, int feat_layout, int dtype, const LsShape* s, void* scratch, size_t scratch_bytes,
                 const void* saved, size_t saved_bytes, void* grad_feat, void* grad_logits, ls_stream_t stream);
