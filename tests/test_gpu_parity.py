@@ -773,6 +773,43 @@ def test_pixel_stationary_epilogue_ragged_feature_map(lib, dtype):
     _check_all(out, _oracle_outputs(shape, c, dtype), tol, 1e-6 if dtype == torch.float32 else None)
 
 
+def test_two_host_threads_share_one_device(lib):
+    """Two host threads drive the same device at the same time, each on its own stream (ctypes releases the GIL, so
+    the enqueue sequences really interleave): the library-owned side streams and events are shared per device and
+    guarded by a mutex for the duration of a call, the scratch blob is per stream - every iteration of both threads
+    must give the bits of a single-threaded run."""
+    import threading
+    shape = LiftSplatShape(batch=2, channels=64)
+    c = _oracle_case(shape, rig_seed=61, in_seed=31)
+    args = (shape, c["feat"], c["logits"], c["M"], c["t"], c["gb"], c["gp"])
+    ref = _run(*args, bev_format=torch.channels_last)
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream()
+            fmt = torch.channels_last if i == 0 else torch.contiguous_format     # different pipelines side by side
+            with torch.cuda.stream(stream):
+                for _ in range(6):
+                    out = _run(*args, bev_format=fmt)
+                    stream.synchronize()
+                    for k in ("prob", "grad_feat", "grad_logits"):
+                        assert torch.equal(out[k], ref[k]), (i, k)
+                    assert maxerr(out["bev"], ref["bev"]) <= 1e-6
+            results[i] = True
+        except BaseException as exc:      # surfaced in the main thread below
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert results == {0: True, 1: True}
+
+
 def test_full_size_values_on_sampled_batch_indices(lib):
     """BASELINE.json configs[1] at its full size (B=16, C=64): the BEV features and gradients of
     three batch indices against the oracle's values (the rest of the batch is covered by the
