@@ -336,7 +336,9 @@ int ls_launch_from_nhwc(const void* src, int dtype, int images, int C, int Cp, i
 // slot until the whole gather has drained.  The grid still cannot complete before the gather's last
 // warp has signalled, because every image has CTAs here.
 // =====================================================================================
+#ifndef LS_EPI_THREADS
 #define LS_EPI_THREADS 128
+#endif
 template <typename T, int kD>
 __device__ __forceinline__ void ls_softmax_bwd_pixel(const T* prob, const float* gprob_pm, const T* gext, int HW,
                                                      T* glogits, int img, int hw) {
