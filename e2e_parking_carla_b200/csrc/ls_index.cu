@@ -1,6 +1,8 @@
 // Index side of the lift-splat path: camera transform, fused geometry -> voxel -> rank,
 // counting sort (histogram with ticket, scan, placement).  Integer work is bit-exact with
 // the reference (model/bev_model.py:45-57,85-97); see include/ls_b200.h.
+#include <stdlib.h>
+
 #include "ls_internal.h"
 
 // =====================================================================================
@@ -182,6 +184,62 @@ ls_index_kernel(const float* __restrict__ M, const float* __restrict__ t, const 
   }
 }
 
+
+// The hot form of K1 (what ls_forward launches: sort outputs only, single z cell): LS_IDX_PIPE points per thread,
+// one after the other, software-pipelined around the histogram atomic.  The kernel above issues a thread's atomics
+// together and then WAITS for the tickets before it can store them and retire (the stores of `within` collect most
+// of its stall samples; without the returning atomic it runs in 21 us instead of 27).  Here the ticket of point i
+// is stored after the geometry of point i+1 has been computed, so the L2 round trip of the atomic hides behind
+// ~150 arithmetic instructions of the same thread.
+#ifndef LS_IDX_PIPE
+#define LS_IDX_PIPE 4
+#endif
+template <int kPolicy>
+__global__ void __launch_bounds__(256)
+ls_index_pipe_kernel(const float* __restrict__ M, const float* __restrict__ t, const float* __restrict__ frustum,
+                     LsDims dm, LsGrid grid, int* __restrict__ cell, int* __restrict__ within, int* __restrict__ counts) {
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int b = blockIdx.z, n = blockIdx.y;
+  float cam[12];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cam[k] = __ldg(M + (b * dm.N + n) * 9 + k);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cam[9 + k] = __ldg(t + (b * dm.N + n) * 3 + k);
+  const int i0 = blockIdx.x * (256 * LS_IDX_PIPE) + threadIdx.x;
+  int* __restrict__ cnt = counts + (size_t)b * grid.Vc;
+  const size_t base = (size_t)b * dm.Npts + (size_t)n * dm.DHW;
+  int* __restrict__ cellp = cell + base;
+  int* __restrict__ withp = within + base;
+  // the frustum of every point of this thread up front (independent loads, L2-resident table)
+  float u[LS_IDX_PIPE], v[LS_IDX_PIPE], d[LS_IDX_PIPE];
+#pragma unroll
+  for (int k = 0; k < LS_IDX_PIPE; ++k) {
+    const int i = i0 + k * 256;
+    const float* src = frustum + 3 * (i < dm.DHW ? i : 0);
+    u[k] = __ldg(src + 0); v[k] = __ldg(src + 1); d[k] = __ldg(src + 2);
+  }
+  int prev_tk = 0, prev_i = -1;
+#pragma unroll
+  for (int k = 0; k < LS_IDX_PIPE; ++k) {
+    const int i = i0 + k * 256;
+    float g[3];
+    int vx[3];
+    ls_point_geom<kPolicy>(cam, cam + 9, u[k], v[k], d[k], g);
+    const bool keep = ls_point_voxel_xy(g, grid, vx) && i < dm.DHW;
+    const int cid = keep ? ls_cell_of_xy(vx[0], vx[1], grid) : -1;
+    if (prev_i >= 0) withp[prev_i] = prev_tk;           // the previous point's ticket has had a whole point's arithmetic to arrive
+    prev_tk = 0;
+    prev_i = -1;
+    if (i < dm.DHW) {
+      if (keep) prev_tk = atomicAdd(cnt + cid, 1);
+      cellp[i] = cid;
+      prev_i = i;
+    }
+  }
+  if (prev_i >= 0) withp[prev_i] = prev_tk;
+}
+
 // zero the per-cell histogram (B * Vc ints, a multiple of 128): one 16-byte store per thread and trip
 __global__ void __launch_bounds__(256)
 ls_zero_counts_kernel(int4* __restrict__ p, int n16, int* __restrict__ extra, int n_extra) {
@@ -207,6 +265,15 @@ int ls_launch_zero_counts(int* counts, const LsDims& dm, const LsGrid& g, int* e
 
 int ls_launch_index(const float* M, const float* t, const float* frustum, const LsDims& dm, const LsGrid& g,
                     int* rank, int* cell, int* within, int* counts, cudaStream_t s) {
+  static const bool no_pipe = getenv("LS_INDEX_NO_PIPE") != nullptr;
+  if (!rank && cell && within && counts && g.zfast && !no_pipe) {      // the hot form: ls_forward
+    dim3 pgrid((dm.DHW + 256 * LS_IDX_PIPE - 1) / (256 * LS_IDX_PIPE), dm.N, dm.B);
+    if (dm.policy == LS_GEOM_TORCH_CUDA)
+      LS_LAUNCH(ls_index_pipe_kernel<LS_GEOM_TORCH_CUDA>, pgrid, dim3(256), 0, s, M, t, frustum, dm, g, cell, within, counts);
+    else
+      LS_LAUNCH(ls_index_pipe_kernel<LS_GEOM_TORCH_CPU>, pgrid, dim3(256), 0, s, M, t, frustum, dm, g, cell, within, counts);
+    return LS_OK;
+  }
   dim3 grid((dm.DHW + 256 * LS_IDX_ILP - 1) / (256 * LS_IDX_ILP), dm.N, dm.B);
   if (dm.policy == LS_GEOM_TORCH_CUDA)
     LS_LAUNCH((ls_index_kernel<false, false, LS_GEOM_TORCH_CUDA>), grid, dim3(256), 0, s, M, t, frustum, dm, g, rank,
