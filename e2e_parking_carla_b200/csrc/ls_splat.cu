@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is looked up through the runtime at first use)
+
 #include "ls_internal.h"
 
 
@@ -460,6 +462,10 @@ ls_splat_fwd_kernel(const T* __restrict__ featT, const int* __restrict__ seg_sta
 // (the same ray crosses it in consecutive depth bins) are served on-chip instead of going back
 // to L2, which the tile version saturates (9.6 of ~12.4 TB/s of L2 throughput).
 // =====================================================================================
+#ifndef LS_ABLATE
+#define LS_ABLATE 0       // developer builds only (tools/ab_build.sh): 1 = memory traffic without the arithmetic, 2 = arithmetic
+                          // without the row gathers, in the direct splat and the register-lean gather.  Results are WRONG.
+#endif
 #ifndef LS_SPLATD_MINB
 #define LS_SPLATD_MINB 6
 #endif
@@ -591,6 +597,11 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
   }
 #define LS_ACC_GET() { ls_unpack2(a01, acc0.x, acc0.y); ls_unpack2(a23, acc0.z, acc0.w); ls_unpack2(a45, acc1.x, acc1.y); ls_unpack2(a67, acc1.z, acc1.w); }
 #define LS_ACC_ZERO() { a01 = ls_pack2(0.f, 0.f); a23 = a01; a45 = a01; a67 = a01; }
+#elif LS_ABLATE == 1      /* developer ablation: every load and store, two adds instead of eight FMAs per record */
+#define LS_X3(a, b, c) __int_as_float(__float_as_int(a) ^ __float_as_int(b) ^ __float_as_int(c))
+#define LS_ACC8(WT__, A, B) { acc0.x = LS_X3(acc0.x, A.x, A.y); acc0.y = LS_X3(acc0.y, A.z, A.w); acc1.x = LS_X3(acc1.x, B.x, B.y); acc1.y = LS_X3(acc1.y, B.z, B.w); acc0.z += WT__; }
+#define LS_ACC_GET() {}
+#define LS_ACC_ZERO() { acc0 = make_float4(0.f, 0.f, 0.f, 0.f); acc1 = make_float4(0.f, 0.f, 0.f, 0.f); }
 #else
 #define LS_ACC8(WT__, A, B)                                                                          \
   {                                                                                                  \
@@ -614,7 +625,10 @@ ls_splat_fwd_direct_kernel(const T* __restrict__ featT, const int* __restrict__ 
     float4 fa[LS_QWIN], fb[LS_QWIN];                                                                 \
     _Pragma("unroll") for (int u = 0; u < LS_QWIN; ++u) {                                            \
       const char* row = f0 + (unsigned long long)((unsigned)cur[u].x >> 12) * row_bytes;             \
-      if (kHalf) ls_load8_bf16(row, fa[u], fb[u]);                                                   \
+      if (LS_ABLATE == 2) {          /* developer ablation: no feature-row traffic, same arithmetic */ \
+        fa[u] = make_float4(__int_as_float(cur[u].x), 1.f, 2.f, 3.f);                                \
+        fb[u] = make_float4(__int_as_float(cur[u].y), 1.f, 2.f, 3.f);                                \
+      } else if (kHalf) ls_load8_bf16(row, fa[u], fb[u]);                                            \
       else {                                                                                         \
         fa[u] = ls_load4<T>(reinterpret_cast<const T*>(row));                                        \
         fb[u] = ls_load4<T>(reinterpret_cast<const T*>(row + f1off));                                \
@@ -1221,12 +1235,20 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
           const unsigned rank = (unsigned)__shfl_sync(hmask, rec.x, LS_GOCC_ROWS * h + u, 16);
+#if LS_ABLATE == 2        // developer ablation: no gradient-row traffic, same arithmetic
+          g[u] = make_float4(__uint_as_float(rank), 1.f, 2.f, 3.f);
+#else
           g[u] = ls_grad_row4<MODE, TG>(gb, zrow, rank, rows.row_bytes, rows.nrows);
+#endif
         }
 #pragma unroll
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
           const float wgt = __int_as_float(__shfl_sync(hmask, rec.y, LS_GOCC_ROWS * h + u, 16));
-#if LS_FFMA2
+#if LS_ABLATE == 1        // developer ablation: every load and store, one add instead of nine multiply-adds per row
+          dot[LS_GOCC_ROWS * h + u] = wgt;
+          gf.x = __int_as_float(__float_as_int(gf.x) ^ __float_as_int(g[u].x) ^ __float_as_int(g[u].y));
+          gf.y = __int_as_float(__float_as_int(gf.y) ^ __float_as_int(g[u].z) ^ __float_as_int(g[u].w));
+#elif LS_FFMA2
           // packed pairs: (x,y) and (z,w) of the row take one FFMA2 each for the feature gradient and
           // one FMUL2 + one FFMA2 for the dot product (6 issue slots per row instead of 8)
           const unsigned long long gxy = ls_pack2(g[u].x, g[u].y), gzw = ls_pack2(g[u].z, g[u].w);
@@ -1265,6 +1287,176 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
   }
 }
 
+
+// =====================================================================================
+// Gradient gather through the Blackwell TMA gather4 path (opt-in, LS_GATHER_TMA=1).  Same work split, same
+// arithmetic and the same bits as ls_bwd_gather_occ_kernel; what changes is how the 256-byte gradient rows
+// reach the SM.  The LDG gather keeps 8 rows per half-warp in REGISTERS (96 KB in flight per SM at 24 warps),
+// and `tools/tma_gather_bench.cu` shows the chip's random-row throughput growing with the bytes in flight
+// per SM.  Here lane 0 of a warp hands the copy engine the sixteen row indices of a half depth window as four
+// `cp.async.bulk.tensor.2d.tile::gather4` instructions (SASS UTMALDG.2D.GATHER4: four arbitrary rows of a 2-D
+// tensor map per instruction) that land in a 4 KB shared-memory stage and complete on the stage's mbarrier;
+// two stages per warp = 8 KB per warp, 192 KB per SM in flight with three CTAs, none of it in registers.
+// Dropped points carry a row index beyond the tensor: the copy engine fills their rows with zeros.
+// =====================================================================================
+#define LS_TMA_STAGE_BYTES 4096      // 16 rows of 64 floats: rows 0-7 of half-warp 0, rows 8-15 of half-warp 1
+__device__ __forceinline__ unsigned ls_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ls_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nLS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LS_DONE_%=;\nbra LS_WAIT_%=;\nLS_DONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LS_GATHER_THREADS, 3)
+ls_bwd_gather_tma_kernel(const __grid_constant__ CUtensorMap tm, unsigned rows_per_sample, unsigned nrows, unsigned oob_row,
+                         const T* __restrict__ featT, const int2* __restrict__ pix_recs, LsDims dm,
+                         float* __restrict__ gprob_pm, T* __restrict__ gfeatT) {
+  extern __shared__ __align__(1024) unsigned char ls_tma_smem[];
+  constexpr int kWarps = LS_GATHER_THREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned ring = ls_smem_u32(ls_tma_smem) + (unsigned)warp * 2u * LS_TMA_STAGE_BYTES;
+  const unsigned bar0 = ls_smem_u32(ls_tma_smem) + (unsigned)kWarps * 2u * LS_TMA_STAGE_BYTES + (unsigned)warp * 16u;
+  if (lane == 0) {      // private prologue: the two stage barriers of this warp (one arrival each: the issuing lane)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  ls_pdl_trigger();
+  ls_pdl_wait();
+  const int col = blockIdx.x, bn = LS_GATHER_REVERSE ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int b = bn / dm.N;
+  const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15, h = lane >> 4;
+  const unsigned hmask = ls_half_mask();
+  const int wpp = dm.D >> 4;                                                  // windows per pixel
+  const int npass = (dm.fh + LS_HALFWARPS - 1) / LS_HALFWARPS;
+  const int nwin = npass * wpp;                                               // windows of this half-warp, all passes
+  const unsigned row_base = (unsigned)b * rows_per_sample;
+  const int2 dropped = make_int2((int)nrows, 0);
+  // records of window k of this half-warp (lane hl: depth bin 16 * (k % wpp) + hl of the pixel of pass k / wpp)
+  auto load_rec = [&](int k) -> int2 {
+    const int row = hw + (k / wpp) * LS_HALFWARPS;
+    if (k >= nwin || row >= dm.fh) return dropped;
+    return __ldg(pix_recs + ((size_t)bn * dm.HW + (size_t)row * dm.fw + col) * dm.D + 16 * (k % wpp) + hl);
+  };
+  // Stage `half` <- rows [8 * half, 8 * half + 8) of both half-warps' windows.  All lanes take part in the
+  // shuffles that bring the sixteen row indices to lane 0, which arms the barrier and issues four gather4 copies.
+  auto issue = [&](const int2& rec, int half) {
+    unsigned r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const unsigned rk = (unsigned)__shfl_sync(0xffffffffu, rec.x, (j >> 3) * 16 + half * 8 + (j & 7));
+      r[j] = rk < nrows ? row_base + rk : oob_row;
+    }
+    if (lane == 0) {
+      const unsigned bar = bar0 + 8u * half, dst = ring + (unsigned)half * LS_TMA_STAGE_BYTES;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(LS_TMA_STAGE_BYTES) : "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst + q * 1024u), "l"(&tm), "r"(bar), "r"(0),
+            "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+            : "memory");
+    }
+  };
+  int2 rec = load_rec(0);
+  bool live = __ballot_sync(0xffffffffu, (unsigned)rec.x < nrows) != 0u;     // warp-uniform: any kept point in the window
+  if (live) { issue(rec, 0); issue(rec, 1); }
+  unsigned ncons = 0;                                                          // windows consumed = phase of both barriers
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f), gf = f;
+  for (int k = 0; k < nwin; ++k) {
+    const int w = k % wpp, row = hw + (k / wpp) * LS_HALFWARPS;
+    const bool have = row < dm.fh;
+    const size_t pix = (size_t)bn * dm.HW + (size_t)(have ? row : 0) * dm.fw + col;
+    const bool on = 4 * hl < dm.Cp;
+    if (w == 0) {
+      f = (have && on) ? ls_load4<T>(featT + pix * dm.Cp + 4 * hl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gf = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int2 recn = load_rec(k + 1);
+    const bool live_n = __ballot_sync(0xffffffffu, (unsigned)recn.x < nrows) != 0u;
+    if (live) {
+      float dot[16];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        ls_mbar_wait(bar0 + 8u * half, ncons & 1u);
+        const float4* rows = reinterpret_cast<const float4*>(ls_tma_smem + (size_t)warp * 2 * LS_TMA_STAGE_BYTES +
+                                                             (size_t)half * LS_TMA_STAGE_BYTES + (size_t)h * 2048) + hl;
+        float4 g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] = rows[u * 16];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float wgt = __int_as_float(__shfl_sync(hmask, rec.y, half * 8 + u, 16));
+          float dv = f.x * g[u].x;
+          dv = fmaf(f.y, g[u].y, dv);
+          dv = fmaf(f.z, g[u].z, dv);
+          dv = fmaf(f.w, g[u].w, dv);
+          dot[half * 8 + u] = dv;
+          gf.x = fmaf(wgt, g[u].x, gf.x); gf.y = fmaf(wgt, g[u].y, gf.y);
+          gf.z = fmaf(wgt, g[u].z, gf.z); gf.w = fmaf(wgt, g[u].w, gf.w);
+        }
+        __syncwarp();                               // every lane has its rows in registers: the stage is free
+        if (live_n) issue(recn, half);
+      }
+      ++ncons;
+      const float mine = ls_half_butterfly(dot, hl, hmask);
+      if (have) gprob_pm[pix * dm.D + 16 * w + hl] = mine;
+    } else {
+      if (have) gprob_pm[pix * dm.D + 16 * w + hl] = 0.0f;
+      if (live_n) { issue(recn, 0); issue(recn, 1); }
+    }
+    if (w == wpp - 1 && have && on) ls_store4<T>(gfeatT + pix * dm.Cp + 4 * hl, gf);
+    rec = recn;
+    live = live_n;
+  }
+}
+
+typedef CUresult (*LsEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// LS_OK and *launched = true when the TMA variant took the launch; *launched = false: the caller uses the LDG gather
+template <typename T>
+static int ls_gather_tma_try(const LsRows& rows, const void* featT, const int2* pix_recs, const LsDims& dm, float* gprob_pm,
+                             void* gfeatT, cudaStream_t s, bool* launched) {
+  *launched = false;
+  static LsEncodeTiled encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+    (void)cudaGetLastError();
+    return (LsEncodeTiled)fn;
+  }();
+  const long long row_elems = rows.row_bytes / 4;
+  if (!encode || dm.Cp != 64 || dm.D % 16 != 0 || rows.row_bytes % 16 != 0 || (uintptr_t)rows.base % 16 != 0 ||
+      row_elems <= 0 || rows.sample_stride % row_elems != 0)
+    return LS_OK;
+  const unsigned long long rps = (unsigned long long)(rows.sample_stride / row_elems);
+  const unsigned long long total = rps * (unsigned long long)(dm.B - 1) + rows.nrows;
+  if (rps < rows.nrows || total >= (1ULL << 31)) return LS_OK;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)total};
+  const cuuint64_t gstride[1] = {rows.row_bytes};
+  const cuuint32_t box[2] = {64, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(rows.base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return LS_OK;
+  constexpr int kSmem = (LS_GATHER_THREADS / 32) * (2 * LS_TMA_STAGE_BYTES + 16);
+  static unsigned long long attr_done = 0;
+  if (ls_attr_needed(&attr_done))
+    LS_CUDA(cudaFuncSetAttribute(ls_bwd_gather_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  LS_LAUNCH((ls_bwd_gather_tma_kernel<T>), dim3(dm.fw, dm.B * dm.N), dim3(LS_GATHER_THREADS), (size_t)kSmem, s, tm,
+            (unsigned)rps, rows.nrows, (unsigned)total, (const T*)featT, pix_recs, dm, gprob_pm, (T*)gfeatT);
+  *launched = true;
+  return LS_OK;
+}
 
 // arrivals that complete an image in ready[] (ls_bwd_gather_occ_kernel)
 int ls_gather_ready_target(const LsDims& dm) { return dm.fw * (LS_GATHER_THREADS / 32); }
@@ -1305,6 +1497,12 @@ static int ls_gather_dispatch(const LsRows& rows, const void* featT, const int2*
     LS_LAUNCH((ls_bwd_gather_occ_kernel<T, LS_GRAD_DIRECT_VEC, __nv_bfloat16>), grid, dim3(LS_GATHER_THREADS), 0, s, rows,
               (const T*)featT, pix_recs, dm, gprob_pm, (T*)gfeatT, ready);
     return LS_OK;
+  }
+  static const bool want_tma = getenv("LS_GATHER_TMA") && atoi(getenv("LS_GATHER_TMA")) != 0;
+  if (want_tma && MODE == LS_GRAD_DIRECT_VEC && !ready && nch == 1) {      // rows through the TMA gather4 path
+    bool launched = false;
+    const int rc = ls_gather_tma_try<T>(rows, featT, pix_recs, dm, gprob_pm, gfeatT, s, &launched);
+    if (rc != LS_OK || launched) return rc;
   }
   if (LS_GATHER_OCC && dm.D % 16 == 0 && nch == 1) {
     LS_LAUNCH((ls_bwd_gather_occ_kernel<T, MODE, float>), grid, dim3(LS_GATHER_THREADS), 0, s, rows, (const T*)featT,

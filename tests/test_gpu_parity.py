@@ -1048,6 +1048,36 @@ def test_bulk_store_variant_matches(lib):
         assert torch.equal(a[k], b[k]), k
 
 
+def test_tma_gather_variant_matches(lib):
+    """LS_GATHER_TMA=1 (gradient rows fetched by the copy engine: cp.async.bulk.tensor gather4 into
+    shared-memory stages, tools/tma_gather_bench.cu) against the default LDG gather: a child process
+    per variant, fp32 and bf16 features, every gradient must have the same bits."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        for dt in ("float32", "bfloat16"):
+            outs = []
+            for mode in ("0", "1"):
+                path = os.path.join(tmp, dt + mode + ".pt")
+                code = (
+                    "import sys, torch; sys.path.insert(0, %r); import bench\n"
+                    "from e2e_parking_carla_b200.synthetic import LiftSplatShape\n"
+                    "st = bench.Stepper(LiftSplatShape(batch=3, channels=64), torch.%s, torch.device('cuda:0'))\n"
+                    "st.step(); torch.cuda.synchronize()\n"
+                    "torch.save({k: getattr(st, k).float().cpu() for k in ('bev', 'prob', 'gfeat', 'glogits')}, %r)\n"
+                    % (root, dt, path))
+                env = dict(os.environ, LS_GATHER_TMA=mode)
+                out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+                assert out.returncode == 0, out.stderr[-2000:]
+                outs.append(torch.load(path))
+            a, b = outs
+            assert a["gfeat"].abs().sum() > 0 and a["glogits"].abs().sum() > 0
+            for k in ("bev", "prob", "gfeat", "glogits"):
+                assert torch.equal(a[k], b[k]), (dt, k)
+
+
 @pytest.mark.parametrize("tile_x", [8, 32])
 def test_square_tiles_same_bits_as_strips(lib, tile_x):
     """The channels-last splat with tile_x x (128 / tile_x) tiles (LsShape.tile_x) against 1 x 128
