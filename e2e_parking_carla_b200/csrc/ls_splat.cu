@@ -876,10 +876,13 @@ int ls_launch_refresh(const void* prob, int dtype, const int* perm, const int* s
 #define LS_GOCC_ROWS 8    // rows gathered at a time by a half-warp of the register-lean gather
 #endif
 #ifndef LS_GOCC_MINB
-#define LS_GOCC_MINB 3    // its CTAs per SM
+#define LS_GOCC_MINB 4    // its CTAs per SM (32 warps: 64 registers; 3 CTAs at 80 registers measured 2 us slower)
+#endif
+#ifndef LS_GOCC_BFLY8
+#define LS_GOCC_BFLY8 1   // reduce each batch of 8 dot products right away (needs LS_GOCC_ROWS == 8, LS_GATHER_SKIP_DEAD != 2): what lets 8 rows in flight fit 64 registers
 #endif
 #ifndef LS_GATHER_OCC
-#define LS_GATHER_OCC 1   // register-lean gradient gather (24 warps/SM) for Cp <= 64, D % 16 == 0
+#define LS_GATHER_OCC 1   // register-lean gradient gather (32 warps/SM) for Cp <= 64, D % 16 == 0
 #endif
 #ifndef LS_GATHER_REVERSE
 #define LS_GATHER_REVERSE 1
@@ -1065,6 +1068,30 @@ __device__ __forceinline__ float ls_half_butterfly(float (&dot)[16], int hl, uns
   return keep + __shfl_xor_sync(hmask, send, 1, 16);
 }
 
+// the same tree for EIGHT values (one batch of rows of the register-lean gather): the xor-8, -4, -2 levels leave row
+// hl >> 1 in each lane pair, the xor-1 level adds the pair's two partial sums (a + b == b + a: same bits as above)
+__device__ __forceinline__ float ls_half_butterfly8(float (&dot)[8], int hl, unsigned hmask) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool hi = hl & 8;
+    const float send = hi ? dot[u] : dot[u + 4];
+    const float keep = hi ? dot[u + 4] : dot[u];
+    dot[u] = keep + __shfl_xor_sync(hmask, send, 8, 16);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const bool hi = hl & 4;
+    const float send = hi ? dot[u] : dot[u + 2];
+    const float keep = hi ? dot[u + 2] : dot[u];
+    dot[u] = keep + __shfl_xor_sync(hmask, send, 4, 16);
+  }
+  const bool hi = hl & 2;
+  const float send = hi ? dot[0] : dot[1];
+  const float keep = hi ? dot[1] : dot[0];
+  const float v = keep + __shfl_xor_sync(hmask, send, 2, 16);
+  return v + __shfl_xor_sync(hmask, v, 1, 16);
+}
+
 // Where a sample's gradient rows live: base + b * sample_stride floats, rows row_bytes apart.
 struct LsRows {
   const void* base;
@@ -1145,7 +1172,9 @@ ls_bwd_gather_kernel(LsRows rows, const T* __restrict__ featT, const int2* __res
 // TB/s at 16 / 24 / 32 warps per SM), so this version trades registers for warps: the sixteen
 // records of a depth window are loaded one per lane (a single coalesced 128-byte load per
 // half-warp, prefetched a window ahead, broadcast with 16-wide shuffles) and the rows are
-// gathered eight at a time - under 86 registers, three CTAs (24 warps) per SM.
+// gathered eight at a time, each batch's eight dot products reduced right away (ls_half_butterfly8) - 64 registers,
+// four CTAs (32 warps) per SM; with the sixteen dot products of a window kept until its end it needed 80 registers
+// (24 warps) and ran 2 us longer.
 // ready != NULL: the backward's epilogue (ls_bwd_epilogue_kernel: softmax backward + layout fix-up of
 // grad_feat) is the next launch in the stream and runs OVERLAPPED with this kernel's tail.  Every CTA
 // lets the dependent launch be scheduled as soon as it has passed its own dependency wait; the
@@ -1221,9 +1250,19 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
         continue;
       }
 #endif
+#if LS_GOCC_BFLY8
+      // the eight dot products of a batch are reduced right after the batch (same butterfly tree, same bits):
+      // eight live registers instead of sixteen across the second batch's loads
+#define LS_DOT(i) dot8[(i) - LS_GOCC_ROWS * h]
+#else
       float dot[16];
+#define LS_DOT(i) dot[i]
+#endif
 #pragma unroll
       for (int h = 0; h < 16 / LS_GOCC_ROWS; ++h) {
+#if LS_GOCC_BFLY8
+        float dot8[8];
+#endif
 #if LS_GATHER_SKIP_DEAD == 2
         if (!((kept16 >> (LS_GOCC_ROWS * h)) & ((1u << LS_GOCC_ROWS) - 1u))) {      // half-warp uniform
 #pragma unroll
@@ -1245,7 +1284,7 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
         for (int u = 0; u < LS_GOCC_ROWS; ++u) {
           const float wgt = __int_as_float(__shfl_sync(hmask, rec.y, LS_GOCC_ROWS * h + u, 16));
 #if LS_ABLATE == 1        // developer ablation: every load and store, one add instead of nine multiply-adds per row
-          dot[LS_GOCC_ROWS * h + u] = wgt;
+          LS_DOT(LS_GOCC_ROWS * h + u) = wgt;
           gf.x = __int_as_float(__float_as_int(gf.x) ^ __float_as_int(g[u].x) ^ __float_as_int(g[u].y));
           gf.y = __int_as_float(__float_as_int(gf.y) ^ __float_as_int(g[u].z) ^ __float_as_int(g[u].w));
 #elif LS_FFMA2
@@ -1255,7 +1294,7 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
           const unsigned long long w2 = ls_pack2(wgt, wgt);
           float d0, d1;
           ls_unpack2(ls_fma2(fzw, gzw, ls_mul2(fxy, gxy)), d0, d1);
-          dot[LS_GOCC_ROWS * h + u] = d0 + d1;
+          LS_DOT(LS_GOCC_ROWS * h + u) = d0 + d1;
           gfxy = ls_fma2(w2, gxy, gfxy);
           gfzw = ls_fma2(w2, gzw, gfzw);
 #else
@@ -1263,13 +1302,20 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
           dv = fmaf(f.y, g[u].y, dv);
           dv = fmaf(f.z, g[u].z, dv);
           dv = fmaf(f.w, g[u].w, dv);
-          dot[LS_GOCC_ROWS * h + u] = dv;
+          LS_DOT(LS_GOCC_ROWS * h + u) = dv;
           gf.x = fmaf(wgt, g[u].x, gf.x); gf.y = fmaf(wgt, g[u].y, gf.y);
           gf.z = fmaf(wgt, g[u].z, gf.z); gf.w = fmaf(wgt, g[u].w, gf.w);
 #endif
         }
+#if LS_GOCC_BFLY8
+        const float v8 = ls_half_butterfly8(dot8, hl, hmask);
+        if (!(hl & 1)) gprob_pm[pix * dm.D + 16 * w + 8 * h + (hl >> 1)] = v8;
+#endif
       }
+#undef LS_DOT
+#if !LS_GOCC_BFLY8
       gprob_pm[pix * dm.D + 16 * w + hl] = ls_half_butterfly(dot, hl, hmask);
+#endif
       rec = recn;
     }
 #if LS_FFMA2
@@ -1291,7 +1337,7 @@ ls_bwd_gather_occ_kernel(LsRows rows, const T* __restrict__ featT, const int2* _
 // =====================================================================================
 // Gradient gather through the Blackwell TMA gather4 path (opt-in, LS_GATHER_TMA=1).  Same work split, same
 // arithmetic and the same bits as ls_bwd_gather_occ_kernel; what changes is how the 256-byte gradient rows
-// reach the SM.  The LDG gather keeps 8 rows per half-warp in REGISTERS (96 KB in flight per SM at 24 warps),
+// reach the SM.  The LDG gather keeps 8 rows per half-warp in REGISTERS (128 KB in flight per SM at 32 warps),
 // and `tools/tma_gather_bench.cu` shows the chip's random-row throughput growing with the bytes in flight
 // per SM.  Here lane 0 of a warp hands the copy engine the sixteen row indices of a half depth window as four
 // `cp.async.bulk.tensor.2d.tile::gather4` instructions (SASS UTMALDG.2D.GATHER4: four arbitrary rows of a 2-D
