@@ -123,7 +123,7 @@ if all(have("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8", "train", "train
     n2, n4, n8 = [line("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8")]
     t8, t1, tr = line("r02_bench_train8.json"), line("r02_bench_train.json"), line("r02_bench_train_reference.json")
     md += f'''Multi-GPU (torchrun, one rank per GPU, per-GPU batch 16 for the lift-splat and 12 for training; `r02_bench_n2/n4/n8.json`:
-separate `gpurun --gpus N` calls of the final build; `r02_bench_train8.json` / `r02_nccl_n8.txt`: the 20-step training run at 8 GPUs,
+separate `gpurun --gpus N` calls at commit 146129d (before the 32-warp gather: the lift-splat step was 0.234 ms there); `r02_bench_train8.json` / `r02_nccl_n8.txt`: the 20-step training run at 8 GPUs,
 taken earlier in the round at commit 129717f - the harness has not changed since and the lift-splat is 0.5 % of its step):
 
 | GPUs | lift-splat samples/s (device) | ms/step | efficiency | e2e samples/s (ms; link floor) | train samples/s (ms/step) | train efficiency |
@@ -161,7 +161,8 @@ md += f'''## Reading
 
 * **Backward = two kernels.**  The gather reads the channels-last gradient rows in place ({ga["dram_read_MB"]:.0f} MB of DRAM reads: 118 MB of
   distinct rows + feature rows + the pixel-major index, essentially every byte once; L1 hit {ga["l1_hit_pct"]:.0f} %, L2 hit {ga["l2_hit_pct"]:.0f} %,
-  {ga["issue_active_pct"]:.0f} % issue-active, 24 warps/SM at {int(ga["regs"])} registers).  The epilogue - softmax backward and the NHWC -> NCHW fix-up of
+  {ga["issue_active_pct"]:.0f} % issue-active, 32 warps/SM at {int(ga["regs"])} registers: each batch of eight dot products is reduced right away, which
+  is what lets eight rows in flight per half-warp fit 64 registers; at 80 registers / 24 warps the kernel ran 2 us longer).  The epilogue - softmax backward and the NHWC -> NCHW fix-up of
   `grad_feat`, formerly two kernels staged through shared memory (17 us in situ, ~80 instructions per element) - is ONE
   thread-per-pixel kernel now ({ep["dram_read_MB"]:.0f} + {ep["dram_write_MB"]:.0f} MB, {ep["dram_pct"]:.0f} % of the DRAM peak, {ep["issue_active_pct"]:.0f} % issue-active, {int(ep["regs"])} registers): same bits, {t("bwd_epilogue"):.1f} us in situ.
   DRAM traffic of the whole backward stage: {bwd_traffic / 1e6:.1f} MB against 222.6 MB algorithmic ({bwd_traffic / 222.56e6:.2f}x; round 1: 450 MB, 2.02x).
@@ -181,9 +182,23 @@ md += f'''## Reading
   per thread, not k^2-bound (10 compares per record on average): 64 / 128 / 256 / 512 / 1024 threads per tile give 73 / 36 / 21 / 30 /
   52 us; ordering a tile's cells by size so that a warp's compare loops have equal trip counts made it slower (27 us).  The
   opt-in static-rig cache replaces index, scan, place and canon by two streaming refresh kernels.
+* **What bounds the two row gathers** (`r02_ablation.txt`: developer builds `LS_ABLATE=1/2` of the same kernels, timed in the same
+  step): backward gather 73.8 us shipped / 69.0 us with all its memory traffic and a quarter of its arithmetic / 37.1 us with
+  its arithmetic and no row traffic; canon + forward splat 80.0 / 80-83 / 58.6 us.  Both run in the time of their access pattern
+  alone - one 256-byte row per record from L2, 636 MB per kernel.  `r02_tma_gather_bench.txt` (`tools/tma_gather_bench.cu`) is
+  the chip's throughput for exactly that pattern: 2.49 M uniformly random rows of a 164 MB table at 6.9 / 8.1 / 9.2 TB/s with
+  24 / 32 / 48 warps per SM of `LDG.128`, 8.2-8.6 TB/s through TMA gather4 (`UTMALDG.2D.GATHER4`), 14.5-16.5 TB/s from an
+  L2-resident table.  The gather moves its 636 MB at 9 TB/s, the splat at 11 TB/s: 0.75-1.0 of what the hardware delivers for
+  random row gathers; the HBM fraction is low because the algorithmic bytes are a third of that row traffic.
+* **Measured and rejected in the last session** (A/B logs `r02_ab_*.txt`): canon ranking from a shared-memory copy of the tile's
+  keys with warp-uniform 16-byte broadcast windows (+2.3 to +14 us); bulk L2 prefetch of the gradient 1-8 samples ahead
+  (`UBLKPF.L2`: +-0.1 us - DRAM latency is not what the gather waits for); the gradient rows through TMA gather4 into
+  mbarrier-completed shared-memory stages (`ls_bwd_gather_tma_kernel`, `LS_GATHER_TMA=1`: bit-identical, 91 vs 74 us; stays
+  in the library as the opt-in Blackwell-native variant).
 * SASS: `UBLKCP.G.S` (bulk async copy shared -> global, the TMA path) is in `ls_splat_fwd_kernel<.., LS_OUT_NHWC_BULK, 64>`
   (`cuobjdump -sass libls_b200.so | grep UBLKCP`: fp32 and bf16 variants); `griddepcontrol.launch_dependents` (ACQBULK / PDL trigger)
-  in `ls_camera_transform_kernel` and, with `LS_OVERLAP_BWD=1`, in the gather.
+  in `ls_camera_transform_kernel` and, with `LS_OVERLAP_BWD=1`, in the gather; `UTMALDG.2D.GATHER4` + `SYNCS` (mbarrier) in
+  `ls_bwd_gather_tma_kernel` (fp32 and bf16 features).
 '''
 open(P + "r02_summary.md", "w").write(md)
 print("written", len(md))
