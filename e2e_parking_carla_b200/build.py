@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     base = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
-    for macro in ("LS_TX", "LS_TY", "LS_PDL_TRIGGER", "LS_IDX_ILP", "LS_TCHUNK", "LS_QWIN", "LS_SPLAT_MINB", "LS_PLACE_GROUPS", "LS_GATHER_THREADS", "LS_GATHER_MINB", "LS_GATHER_REVERSE", "LS_GATHER_OCC", "LS_GOCC_ROWS", "LS_GOCC_MINB", "LS_SPLATD_MINB", "LS_CANON_BIG", "LS_GATHER_SKIP_DEAD", "LS_FFMA2", "LS_GL_DIRECT", "LS_SPLAT_FASTLOOP", "LS_CANON_THREADS", "LS_GATHER_L2PF", "LS_EPI_THREADS", "LS_IDX_PIPE", "LS_ABLATE", "LS_GOCC_BFLY8"):     # developer knobs: tile shape, early-launch trigger
+    for macro in ("LS_TX", "LS_TY", "LS_PDL_TRIGGER", "LS_IDX_ILP", "LS_TCHUNK", "LS_QWIN", "LS_SPLAT_MINB", "LS_PLACE_GROUPS", "LS_GATHER_THREADS", "LS_GATHER_MINB", "LS_GATHER_REVERSE", "LS_GATHER_OCC", "LS_GOCC_ROWS", "LS_GOCC_MINB", "LS_SPLATD_MINB", "LS_CANON_BIG", "LS_GATHER_SKIP_DEAD", "LS_FFMA2", "LS_GL_DIRECT", "LS_SPLAT_FASTLOOP", "LS_CANON_THREADS", "LS_GATHER_L2PF", "LS_EPI_THREADS", "LS_IDX_PIPE", "LS_ABLATE", "LS_GOCC_BFLY8", "LS_GATHER_PF1"):     # developer knobs: tile shape, early-launch trigger
         if os.environ.get(macro):
             base += ["-D%s=%s" % (macro, os.environ[macro])]
     if os.environ.get("LS_PROFILE"):
