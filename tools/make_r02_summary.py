@@ -101,6 +101,7 @@ for f, desc in (("r02_bench_featcl.json", "+ channels-last features (LS_FEAT_NHW
                 ("r02_bench_nchw.json", "NCHW BEV + gradient (the reference's strides; staged backward)"),
                 ("r02_bench_bulk_tma.json", "`LS_SPLAT_OUT=bulk`: one bulk (TMA) store per tile instead of direct rows"),
                 ("r02_bench_overlap_bwd.json", "`LS_OVERLAP_BWD=1`: epilogue launched as the gather's programmatic dependent, per-image arrival counters"),
+                ("r02_bench_gather_tma.json", "`LS_GATHER_TMA=1`: gradient rows through TMA gather4 into mbarrier-completed shared-memory stages instead of LDG.128"),
                 ("r02_bench_staged_epilogue.json", "`LS_SOFTMAX_BWD_STAGED=1`: the two staged epilogue kernels (softmax backward || layout) instead of the thread-per-pixel one"),
                 ("r02_bench_stress.json", "stress: B=32, 6 cams, D=96, 400x400 (configs[3]); round 1: 2.01 ms"),
                 ("r02_bench_stress_bf16.json", "stress, bf16")):
@@ -123,7 +124,8 @@ if all(have("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8", "train", "train
     n2, n4, n8 = [line("r02_bench_%s.json" % x) for x in ("n2", "n4", "n8")]
     t8, t1, tr = line("r02_bench_train8.json"), line("r02_bench_train.json"), line("r02_bench_train_reference.json")
     md += f'''Multi-GPU (torchrun, one rank per GPU, per-GPU batch 16 for the lift-splat and 12 for training; `r02_bench_n2/n4/n8.json`:
-separate `gpurun --gpus N` calls at commit 146129d (before the 32-warp gather: the lift-splat step was 0.234 ms there); `r02_bench_train8.json` / `r02_nccl_n8.txt`: the 20-step training run at 8 GPUs,
+separate `gpurun --gpus N` calls at commit 146129d (before the 32-warp / L1-prefetch gather: the lift-splat step was 0.234 ms there; training, agent and
+reference-arm lines: commit ed5b6c2 of this session, same harness); `r02_bench_train8.json` / `r02_nccl_n8.txt`: the 20-step training run at 8 GPUs,
 taken earlier in the round at commit 129717f - the harness has not changed since and the lift-splat is 0.5 % of its step):
 
 | GPUs | lift-splat samples/s (device) | ms/step | efficiency | e2e samples/s (ms; link floor) | train samples/s (ms/step) | train efficiency |
@@ -194,7 +196,13 @@ md += f'''## Reading
   keys with warp-uniform 16-byte broadcast windows (+2.3 to +14 us); bulk L2 prefetch of the gradient 1-8 samples ahead
   (`UBLKPF.L2`: +-0.1 us - DRAM latency is not what the gather waits for); the gradient rows through TMA gather4 into
   mbarrier-completed shared-memory stages (`ls_bwd_gather_tma_kernel`, `LS_GATHER_TMA=1`: bit-identical, 91 vs 74 us; stays
-  in the library as the opt-in Blackwell-native variant).
+  in the library as the opt-in Blackwell-native variant); L1 prefetch two batches ahead in the gather (73 vs 69.7 us) and the
+  same one-window-ahead L1 prefetch in the forward splat (records two windows ahead, 79 registers: splat +10 us).
+* **What did help in the last session**: the gather at 32 warps per SM (each batch of eight dot products reduced right away:
+  64 registers, `r02_ab_gather_32warps.txt`: 74.0 -> 71.8 us) and `prefetch.global.L1` (SASS `CCTL.E.PF1`) of the next batch's
+  rows by the lanes that hold their records (`r02_ab_gather_l1_prefetch.txt`: 71.7 -> 69.7 us): the batch in flight lives in
+  registers, the one behind it in L1 - more bytes in flight per SM without registers.  Same bits in every variant (sha256 of
+  BEV + gradients printed by `tools/ab_sha.sh`).
 * SASS: `UBLKCP.G.S` (bulk async copy shared -> global, the TMA path) is in `ls_splat_fwd_kernel<.., LS_OUT_NHWC_BULK, 64>`
   (`cuobjdump -sass libls_b200.so | grep UBLKCP`: fp32 and bf16 variants); `griddepcontrol.launch_dependents` (ACQBULK / PDL trigger)
   in `ls_camera_transform_kernel` and, with `LS_OVERLAP_BWD=1`, in the gather; `UTMALDG.2D.GATHER4` + `SYNCS` (mbarrier) in
