@@ -81,3 +81,24 @@ def grid_of(shape: LiftSplatShape):
 def frustum_of(shape: LiftSplatShape) -> np.ndarray:
     from oracle import lift_splat_oracle as lo
     return lo.create_frustum(shape.d_bound, shape.final_dim, shape.bev_down_sample)
+
+
+# ------------------------------------------------------------------------------------
+# add_target_bev fixtures (tests/golden/make_golden_target_bev.py)
+# ------------------------------------------------------------------------------------
+TARGET_BEV_CASES = ("inner_b16", "border_b12", "stress_b8", "ragged_b6")
+
+
+def target_bev_golden(name):
+    """(target points f32[B,3], x_res, y_res, H, W, seed, target map f32[B,1,H,W]) of one frozen case.
+    The reference stamps one python-slice box per sample, so the stored row / column occupancy is
+    the map: map[b] = rows[b] (outer) cols[b]; the stored per-sample sums cross-check it."""
+    import torch
+    z = np.load(os.path.join(GOLDEN_DIR, "target_bev.npz"))
+    xr, yr, h, w, seed = z[name + "_meta"]
+    h, w = int(h), int(w)
+    rows = np.unpackbits(z[name + "_rows"], axis=1)[:, :h].astype(np.float32)
+    cols = np.unpackbits(z[name + "_cols"], axis=1)[:, :w].astype(np.float32)
+    tmap = rows[:, :, None] * cols[:, None, :]
+    assert np.array_equal(tmap.sum((1, 2)).astype(np.int32), z[name + "_sum"])
+    return torch.from_numpy(z[name + "_target"]), float(xr), float(yr), h, w, int(seed), torch.from_numpy(tmap)[:, None]

@@ -947,6 +947,32 @@ def test_add_target_bev_matches_reference_semantics(lib):
         assert relerr(r[1], results[0][1]) < 1e-4 and relerr(r[2], results[0][2]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["inner_b16", "border_b12", "stress_b8", "ragged_b6"])
+def test_target_bev_kernel_vs_reference_golden(lib, name):
+    """ls_target_bev against maps frozen from the UNMODIFIED reference method (tests/golden/
+    target_bev.npz): the noised pixels are drawn as the reference draws them (torch's CPU generator
+    under the fixture's seed, the product's own target_pixels on CPU tensors), the stamp runs on the GPU
+    into an NCHW map, a channels-last map and channel C of a channels-last [B,C+1,X,Y] buffer whose
+    other channels must stay untouched."""
+    import types
+    from _util import target_bev_golden
+    from e2e_parking_carla_b200.target_bev import _stamp, target_pixels
+    pts, xr, yr, h, w, seed, tmap = target_bev_golden(name)
+    b = pts.shape[0]
+    cfg = types.SimpleNamespace(bev_x_bound=[0.0, 0.0, xr], bev_y_bound=[0.0, 0.0, yr])
+    torch.manual_seed(seed)
+    pix = target_pixels((b, 2, h, w), pts.clone(), cfg).to(DEV)
+    nchw = torch.full((b, 1, h, w), 7.0, device=DEV)
+    _stamp(pix, nchw)
+    assert torch.equal(nchw.cpu(), tmap)
+    cl = torch.full((b, h, w, 1), 7.0, device=DEV).permute(0, 3, 1, 2)
+    _stamp(pix, cl)
+    assert torch.equal(cl.cpu(), tmap)
+    wide = torch.full((b, h, w, 5), 3.0, device=DEV).permute(0, 3, 1, 2)     # channels-last [B,5,H,W]
+    _stamp(pix, wide[:, 4:])
+    assert torch.equal(wide[:, 4:].cpu(), tmap) and bool((wide[:, :4] == 3.0).all())
+
+
 def test_proj_bev_feature_compat_api(lib):
     """The reference's three-call form get_geometry -> encoder_forward -> proj_bev_feature
     (model/bev_model.py:109-113) on the materialised tensors gives the fused path's result

@@ -226,3 +226,63 @@ def test_depth_loss_live_reference():
     assert np.array_equal(labels, lab_ref.numpy())
     assert abs(loss - loss_ref.item()) <= 1e-6 * abs(loss)
     assert np.abs(grad - prob.grad.numpy()).max() <= 1e-6 * np.abs(grad).max()
+
+
+# ------------------------------------------------------------------------------------
+# add_target_bev (model/parking_model.py:28-46): fixtures frozen from the unmodified method
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["inner_b16", "border_b12", "stress_b8", "ragged_b6"])
+def test_target_bev_port_vs_golden(name):
+    """The port (what the GPU tests check ``add_target_bev`` against) reproduces the unmodified
+    reference method under the same generator seed: noise draw, truncation, python-slice borders."""
+    from _util import target_bev_golden
+    tp_pts, xr, yr, h, w, seed, tmap = target_bev_golden(name)
+    bev = torch.zeros(tp_pts.shape[0], 2, h, w)
+    torch.manual_seed(seed)
+    wide, got = tp.add_target_bev_ref(bev, tp_pts.clone(), xr, yr)
+    assert torch.equal(got, tmap) and torch.equal(wide[:, 2:], tmap) and float(wide[:, :2].abs().sum()) == 0.0
+    # the host half of the product (the pixel computation is torch ops on whatever device the points
+    # live on) lands on the same pixels: the stamp is rows cx-4..cx+3 / cols cy-4..cy+3 where in range
+    from e2e_parking_carla_b200.target_bev import target_pixels
+    import types
+    cfg = types.SimpleNamespace(bev_x_bound=[0.0, 0.0, xr], bev_y_bound=[0.0, 0.0, yr])
+    torch.manual_seed(seed)
+    pix = target_pixels((tp_pts.shape[0], 2, h, w), tp_pts.clone(), cfg)
+    assert pix.dtype == torch.int32 and tuple(pix.shape) == (tp_pts.shape[0], 2)
+    for i in range(pix.shape[0]):
+        ref = torch.zeros(h, w)
+        cx, cy = int(pix[i, 0]), int(pix[i, 1])
+        ref[cx - 4:cx + 4, cy - 4:cy + 4] = 1.0
+        assert torch.equal(ref, tmap[i, 0])
+
+
+def test_target_bev_known_answers():
+    """What the border fixture pins: a stamp fully inside has 64 ones; a negative slice start next to
+    a positive stop selects nothing; the far border clips; two negative bounds wrap around."""
+    from _util import target_bev_golden
+    sums = {n: target_bev_golden(n)[6].sum((1, 2, 3)).int().tolist() for n in ("inner_b16", "border_b12")}
+    assert sums["inner_b16"] == [64] * 16
+    assert sums["border_b12"] == [0, 25, 64, 64, 0, 0, 64, 0, 32, 0, 0, 64]
+    tmap = target_bev_golden("border_b12")[6]
+    assert tmap[6, 0, 150:, 150:].sum() == 64        # target (-11, -11) m: both bounds negative -> wraps to the far corner
+
+
+def test_target_bev_live_reference():
+    """The fixtures regenerate from the reference tree when it is mounted."""
+    if not os.path.isfile("/root/reference/model/parking_model.py"):
+        pytest.skip("reference tree not present")
+    import importlib.util
+    from _util import TARGET_BEV_CASES, target_bev_golden
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_target_bev",
+                                                  os.path.join(here, "golden", "make_golden_target_bev.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fn, lines = gen.reference_add_target_bev()
+    assert tuple(lines) == (28, 46)                  # the lines every citation in this repo names
+    cases = gen.cases()
+    assert set(cases) == set(TARGET_BEV_CASES)
+    for name, (pts, xr, yr, h, w, seed) in cases.items():
+        g_pts, g_xr, g_yr, g_h, g_w, g_seed, tmap = target_bev_golden(name)
+        assert torch.equal(pts, g_pts) and (xr, yr, h, w, seed) == (g_xr, g_yr, g_h, g_w, g_seed)
+        assert torch.equal(gen.run_reference(fn, pts, xr, yr, h, w, seed), tmap)
