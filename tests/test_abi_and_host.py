@@ -171,3 +171,26 @@ def test_reference_state_dict_loads(tmp_path):
     ours.load_state_dict(sd, strict=True)
     for k, v in sd.items():
         assert torch.equal(getattr(ours, k).data, v) and getattr(ours, k).dtype == v.dtype
+
+
+def test_integration_doc_stub_matches_the_header():
+    """The ctypes stub INTEGRATION.md shows a maintainer declares LsShape / LsBevStrides with the
+    fields of include/ls_b200.h in order (a stale stub would hand the library a short struct), and
+    every entry point its table names is declared in the header."""
+    from e2e_parking_carla_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class LsShape(C.Structure)"):doc.index("class LsBevStrides(C.Structure)")]
+    ints = re.search(r'for n in \(([^)]*)\)', stub).group(1)
+    names = re.findall(r'"(\w+)"', ints) + re.findall(r'\("(\w+)", C\.c_', stub)
+    assert names == [f[0] for f in _lib.LsShape._fields_]
+    strides = doc[doc.index("class LsBevStrides(C.Structure)"):]
+    assert re.findall(r'"(\w+)"', re.search(r'for n in \(([^)]*)\)', strides).group(1)) == \
+        [f[0] for f in _lib.LsBevStrides._fields_]
+    table = doc[doc.index("## Entry points and the reference lines they replace"):doc.index("## Streams, graphs")]
+    declared = set(_declared_symbols())
+    named = set(re.findall(r"`(ls_[a-z0-9_]+)`", table))
+    assert named and named <= declared, named - declared
+    # the table covers the whole ABI except the introspection helpers
+    helpers = {"ls_version", "ls_strerror", "ls_last_cuda_error", "ls_launch_count", "ls_debug_phase_cycles",
+               "ls_grid_cells", "ls_padded_channels", "ls_sorted_records"}
+    assert declared - named <= helpers, declared - named - helpers
