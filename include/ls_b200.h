@@ -50,9 +50,10 @@ typedef struct LsShape {
   float res[3];        /* bev_res                                               */
   int32_t geom_policy; /* LsGeomPolicy: float32 evaluation order of M.(u*d, v*d, d) + t    */
   int32_t tile_x;      /* internal BEV tiling: tiles of 128 cells, tile_x x (128 / tile_x); 0 or 1 =
-                        * 1 x 128 strips (required for NCHW BEV tensors), 8 = 8 x 16 (what the
-                        * channels-last 64-channel splat wants); a power of two <= 128.  Use the
-                        * same value for every call of one forward/backward pair.            */
+                        * 1 x 128 strips (the default; required for NCHW BEV tensors), 8 = 8 x 16
+                        * (accepted by the channels-last 64-channel splat; same bits, measured slower
+                        * on a B200); a power of two <= 128.  Use the same value for every call of
+                        * one forward/backward pair.                                          */
   int32_t bev_dtype;   /* LsDtype of the BEV tensor and of the gradient arriving on it.  LS_F32 (0) is the
                         * reference's contract (model/bev_model.py:76: always float32).  LS_BF16 is an opt-in
                         * for autocast training (the consumer convolution runs in bf16 anyway): 128-byte
