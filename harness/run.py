@@ -8,6 +8,7 @@ import time
 
 import torch
 
+from .agent_target import prev_target_point
 from .parking_stack import Losses, ParkingStack, count_parameters, default_cfg, synthetic_batch
 
 
@@ -85,22 +86,25 @@ def train_benchmark(per_gpu_batch, steps, warmup, rank, world, device, lift_spla
 
 def agent_benchmark(iters, warmup, device, lift_splat="b200", use_graph=True):
     """Closed-loop agent step without the CARLA server (agent/parking_agent.py:379-391): model.predict
-    on one synthetic frame set (B=1, 4 cameras) + the next-target centroid of save_prev_target (:290-311)
-    computed on the device instead of a python 200x200 loop.  Per-iteration latency by CUDA events and by
+    on one synthetic frame set (B=1, 4 cameras) + the next-target point of save_prev_target (:290-318)
+    computed on the device (harness/agent_target.py) instead of a python 200x200 loop and fed back as the
+    next tick's target point.  Per-iteration latency by CUDA events and by
     wall clock (the reference's own time.time() bracket, which includes the final device->host read)."""
     cfg = default_cfg(device)
     torch.manual_seed(42)
     model = ParkingStack(cfg, lift_splat=lift_splat).to(device).eval()
     data = synthetic_batch(cfg, 1, device, seed=0)
     data["gt_control"] = data["gt_control"][:, :1]            # BOS only (agent/parking_agent.py:470)
-    xs = torch.arange(200, device=device, dtype=torch.float32)
+    x_res, y_res = cfg.bev_x_bound[2], cfg.bev_y_bound[2]
 
     def tick():
         tokens, seg, _, _ = model.predict(data)
-        slot = seg[0].argmax(dim=0) == 2                     # target-slot pixels
-        n = slot.sum().clamp_min(1).float()
-        centroid = torch.stack([(slot.float().sum(1) * xs).sum() / n, (slot.float().sum(0) * xs).sum() / n])
-        return tokens, centroid
+        # save_prev_target (:290-318) on the device, bit-equal to the reference's python loop
+        # (tests/test_agent_target.py); the next tick aims at it (:474-475), which closes the loop
+        # inside the captured graph: the copy below feeds the graph's own static input
+        target, _ = prev_target_point(seg, x_res, y_res, data["target_point"][0, :2])
+        data["target_point"][0, :2].copy_(target)
+        return tokens, target
 
     def measure(run_once):
         dev_ms, wall_ms = [], []
