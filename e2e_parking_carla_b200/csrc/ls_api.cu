@@ -95,6 +95,17 @@ struct LsFork {
   }
 };
 
+// Product of positive 32-bit factors, saturating at `cap` (<= 2^31): the 64-bit product of five
+// int32 sizes can wrap, and a wrapped product must not pass a limit test.
+static long long ls_prod_capped(const int* f, int n, long long cap) {
+  long long p = 1;
+  for (int i = 0; i < n; ++i) {
+    p *= f[i];                       // p < cap <= 2^31 and f[i] < 2^31: no overflow
+    if (p >= cap) return cap;
+  }
+  return p;
+}
+
 static int ls_check_shape(const LsShape* s) {
   if (!s) return LS_ERR_BAD_ARG;
   if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fh <= 0 || s->fw <= 0 || s->C <= 0) return LS_ERR_BAD_ARG;
@@ -102,8 +113,10 @@ static int ls_check_shape(const LsShape* s) {
   if (s->geom_policy != LS_GEOM_TORCH_CPU && s->geom_policy != LS_GEOM_TORCH_CUDA) return LS_ERR_BAD_ARG;
   if (s->tile_x < 0 || s->tile_x > LS_TILE || (s->tile_x & (s->tile_x - 1))) return LS_ERR_BAD_ARG;
   if (s->bev_dtype != LS_F32 && s->bev_dtype != LS_BF16) return LS_ERR_BAD_ARG;
-  if ((long long)s->X * s->Y * s->Z >= (1LL << 28)) return LS_ERR_UNSUPPORTED;
-  if ((long long)s->B * s->N * s->D * s->fh * s->fw >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
+  const int cells[3] = {s->X, s->Y, s->Z};
+  const int points[5] = {s->B, s->N, s->D, s->fh, s->fw};
+  if (ls_prod_capped(cells, 3, 1LL << 28) >= (1LL << 28)) return LS_ERR_UNSUPPORTED;
+  if (ls_prod_capped(points, 5, 1LL << 31) >= (1LL << 31)) return LS_ERR_UNSUPPORTED;
   return LS_OK;
 }
 static int ls_check_splat_shape(const LsShape* s) {

@@ -194,3 +194,46 @@ def test_integration_doc_stub_matches_the_header():
     helpers = {"ls_version", "ls_strerror", "ls_last_cuda_error", "ls_launch_count", "ls_debug_phase_cycles",
                "ls_grid_cells", "ls_padded_channels", "ls_sorted_records"}
     assert declared - named <= helpers, declared - named - helpers
+
+
+def test_size_functions_never_accept_a_wrapped_shape(lib):
+    """Seeded fuzz of the shape checker behind ls_scratch_bytes / ls_saved_bytes / ls_cache_bytes (all
+    host-only): whatever it accepts obeys the documented limits in exact integer arithmetic (a 64-bit
+    product of five int32 sizes can wrap; a wrapped product must not pass), the three sizes are
+    positive, far from wrapping, agree on acceptance and grow with the batch."""
+    import random
+    from e2e_parking_carla_b200 import lift_splat as ls
+    rnd = random.Random(7)
+    vals = [0, 1, 2, 3, 4, 7, 8, 16, 31, 32, 33, 48, 63, 64, 65, 96, 128, 191, 192, 200, 255, 256, 257, 400, 1000, 1024,
+            4096, 65535, 65536, 1 << 20, (1 << 31) - 1, -1, -5]
+    accepted = 0
+    for _ in range(30000):
+        B, X, Y = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
+        N, D, Cc = rnd.choice(vals[:20] + [-1]), rnd.choice(vals[:24]), rnd.choice(vals[:24])
+        fh, fw = rnd.choice(vals[:28] + [65535]), rnd.choice(vals[:28] + [65535])
+        Z, tx = rnd.choice([1, 1, 1, 0, 2]), rnd.choice([0, 1, 2, 4, 8, 16, 32, 64, 128, 3, 256, -1])
+        grid = ls.GridSpec((-9.95, -9.95, 0.0), (0.1, 0.1, 20.0), (X, Y, Z))
+        s = ls.make_shape(B, N, D, fh, fw, Cc, grid, 0, tx)
+        for code in (ls.LS_F32, ls.LS_BF16):
+            full = lib.ls_scratch_bytes(C.byref(s), code, 1)
+            fwd_only = lib.ls_scratch_bytes(C.byref(s), code, 0)
+            saved = lib.ls_saved_bytes(C.byref(s), code, ls.LS_FEAT_NCHW)
+            cache = lib.ls_cache_bytes(C.byref(s))
+            assert (full > 0) == (fwd_only > 0) == (saved > 0) == (cache > 0), (B, N, D, fh, fw, Cc, X, Y, Z, tx)
+            if not full:
+                continue
+            accepted += 1
+            assert min(B, N, D, fh, fw, Cc, X, Y) >= 1 and Z == 1
+            assert B * N * D * fh * fw < 1 << 31 and X * Y * Z < 1 << 28 and Cc <= 256 and D <= 191
+            assert N * fh * fw <= 1 << 20
+            assert fwd_only <= full < 1 << 60 and saved < 1 << 60 and cache < 1 << 60
+            if B > 1:
+                half = ls.make_shape(B // 2, N, D, fh, fw, Cc, grid, 0, tx)
+                assert 0 < lib.ls_scratch_bytes(C.byref(half), code, 1) <= full
+                assert 0 < lib.ls_saved_bytes(C.byref(half), code, ls.LS_FEAT_NCHW) <= saved
+    assert accepted > 1000
+    # the shapes that used to wrap: B * N * D * fh * fw = 2.4e21 and 2.5e22
+    for B, N, D, fh, fw, Cc, X, Y, tx in ((2147483647, 33, 8, 65535, 65535, 63, 256, 255, 32),
+                                          (2147483647, 96, 31, 65535, 65535, 191, 33, 1000, 32)):
+        s = ls.make_shape(B, N, D, fh, fw, Cc, ls.GridSpec((0.0, 0.0, 0.0), (0.1, 0.1, 20.0), (X, Y, 1)), 0, tx)
+        assert lib.ls_scratch_bytes(C.byref(s), ls.LS_F32, 1) == 0 and lib.ls_cache_bytes(C.byref(s)) == 0
