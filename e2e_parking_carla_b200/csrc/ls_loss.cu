@@ -147,8 +147,15 @@ static inline int ls_dl_blocks(int BN, int HW) { return ((HW + 31) / 32) * BN; }
 
 extern "C" {
 
+// Launch limits: grid.y = BN, fh * fw and the block count are 32-bit.
+static inline bool ls_dl_shape_ok(int BN, int fh, int fw) {
+  if (BN <= 0 || fh <= 0 || fw <= 0 || BN > 65535) return false;
+  const long long hw = (long long)fh * fw;
+  return hw < (1LL << 31) && ((hw + 31) / 32) * BN < (1LL << 31);
+}
+
 size_t ls_depth_loss_ws_bytes(int32_t BN, int32_t fh, int32_t fw) {
-  if (BN <= 0 || fh <= 0 || fw <= 0) return 0;
+  if (!ls_dl_shape_ok(BN, fh, fw)) return 0;
   return (size_t)ls_dl_blocks(BN, fh * fw) * 2 * sizeof(float);
 }
 
@@ -158,6 +165,7 @@ int ls_depth_loss_fwd(const void* prob, int dtype, const float* gt_depth, int32_
   if (!prob || !gt_depth || !labels || !ws || !out2) return LS_ERR_BAD_ARG;
   if (BN <= 0 || D <= 0 || fh <= 0 || fw <= 0 || down <= 0 || !(d_step > 0.0f)) return LS_ERR_BAD_ARG;
   if (dtype != LS_F32 && dtype != LS_BF16) return LS_ERR_BAD_ARG;
+  if (!ls_dl_shape_ok(BN, fh, fw)) return LS_ERR_UNSUPPORTED;
   if (ws_bytes < ls_depth_loss_ws_bytes(BN, fh, fw)) return LS_ERR_WORKSPACE;
   const int HW = fh * fw;
   dim3 grid((HW + 31) / 32, BN);
@@ -177,6 +185,7 @@ int ls_depth_loss_bwd(const void* prob, int dtype, const int32_t* labels, const 
   if (!prob || !labels || !fwd_out2 || !grad_prob) return LS_ERR_BAD_ARG;
   if (BN <= 0 || D <= 0 || fh <= 0 || fw <= 0) return LS_ERR_BAD_ARG;
   if (dtype != LS_F32 && dtype != LS_BF16) return LS_ERR_BAD_ARG;
+  if (!ls_dl_shape_ok(BN, fh, fw)) return LS_ERR_UNSUPPORTED;
   const int HW = fh * fw;
   dim3 grid((HW + 31) / 32, BN);
   cudaStream_t s = (cudaStream_t)stream;

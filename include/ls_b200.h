@@ -273,7 +273,8 @@ int ls_target_bev(const int32_t* target_pix, int32_t B, int32_t X, int32_t Y, fl
  * [B*N,H,W]).  d_off = float32(d_bound[0] - d_bound[2]), d_step = float32(d_bound[2]).
  * Outputs: labels i32[BN*fh*fw] (0 background, k >= 1: depth bin k-1 is the positive class;
  * kept for the backward), out2 f32[2] = {loss, 1 / max(1, #foreground pixels)}.
- * ws: >= ls_depth_loss_ws_bytes() of scratch (per-CTA partial sums; sums have a fixed order). */
+ * ws: >= ls_depth_loss_ws_bytes() of scratch (per-CTA partial sums; sums have a fixed order).
+ * Limits: BN <= 65535, fh*fw < 2^31, BN * ceil(fh*fw / 32) < 2^31 (LS_ERR_UNSUPPORTED; ws_bytes() = 0). */
 size_t ls_depth_loss_ws_bytes(int32_t BN, int32_t fh, int32_t fw);
 int ls_depth_loss_fwd(const void* prob, int dtype, const float* gt_depth, int32_t BN, int32_t D, int32_t fh,
                       int32_t fw, int32_t down, float d_off, float d_step, int32_t* labels, void* ws,

@@ -85,6 +85,12 @@ def test_abi_argument_checking(lib):
     assert lib.ls_depth_loss_fwd(dummy16, 0, dummy16, 4, 48, 32, 32, 8, 0.25, 0.25, dummy16, dummy16, 8, dummy16,
                                  None) == -3                       # workspace too small
     assert lib.ls_depth_loss_bwd(dummy16, 3, dummy16, dummy16, None, 4, 48, 32, 32, dummy16, None) == -1   # dtype
+    # launch limits (grid.y = B*N, 32-bit pixel and block counts) are reported, not wrapped
+    assert lib.ls_depth_loss_ws_bytes(65535, 32, 32) > 0 and lib.ls_depth_loss_ws_bytes(65536, 32, 32) == 0
+    assert lib.ls_depth_loss_ws_bytes(4, 65535, 65535) == 0 and lib.ls_depth_loss_ws_bytes(65535, 4096, 4096) == 0
+    assert lib.ls_depth_loss_fwd(dummy16, 0, dummy16, 70000, 48, 32, 32, 8, 0.25, 0.25, dummy16, dummy16, 1 << 40,
+                                 dummy16, None) == -2
+    assert lib.ls_depth_loss_bwd(dummy16, 0, dummy16, dummy16, None, 4, 48, 65535, 65535, dummy16, None) == -2
     assert lib.ls_target_bev(None, 2, 200, 200, None, 0, 0, 0, None) == -1
     assert lib.ls_index_geom(None, C.byref(s), None, None, None, None, None) == -1
     odd_policy = ls.make_shape(1, 4, 48, 32, 32, 64, grid, geom_policy=7)
