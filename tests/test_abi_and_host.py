@@ -243,3 +243,35 @@ def test_size_functions_never_accept_a_wrapped_shape(lib):
                                           (2147483647, 96, 31, 65535, 65535, 191, 33, 1000, 32)):
         s = ls.make_shape(B, N, D, fh, fw, Cc, ls.GridSpec((0.0, 0.0, 0.0), (0.1, 0.1, 20.0), (X, Y, 1)), 0, tx)
         assert lib.ls_scratch_bytes(C.byref(s), ls.LS_F32, 1) == 0 and lib.ls_cache_bytes(C.byref(s)) == 0
+
+
+def test_every_entry_point_survives_all_null_arguments(lib):
+    """Each of the header's entry points called with NULL / zero for every argument returns
+    LS_ERR_BAD_ARG (int status), 0 (a size) or a string - never a crash, never LS_OK - and a valid
+    shape with null buffers is refused the same way."""
+    from e2e_parking_carla_b200 import _lib
+    from e2e_parking_carla_b200 import lift_splat as ls
+    good = ls.make_shape(1, 4, 48, 32, 32, 64, ls.GridSpec((-9.95, -9.95, 0.0), (0.1, 0.1, 20.0), (200, 200, 1)))
+    for with_shape in (False, True):
+        for name, (res, args) in sorted(_lib.PROTOTYPES.items()):
+            vals = []
+            for a in args:
+                if a is _lib._SH and with_shape:
+                    vals.append(C.byref(good))
+                elif a in (C.c_float, C.c_double):
+                    vals.append(0.0)
+                elif a is C.c_void_p or getattr(a, "__name__", "").startswith("LP_"):
+                    vals.append(None)
+                else:
+                    vals.append(0)
+            out = getattr(lib, name)(*vals)
+            if res is C.c_int and name not in ("ls_padded_channels",):
+                if with_shape and name == "ls_grid_cells":
+                    assert out == 0                        # its three outputs are optional
+                else:
+                    assert out == -1, (name, out)
+            elif res is C.c_char_p:
+                assert isinstance(out, bytes)
+            elif not with_shape or _lib._SH not in args:
+                assert out == 0, (name, out)
+    assert lib.ls_launch_count() == 0                      # nothing was launched by any of it
