@@ -179,6 +179,51 @@ def test_live_reference_equals_port_and_oracle():
     assert relerr(bev_o, ref64["bev"]) < 5e-7
 
 
+_SWEEP = {
+    # name: (LiftSplatShape kwargs, cameras, jitter, rig seed)
+    "default_seed1": (dict(), 4, True, 1),
+    "default_seed2": (dict(), 4, True, 2),
+    "default_seed3": (dict(), 4, True, 3),
+    "carla_rig_exact": (dict(), 4, False, 0),                      # 16 384 points exactly on voxel boundaries
+    "stress_6cam": (dict(cams=6, bev_x_bound=[-10.0, 10.0, 0.05], bev_y_bound=[-10.0, 10.0, 0.05],
+                         d_bound=[0.5, 12.5, 0.125]), 6, True, 4),
+    "coarse_1m": (dict(bev_x_bound=[-10.0, 10.0, 1.0], bev_y_bound=[-10.0, 10.0, 1.0]), 4, True, 5),
+    "ragged_grid": (dict(bev_x_bound=[-7.0, 9.8, 0.3], bev_y_bound=[-12.0, 4.0, 0.125]), 4, True, 6),
+    "far_depths": (dict(d_bound=[2.0, 58.0, 1.0]), 4, True, 7),
+    "thin_z_slab": (dict(bev_z_bound=[-1.0, 1.0, 2.0]), 4, True, 8),  # most points fail the z test
+    "small_maps": (dict(final_dim=[128, 192], bev_down_sample=16), 4, True, 9),
+}
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present")
+@pytest.mark.parametrize("name", list(_SWEEP))
+def test_live_reference_index_sweep(name):
+    """Voxel indices, keep mask and sorted ranks of the numpy oracle against the unmodified reference's
+    own tensor ops on rigs, grids and depth ranges beyond the three frozen fixtures (indices only: the
+    bit-exact half of the bar, and what every GPU parity test at other sizes leans on)."""
+    kw, cams, jitter, seed = _SWEEP[name]
+    shape = LiftSplatShape(batch=2, channels=4, **kw)
+    assert shape.cams == cams
+    cfg = make_cfg(shape)
+    intr, extr = make_rig(2, cams, jitter=jitter, seed=seed)
+    geom, vox, keep, ranks = rh.reference_indices(cfg, intr, extr)
+    res, start, dim = grid_of(shape)
+    # grid parameters themselves: tool/geometry.py:40-59
+    model = rh.reference_bev_model(cfg)
+    assert np.array_equal(model.bev_res.numpy(), res) and np.array_equal(model.bev_start_pos.numpy(), start)
+    assert np.array_equal(model.bev_dim.numpy(), dim) and np.array_equal(model.frustum.numpy(), frustum_of(shape))
+    inv = torch.inverse(extr)
+    M = inv[..., :3, :3].matmul(torch.inverse(intr)).numpy()
+    geom_o = lo.geometry(M, inv[..., :3, 3].numpy(), frustum_of(shape))
+    assert np.array_equal(geom_o, geom.numpy())                       # torch-CPU's float32 evaluation order
+    vox_o, keep_o, rank_o = lo.voxel_index(geom_o, start, res, dim)
+    assert np.array_equal(vox_o, vox.numpy()) and np.array_equal(keep_o, keep.numpy())
+    for b in range(2):
+        kept = np.sort(rank_o[b][rank_o[b] >= 0])
+        assert np.array_equal(kept, ranks[b].numpy())
+    assert 0 < keep_o.sum() < keep_o.size or name == "thin_z_slab"
+
+
 # ------------------------------------------------------------------------------------
 # DepthLoss (loss/depth_loss.py:18-48): the consumer of pred_depth (SURVEY.md 8f#3)
 # ------------------------------------------------------------------------------------
