@@ -248,9 +248,13 @@ def test_depth_loss_oracle_vs_golden():
     assert np.abs(grad - z["grad32"]).max() <= 1e-6 * np.abs(z["grad32"]).max()
 
 
-def test_depth_loss_live_reference():
+@pytest.mark.parametrize("kw", [dict(), dict(d_bound=[0.5, 12.5, 0.125]), dict(d_bound=[2.0, 58.0, 1.0]),
+                                dict(final_dim=[128, 192], bev_down_sample=16), dict(cams=6)],
+                         ids=["default", "96_bins", "1m_bins", "ds16_ragged", "6_cams"])
+def test_depth_loss_live_reference(kw):
     """Against the live reference module when the tree is mounted (labels with exact-boundary
-    depths, all-zero blocks and out-of-range blocks)."""
+    depths, all-zero blocks and out-of-range blocks), for several bin widths, down-sampling factors
+    and camera counts."""
     import sys
     if not os.path.isfile("/root/reference/loss/depth_loss.py"):
         pytest.skip("reference tree not present")
@@ -258,14 +262,14 @@ def test_depth_loss_live_reference():
     from loss.depth_loss import DepthLoss as RefLoss
     from oracle import depth_loss_oracle as dlo
     from e2e_parking_carla_b200.synthetic import make_cfg, make_depth_labels
-    shape = LiftSplatShape(batch=2, channels=4)
+    shape = LiftSplatShape(batch=2, channels=4, **kw)
     _, logits = make_encoder_outputs(shape, seed=32)
     gt = make_depth_labels(shape, seed=32)
     prob = logits.softmax(dim=1).requires_grad_(True)
     ref = RefLoss(make_cfg(shape))
     loss_ref = ref(prob, gt)
     loss_ref.backward()
-    loss, grad, labels = dlo.depth_loss(prob.detach().numpy(), gt.numpy(), shape.d_bound, 8)
+    loss, grad, labels = dlo.depth_loss(prob.detach().numpy(), gt.numpy(), shape.d_bound, shape.bev_down_sample)
     onehot = ref.get_down_sampled_gt_depth(gt)
     lab_ref = torch.where(onehot.sum(1) > 0, onehot.argmax(1) + 1, torch.zeros(onehot.shape[0], dtype=torch.long))
     assert np.array_equal(labels, lab_ref.numpy())
