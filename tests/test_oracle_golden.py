@@ -154,12 +154,17 @@ def test_torch_port_matches_golden(name):
 
 
 @pytest.mark.skipif(not rh.available(), reason="reference tree not present")
-def test_live_reference_equals_port_and_oracle():
+@pytest.mark.parametrize("kw", [dict(channels=6), dict(channels=2, bev_x_bound=[-10.0, 10.0, 1.0], bev_y_bound=[-10.0, 10.0, 1.0]),
+                                dict(channels=2, cams=6, d_bound=[0.5, 12.5, 0.125]),
+                                dict(channels=3, final_dim=[128, 192], bev_down_sample=16,
+                                     bev_x_bound=[-7.0, 9.8, 0.3], bev_y_bound=[-12.0, 4.0, 0.125])],
+                         ids=["default_c6", "1m_voxels_long_segments", "6_cams_96_bins", "ragged_everything"])
+def test_live_reference_equals_port_and_oracle(kw):
     """With /root/reference mounted: the unmodified reference, the torch port and the numpy
     oracle agree (bit-exact ranks and fp32 outputs for the port; fp64-level for the oracle)."""
-    shape = LiftSplatShape(batch=2, channels=6)
+    shape = LiftSplatShape(batch=2, **kw)
     cfg = make_cfg(shape)
-    intr, extr = make_rig(2, 4, jitter=True, seed=77)
+    intr, extr = make_rig(2, shape.cams, jitter=True, seed=77)
     feat, logits = make_encoder_outputs(shape, seed=70)
     gb, gp = make_upstream_grads(shape, seed=70)
     ref32 = rh.run_reference(cfg, feat, logits, intr, extr, double=False, backward_with=(gb, gp))
